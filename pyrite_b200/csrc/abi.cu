@@ -1,0 +1,528 @@
+// C ABI of the B200 render path (include/pyrite_b200.h): context management, scene upload, the
+// wavefront driver loop and the film / trace / camera seams.  No CPU fallback exists: every entry
+// point that computes launches kernels on the context's CUDA device.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <exception>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/pyrite_b200.h"
+#include "kernels.hpp"
+#include "scene_build.hpp"
+
+namespace {
+
+using namespace pyr;
+
+struct CudaError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) throw CudaError(std::string(#call) + ": " + cudaGetErrorString(e_));   \
+    } while (0)
+
+std::string g_init_error;
+struct StateError : std::runtime_error { using std::runtime_error::runtime_error; };
+
+struct DeviceBuffer {
+    void* p = nullptr;
+    size_t bytes = 0;
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    void ensure(size_t n) {
+        if (n <= bytes && p) return;
+        release();
+        if (n == 0) n = 16;
+        CU(cudaMalloc(&p, n));
+        bytes = n;
+    }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+template <class T> void upload(DeviceBuffer& b, const std::vector<T>& v, cudaStream_t s) {
+    b.ensure(v.size() * sizeof(T));
+    if (!v.empty()) CU(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+}
+
+}  // namespace
+
+struct pyr_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    std::string error;
+    bool loaded = false;
+    BakedScene scene;
+    SceneView view{};
+    DeviceBuffer nodes, prims, tri_shade, tri_frames, planes, marched, materials, components, programs, code, spectra, spectrum_data,
+        textures, texels, lamps, tiles, burns, xyz, d65;
+    DeviceBuffer film, develop_params, counters, scalars, tile_first;
+    DeviceBuffer paths, rays[2], hits, light_vertices;
+    DeviceBuffer scratch_a, scratch_b;
+    uint32_t pool = 0;
+    bool develop_params_valid = false;
+    pyr_counters host_counters{};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    unsigned long long* pinned = nullptr;  // [0] ray count, [1] next sample
+
+    size_t film_floats() const { return (size_t)view.film.width * view.film.height * view.film.bins * 2; }
+    // scalars: [0] count A, [1] count B, [2] trace cursor, [4..5] next_sample (u64)
+    uint32_t* count(int i) const { return scalars.as<uint32_t>() + i; }
+    uint32_t* cursor() const { return scalars.as<uint32_t>() + 2; }
+    unsigned long long* next_sample() const { return (unsigned long long*)(scalars.as<uint32_t>() + 4); }
+};
+
+namespace {
+
+pyr_status fail(pyr_ctx* ctx, pyr_status code, const std::string& msg) {
+    if (ctx) ctx->error = msg; else g_init_error = msg;
+    return code;
+}
+
+template <class F> pyr_status guarded(pyr_ctx* ctx, F&& body) {
+    if (!ctx) return fail(nullptr, PYR_ERR_INVALID, "null context");
+    try {
+        CU(cudaSetDevice(ctx->device));
+        body();
+        return PYR_OK;
+    } catch (const CudaError& e) {
+        return fail(ctx, PYR_ERR_CUDA, e.what());
+    } catch (const StateError& e) {
+        return fail(ctx, PYR_ERR_STATE, e.what());
+    } catch (const ir::BuildError& e) {
+        return fail(ctx, PYR_ERR_INVALID, e.what());
+    } catch (const std::bad_alloc&) {
+        return fail(ctx, PYR_ERR_INVALID, "out of host memory");
+    } catch (const std::exception& e) {
+        return fail(ctx, PYR_ERR_INVALID, e.what());
+    }
+}
+
+void need_project(pyr_ctx* ctx) {
+    if (!ctx->loaded) throw StateError("no project is loaded");
+}
+
+void ensure_develop_params(pyr_ctx* ctx) {
+    if (ctx->develop_params_valid) return;
+    ctx->develop_params.ensure(4 * sizeof(float));
+    launch_white_scan(ctx->view, ctx->develop_params.as<float>(), ctx->stream);
+    CU(cudaGetLastError());
+    ctx->develop_params_valid = true;
+}
+
+void ensure_pool(pyr_ctx* ctx, uint32_t pool) {
+    if (pool == ctx->pool && ctx->paths.p) return;
+    const uint32_t per_path = 1 + std::max<uint32_t>(ctx->view.renderer.light_samples, 1);
+    const bool bidir = ctx->view.renderer.algorithm == 1;
+    const size_t ray_cap = (size_t)pool * (bidir ? std::max<uint32_t>(per_path, MAX_LIGHT_PATH + 1) : per_path);
+    ctx->paths.ensure((size_t)pool * path_state_bytes());
+    ctx->rays[0].ensure(ray_cap * sizeof(Ray));
+    ctx->rays[1].ensure(ray_cap * sizeof(Ray));
+    ctx->hits.ensure(ray_cap * sizeof(Hit));
+    if (bidir) ctx->light_vertices.ensure((size_t)pool * MAX_LIGHT_PATH * light_vertex_bytes());
+    ctx->pool = pool;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* pyr_version(void) {
+    static std::string text;
+    text = "pyrite_b200 0.1; sm_100a";
+    int dev = 0;
+    cudaDeviceProp prop;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess)
+        text += std::string("; ") + prop.name + "; " + std::to_string(prop.multiProcessorCount) + " SMs";
+    else
+        text += "; no CUDA device";
+    return text.c_str();
+}
+
+const char* pyr_last_error(const pyr_ctx* ctx) { return ctx ? ctx->error.c_str() : g_init_error.c_str(); }
+
+pyr_status pyr_init(int32_t device, pyr_ctx** out) {
+    if (!out) return fail(nullptr, PYR_ERR_INVALID, "null output pointer");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, PYR_ERR_CUDA, std::string("no usable CUDA device (there is no CPU path): ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    if (device < 0 || device >= count) return fail(nullptr, PYR_ERR_INVALID, "device index out of range");
+    std::unique_ptr<pyr_ctx> ctx(new pyr_ctx);
+    ctx->device = device;
+    try {
+        CU(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, device));
+        ctx->sm_count = prop.multiProcessorCount;
+        CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        CU(cudaEventCreate(&ctx->ev0));
+        CU(cudaEventCreate(&ctx->ev1));
+        CU(cudaMallocHost((void**)&ctx->pinned, 4 * sizeof(unsigned long long)));
+        ctx->counters.ensure(sizeof(DeviceCounters));
+        CU(cudaMemsetAsync(ctx->counters.p, 0, sizeof(DeviceCounters), ctx->stream));
+        ctx->scalars.ensure(16 * sizeof(uint32_t));
+        CU(cudaMemsetAsync(ctx->scalars.p, 0, 16 * sizeof(uint32_t), ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    } catch (const std::exception& ex) {
+        return fail(nullptr, PYR_ERR_CUDA, ex.what());
+    }
+    *out = ctx.release();
+    return PYR_OK;
+}
+
+void pyr_shutdown(pyr_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    DeviceBuffer* all[] = {&ctx->nodes, &ctx->prims, &ctx->tri_shade, &ctx->tri_frames, &ctx->planes, &ctx->marched, &ctx->materials,
+                           &ctx->components, &ctx->programs, &ctx->code, &ctx->spectra, &ctx->spectrum_data, &ctx->textures, &ctx->texels,
+                           &ctx->lamps, &ctx->tiles, &ctx->burns, &ctx->xyz, &ctx->d65, &ctx->film, &ctx->develop_params, &ctx->counters,
+                           &ctx->scalars, &ctx->tile_first, &ctx->paths, &ctx->rays[0], &ctx->rays[1], &ctx->hits, &ctx->light_vertices,
+                           &ctx->scratch_a, &ctx->scratch_b};
+    for (DeviceBuffer* b : all) b->release();
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+pyr_status pyr_project_load(pyr_ctx* ctx, const void* ir_blob, size_t bytes) {
+    return guarded(ctx, [&] {
+        if (!ir_blob) throw ir::BuildError("null project IR");
+        ir::Document doc = ir::decode(ir_blob, bytes);
+        BakedScene baked = build_scene(doc);
+        cudaStream_t s = ctx->stream;
+        upload(ctx->nodes, baked.nodes, s);
+        upload(ctx->prims, baked.prims, s);
+        upload(ctx->tri_shade, baked.tri_shade, s);
+        upload(ctx->tri_frames, baked.tri_frames, s);
+        upload(ctx->planes, baked.planes, s);
+        upload(ctx->marched, baked.marched, s);
+        upload(ctx->materials, baked.materials, s);
+        upload(ctx->components, baked.components, s);
+        upload(ctx->programs, baked.programs, s);
+        upload(ctx->code, baked.code, s);
+        upload(ctx->spectra, baked.spectra, s);
+        upload(ctx->spectrum_data, baked.spectrum_data, s);
+        upload(ctx->textures, baked.textures, s);
+        upload(ctx->texels, baked.texels, s);
+        upload(ctx->lamps, baked.lamps, s);
+        upload(ctx->tiles, baked.tiles, s);
+        upload(ctx->burns, baked.burns, s);
+        upload(ctx->xyz, baked.xyz, s);
+        upload(ctx->d65, baked.d65, s);
+        SceneView v = baked.view;
+        v.nodes = ctx->nodes.as<Node>(); v.prims = ctx->prims.as<Prim>(); v.tri_shade = ctx->tri_shade.as<TriShade>();
+        v.tri_frames = ctx->tri_frames.as<TriFrames>(); v.planes = ctx->planes.as<PlaneRec>(); v.marched = ctx->marched.as<MarchedRec>();
+        v.materials = ctx->materials.as<MaterialRec>(); v.components = ctx->components.as<ComponentRec>();
+        v.programs = ctx->programs.as<ProgramRec>(); v.code = ctx->code.as<Instr>(); v.spectra = ctx->spectra.as<SpectrumRec>();
+        v.spectrum_data = ctx->spectrum_data.as<float>(); v.textures = ctx->textures.as<TextureRec>(); v.texels = ctx->texels.as<float>();
+        v.lamps = ctx->lamps.as<LampRec>(); v.tiles = ctx->tiles.as<TileRec>(); v.burns = ctx->burns.as<float>();
+        v.xyz = ctx->xyz.as<float>(); v.d65 = ctx->d65.as<float>();
+        ctx->view = v;
+        ctx->scene = std::move(baked);
+        ctx->film.ensure(ctx->film_floats() * sizeof(float));
+        CU(cudaMemsetAsync(ctx->film.p, 0, ctx->film_floats() * sizeof(float), s));
+        ctx->develop_params_valid = false;
+        ctx->pool = 0;
+        CU(cudaStreamSynchronize(s));
+        ctx->loaded = true;
+    });
+}
+
+pyr_status pyr_project_info_get(const pyr_ctx* ctx, pyr_project_info* out) {
+    if (!ctx || !out) return PYR_ERR_INVALID;
+    if (!ctx->loaded) return PYR_ERR_STATE;
+    const RendererRec& r = ctx->view.renderer;
+    *out = pyr_project_info{r.width, r.height, r.spectrum_bins, r.algorithm, r.pixel_samples, r.bounces, r.light_samples, r.spectrum_samples,
+                            r.light_bounces, r.tile_size, ctx->scene.n_objects, ctx->view.n_planes, ctx->view.n_lamps,
+                            ctx->scene.n_objects ? 2 * ctx->scene.n_objects - 1 : 0, (uint32_t)ctx->scene.materials.size(), ctx->view.n_marched};
+    return PYR_OK;
+}
+
+pyr_status pyr_trace_device(pyr_ctx* ctx, const void* d_rays, size_t n, void* d_hits, uint32_t repeat) {
+    return guarded(ctx, [&] {
+        need_project(ctx);
+        if (n > 0xFFFFFFF0ull) throw ir::BuildError("ray batch too large");
+        if (n == 0) return;
+        if (!d_rays || !d_hits) throw ir::BuildError("null ray or hit buffer");
+        const int blocks = ctx->sm_count * trace_blocks_per_sm();
+        CU(cudaEventRecord(ctx->ev0, ctx->stream));
+        for (uint32_t r = 0; r < (repeat ? repeat : 1u); ++r) {
+            CU(cudaMemsetAsync(ctx->cursor(), 0, sizeof(uint32_t), ctx->stream));
+            launch_trace_batch(ctx->view, d_rays, n, d_hits, ctx->cursor(), ctx->counters.as<DeviceCounters>(), 0, blocks, ctx->stream);
+            CU(cudaGetLastError());
+            ctx->host_counters.kernel_launches += 1;
+        }
+        CU(cudaEventRecord(ctx->ev1, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        ctx->host_counters.render_seconds = ms * 1e-3;
+    });
+}
+
+pyr_status pyr_trace_stats(pyr_ctx* ctx, const pyr_ray* rays, size_t n, pyr_hit* hits_out) {
+    return guarded(ctx, [&] {
+        need_project(ctx);
+        if (n == 0) return;
+        if (!rays || !hits_out) throw ir::BuildError("null ray or hit buffer");
+        ctx->scratch_a.ensure(n * sizeof(pyr_ray));
+        ctx->scratch_b.ensure(n * sizeof(pyr_hit));
+        CU(cudaMemcpyAsync(ctx->scratch_a.p, rays, n * sizeof(pyr_ray), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemsetAsync(ctx->cursor(), 0, sizeof(uint32_t), ctx->stream));
+        launch_trace_batch(ctx->view, ctx->scratch_a.p, n, ctx->scratch_b.p, ctx->cursor(), ctx->counters.as<DeviceCounters>(), 1,
+                           ctx->sm_count * trace_blocks_per_sm(), ctx->stream);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(hits_out, ctx->scratch_b.p, n * sizeof(pyr_hit), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        ctx->host_counters.kernel_launches += 1;
+    });
+}
+
+pyr_status pyr_trace(pyr_ctx* ctx, const pyr_ray* rays, size_t n, pyr_hit* hits_out) {
+    return guarded(ctx, [&] {
+        need_project(ctx);
+        if (n == 0) return;
+        if (!rays || !hits_out) throw ir::BuildError("null ray or hit buffer");
+        if (n > 0xFFFFFFF0ull) throw ir::BuildError("ray batch too large");
+        ctx->scratch_a.ensure(n * sizeof(pyr_ray));
+        ctx->scratch_b.ensure(n * sizeof(pyr_hit));
+        CU(cudaMemcpyAsync(ctx->scratch_a.p, rays, n * sizeof(pyr_ray), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemsetAsync(ctx->cursor(), 0, sizeof(uint32_t), ctx->stream));
+        launch_trace_batch(ctx->view, ctx->scratch_a.p, n, ctx->scratch_b.p, ctx->cursor(), ctx->counters.as<DeviceCounters>(), 0,
+                           ctx->sm_count * trace_blocks_per_sm(), ctx->stream);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(hits_out, ctx->scratch_b.p, n * sizeof(pyr_hit), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        ctx->host_counters.kernel_launches += 1;
+    });
+}
+
+pyr_status pyr_render(pyr_ctx* ctx, const pyr_render_params* params, pyr_progress_cb cb, void* user) {
+    return guarded(ctx, [&] {
+        need_project(ctx);
+        pyr_render_params p{};
+        if (params) p = *params;
+        const RendererRec& R = ctx->view.renderer;
+        const uint32_t spp = p.spp_override ? p.spp_override : R.pixel_samples;
+        const uint32_t stride = p.sample_stride ? p.sample_stride : 1u;
+        const uint32_t offset = p.sample_offset;
+        if (R.algorithm == 0 && R.light_samples > 0 && ctx->view.n_lamps == 0)
+            throw ir::BuildError("the scene has no lamps: World::pick_lamp would panic (world.rs:303); set light_samples = 0");
+        if (R.algorithm == 1 && ctx->view.n_lamps == 0) throw ir::BuildError("the bidirectional renderer needs at least one lamp (world.rs:303)");
+        cudaStream_t s = ctx->stream;
+
+        // per-tile sample counts for this shard: i = offset, offset + stride, ... < area * spp
+        std::vector<unsigned long long> first(ctx->scene.tiles.size() + 1, 0);
+        for (size_t t = 0; t < ctx->scene.tiles.size(); ++t) {
+            unsigned long long iterations = (unsigned long long)ctx->scene.tiles[t].width * ctx->scene.tiles[t].height * spp;
+            unsigned long long mine = offset < iterations ? (iterations - offset + stride - 1) / stride : 0;
+            first[t + 1] = first[t] + mine;
+        }
+        const unsigned long long total = first.back();
+        upload(ctx->tile_first, first, s);
+
+        uint32_t pool = p.pool_paths ? p.pool_paths : (1u << 20);
+        if ((unsigned long long)pool > total) pool = (uint32_t)std::max<unsigned long long>(total, 1);
+        pool = (pool + 127u) & ~127u;
+        ensure_pool(ctx, pool);
+        if (p.reset_film) CU(cudaMemsetAsync(ctx->film.p, 0, ctx->film_floats() * sizeof(float), s));
+        CU(cudaMemsetAsync(ctx->scalars.p, 0, 16 * sizeof(uint32_t), s));
+        launch_pool_reset(ctx->paths.as<PathState>(), pool, s);
+
+        const int trace_blocks = ctx->sm_count * trace_blocks_per_sm();
+        const int stats = (p.flags & PYR_RENDER_STATS) ? 1 : 0;
+        CU(cudaEventRecord(ctx->ev0, s));
+        int cur = 0;
+        unsigned long long iterations = 0, launches = 1;
+        bool cancelled = false;
+        const int BATCH = 4;
+        for (;;) {
+            for (int b = 0; b < BATCH; ++b) {
+                const int nxt = cur ^ 1;
+                CU(cudaMemsetAsync(ctx->count(nxt), 0, sizeof(uint32_t), s));
+                WaveArgs a{};
+                a.paths = ctx->paths.as<PathState>();
+                a.pool = pool;
+                a.rays_in = ctx->rays[cur].as<Ray>();
+                a.hits_in = ctx->hits.as<Hit>();
+                a.rays_out = ctx->rays[nxt].as<Ray>();
+                a.count_out = ctx->count(nxt);
+                a.trace_cursor = ctx->cursor();
+                a.next_sample = ctx->next_sample();
+                a.total_samples = total;
+                a.tile_first = ctx->tile_first.as<unsigned long long>();
+                a.seed = p.seed;
+                a.sample_offset = offset;
+                a.sample_stride = stride;
+                a.film = ctx->film.as<float>();
+                a.counters = ctx->counters.as<DeviceCounters>();
+                a.light_vertices = ctx->light_vertices.as<LightVertex>();
+                a.ray_capacity = (uint32_t)(ctx->rays[0].bytes / sizeof(Ray));
+                if (R.algorithm == 0) launch_wave_simple(ctx->view, a, s); else launch_wave_bidirectional(ctx->view, a, s);
+                TraceArgs t{};
+                t.rays = ctx->rays[nxt].as<Ray>();
+                t.hits = ctx->hits.as<Hit>();
+                t.count = ctx->count(nxt);
+                t.cursor = ctx->cursor();
+                t.counters = ctx->counters.as<DeviceCounters>();
+                t.stats = stats;
+                launch_trace(ctx->view, t, trace_blocks, s);
+                cur = nxt;
+                ++iterations;
+                launches += 2;
+            }
+            CU(cudaGetLastError());
+            CU(cudaMemcpyAsync(&ctx->pinned[0], ctx->count(cur), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            CU(cudaMemcpyAsync(&ctx->pinned[1], ctx->next_sample(), sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+            CU(cudaStreamSynchronize(s));
+            const uint32_t pending = (uint32_t)ctx->pinned[0];
+            const unsigned long long started = std::min<unsigned long long>(ctx->pinned[1], total);
+            if (pending == 0 && started >= total) break;
+            if (cb) {
+                uint8_t progress = total ? (uint8_t)((started * 100ull) / total) : 100;
+                if (cb(progress, "rendering", user)) { cancelled = true; break; }
+            }
+        }
+        CU(cudaEventRecord(ctx->ev1, s));
+        CU(cudaStreamSynchronize(s));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        ctx->host_counters.render_seconds = ms * 1e-3;
+        ctx->host_counters.wavefront_iterations += iterations;
+        ctx->host_counters.kernel_launches += launches;
+        ctx->host_counters.path_samples += cancelled ? std::min<unsigned long long>(ctx->pinned[1], total) : total;
+        if (cb && !cancelled) cb(100, "done", user);
+        if (cancelled) throw StateError("render cancelled by the progress callback");
+    });
+}
+
+pyr_status pyr_film_expose(pyr_ctx* ctx, const float* positions, const float* samples, size_t n) {
+    return guarded(ctx, [&] {
+        need_project(ctx);
+        if (n == 0) return;
+        if (!positions || !samples) throw ir::BuildError("null sample buffers");
+        ctx->scratch_a.ensure(n * 2 * sizeof(float));
+        ctx->scratch_b.ensure(n * 3 * sizeof(float));
+        CU(cudaMemcpyAsync(ctx->scratch_a.p, positions, n * 2 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->scratch_b.p, samples, n * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        launch_film_expose(ctx->view, ctx->film.as<float>(), ctx->scratch_a.as<float>(), ctx->scratch_b.as<float>(), n, ctx->stream);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(ctx->stream));
+        ctx->host_counters.kernel_launches += 1;
+    });
+}
+
+pyr_status pyr_film_clear(pyr_ctx* ctx) {
+    return guarded(ctx, [&] {
+        need_project(ctx);
+        CU(cudaMemsetAsync(ctx->film.p, 0, ctx->film_floats() * sizeof(float), ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+pyr_status pyr_film_download(pyr_ctx* ctx, float* out) {
+    return guarded(ctx, [&] {
+        need_project(ctx);
+        if (!out) throw ir::BuildError("null film buffer");
+        CU(cudaMemcpyAsync(out, ctx->film.p, ctx->film_floats() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+pyr_status pyr_film_upload(pyr_ctx* ctx, const float* in) {
+    return guarded(ctx, [&] {
+        need_project(ctx);
+        if (!in) throw ir::BuildError("null film buffer");
+        CU(cudaMemcpyAsync(ctx->film.p, in, ctx->film_floats() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+pyr_status pyr_film_device_ptr(pyr_ctx* ctx, void** d_ptr, size_t* bytes) {
+    return guarded(ctx, [&] {
+        need_project(ctx);
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (d_ptr) *d_ptr = ctx->film.p;
+        if (bytes) *bytes = ctx->film_floats() * sizeof(float);
+    });
+}
+
+pyr_status pyr_film_develop(pyr_ctx* ctx, float step_size, float* xyz_out, uint8_t* srgb_out) {
+    return guarded(ctx, [&] {
+        need_project(ctx);
+        if (!(step_size > 0.0f)) throw ir::BuildError("step_size must be positive");
+        const size_t pixels = (size_t)ctx->view.film.width * ctx->view.film.height;
+        ensure_develop_params(ctx);
+        ctx->scratch_a.ensure(pixels * 3 * sizeof(float));
+        ctx->scratch_b.ensure(pixels * 3);
+        launch_develop(ctx->view, ctx->film.as<float>(), ctx->develop_params.as<float>(), step_size, ctx->scratch_a.as<float>(),
+                       ctx->scratch_b.as<uint8_t>(), ctx->stream);
+        CU(cudaGetLastError());
+        if (xyz_out) CU(cudaMemcpyAsync(xyz_out, ctx->scratch_a.p, pixels * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        if (srgb_out) CU(cudaMemcpyAsync(srgb_out, ctx->scratch_b.p, pixels * 3, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        ctx->host_counters.kernel_launches += 1;
+    });
+}
+
+pyr_status pyr_camera_sample(pyr_ctx* ctx, uint64_t seed, uint32_t tile, uint64_t sample, float* position_out, pyr_ray* ray_out,
+                             float* wavelengths_out, uint32_t* hero_out) {
+    return guarded(ctx, [&] {
+        need_project(ctx);
+        if (tile >= ctx->view.n_tiles) throw ir::BuildError("tile index out of range");
+        const size_t floats = 2 + 8 + MAX_SPECTRUM_SAMPLES + 1;
+        ctx->scratch_a.ensure(floats * sizeof(float));
+        launch_camera_sample(ctx->view, seed, tile, sample, ctx->scratch_a.as<float>(), ctx->stream);
+        CU(cudaGetLastError());
+        float host[2 + 8 + MAX_SPECTRUM_SAMPLES + 1];
+        CU(cudaMemcpyAsync(host, ctx->scratch_a.p, sizeof(host), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (position_out) { position_out[0] = host[0]; position_out[1] = host[1]; }
+        if (ray_out) memcpy(ray_out, host + 2, sizeof(pyr_ray));
+        if (wavelengths_out) for (uint32_t k = 0; k < ctx->view.renderer.spectrum_samples; ++k) wavelengths_out[k] = host[10 + k];
+        if (hero_out) memcpy(hero_out, host + 10 + MAX_SPECTRUM_SAMPLES, sizeof(uint32_t));
+    });
+}
+
+pyr_status pyr_counters_get(pyr_ctx* ctx, pyr_counters* out, int32_t reset) {
+    return guarded(ctx, [&] {
+        DeviceCounters dc;
+        CU(cudaMemcpyAsync(&dc, ctx->counters.p, sizeof(dc), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (out) {
+            *out = ctx->host_counters;
+            out->rays = dc.rays;
+            out->nodes_visited = dc.nodes_visited;
+            out->leaves_tested = dc.leaves_tested;
+            out->de_evals = dc.de_evals;
+            out->de_iterations = dc.de_iterations;
+        }
+        if (reset) {
+            CU(cudaMemsetAsync(ctx->counters.p, 0, sizeof(DeviceCounters), ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            double secs = ctx->host_counters.render_seconds;
+            ctx->host_counters = pyr_counters{};
+            ctx->host_counters.render_seconds = secs;
+        }
+    });
+}
+
+// BVH leaf pre-order: object id of every rank (test hook for the tie rule of World::intersect)
+pyr_status pyr_bvh_leaf_order(pyr_ctx* ctx, uint32_t* object_ids_out) {
+    return guarded(ctx, [&] {
+        need_project(ctx);
+        for (uint32_t obj = 0; obj < ctx->scene.n_objects; ++obj) object_ids_out[ctx->scene.rank_of_object[obj]] = obj;
+    });
+}
+
+}  // extern "C"

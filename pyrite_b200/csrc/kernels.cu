@@ -1,0 +1,310 @@
+// sm_100a kernels of the wavefront render path.  Compiled with -fmad=false: the reference never
+// contracts a*b+c and hit/primitive IDs must come out bit-exact.
+//
+//   k_wave_simple   stage 1 + 4 + 5 + 6: regenerate finished path slots (camera ray, wavelengths),
+//                   shade the closest hits of the previous trace pass (surface data, expression VM,
+//                   BSDF scatter, next-event estimation, the `contribute` fold), expose finished
+//                   samples on the film, and append the next rays to the ray queue with a
+//                   warp-level prefix sum + one atomic per warp
+//   k_trace         stage 2 + 3: World::intersect for every queued ray (planes, BVH walk, triangle /
+//                   sphere tests, sphere tracing); persistent warps pull 32-ray packets
+//   k_develop       stage 6 tail: spectral film -> CIE XYZ -> sRGB
+#include <cuda_runtime.h>
+
+#include "kernels.hpp"
+#include "shading.cuh"
+#include "bdpt.cuh"
+
+namespace pyr {
+
+namespace {
+
+constexpr int WAVE_THREADS = 128;
+constexpr int TRACE_THREADS = 128;
+constexpr unsigned FULL = 0xffffffffu;
+
+struct FilmAdd {
+    float* film;
+    __device__ __forceinline__ void operator()(uint64_t index, float increment, float weight) const {
+        atomicAdd(reinterpret_cast<float2*>(film) + index, make_float2(increment, weight));
+    }
+};
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+
+// exclusive prefix sum of `n` over the warp; returns the warp total in `total`
+__device__ __forceinline__ uint32_t warp_exclusive_scan(uint32_t n, uint32_t& total) {
+    uint32_t inc = n;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(FULL, inc, d);
+        if (lane_id() >= (uint32_t)d) inc += t;
+    }
+    total = __shfl_sync(FULL, inc, 31);
+    return inc - n;
+}
+
+// Reserve `n` consecutive queue entries for this thread: one atomicAdd per warp.
+__device__ __forceinline__ uint32_t queue_reserve(uint32_t* counter, uint32_t n) {
+    uint32_t total;
+    uint32_t offset = warp_exclusive_scan(n, total);
+    uint32_t base = 0;
+    if (lane_id() == 31 && total) base = atomicAdd(counter, total);
+    base = __shfl_sync(FULL, base, 31);
+    return base + offset;
+}
+
+// Hand out global path-sample indices to the lanes that want one.
+__device__ __forceinline__ bool claim_sample(unsigned long long* next, unsigned long long total, bool want, unsigned long long& index) {
+    unsigned mask = __ballot_sync(FULL, want);
+    if (!mask) return false;
+    unsigned long long base = 0;
+    int leader = __ffs(mask) - 1;
+    if ((int)lane_id() == leader) base = atomicAdd(next, (unsigned long long)__popc(mask));
+    base = __shfl_sync(FULL, base, leader);
+    if (!want) return false;
+    index = base + __popc(mask & ((1u << lane_id()) - 1u));
+    return index < total;
+}
+
+// global sample index -> (tile, per-tile sample number); tile_first has n_tiles + 1 entries
+__device__ __forceinline__ void locate_sample(const unsigned long long* tile_first, uint32_t n_tiles, unsigned long long g, uint32_t& tile,
+                                              unsigned long long& k) {
+    uint32_t lo = 0, hi = n_tiles;  // tile_first[lo] <= g < tile_first[hi]
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (tile_first[mid] <= g) lo = mid; else hi = mid;
+    }
+    tile = lo;
+    k = g - tile_first[lo];
+}
+
+__device__ __forceinline__ void store_ray(Ray* dst, const Ray& r) {
+    float4* d = reinterpret_cast<float4*>(dst);
+    d[0] = make_float4(r.o[0], r.o[1], r.o[2], __uint_as_float(r.mode));
+    d[1] = make_float4(r.d[0], r.d[1], r.d[2], r.limit);
+}
+__device__ __forceinline__ Ray load_ray(const Ray* src) {
+    const float4* s = reinterpret_cast<const float4*>(src);
+    float4 a = s[0], b = s[1];
+    Ray r;
+    r.o[0] = a.x; r.o[1] = a.y; r.o[2] = a.z; r.mode = __float_as_uint(a.w);
+    r.d[0] = b.x; r.d[1] = b.y; r.d[2] = b.z; r.limit = b.w;
+    return r;
+}
+
+__global__ void k_pool_reset(PathState* paths, uint32_t pool) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < pool) paths[i].flags = 0;
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(WAVE_THREADS) k_wave_simple(const SceneView sc, const WaveArgs a) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = slot < a.pool;
+    if (slot == 0) *a.trace_cursor = 0;
+    PathState& ps = a.paths[valid ? slot : 0];
+    FilmAdd add{a.film};
+    ShadeOut out;
+    out.alive = 0; out.has_main = 0; out.n_shadow = 0;
+    PathCounters pc;
+    pc.de_evals = 0; pc.de_iters = 0;
+
+    bool alive = valid && (ps.flags & PS_ALIVE);
+    if (alive) {
+        shade_simple(sc, ps, a.rays_in + ps.ray_base, a.hits_in + ps.ray_base, out, add, pc);
+        alive = out.alive != 0;
+        if (!alive) ps.flags = 0;
+    }
+    unsigned long long g = 0;
+    if (claim_sample(a.next_sample, a.total_samples, valid && !alive, g)) {
+        uint32_t tile; unsigned long long k;
+        locate_sample(a.tile_first, sc.n_tiles, g, tile, k);
+        generate_simple(sc, a.seed, tile, (uint64_t)a.sample_offset + k * a.sample_stride, ps, out.main);
+        ps.flags |= PS_ALIVE;
+        out.has_main = 1; out.n_shadow = 0; out.alive = 1;
+        alive = true;
+    }
+    const uint32_t n = alive ? out.has_main + out.n_shadow : 0u;
+    const uint32_t base = queue_reserve(a.count_out, n);
+    if (n) {
+        ps.ray_base = base;
+        uint32_t w = base;
+        if (out.has_main) store_ray(a.rays_out + w++, out.main);
+        for (uint32_t j = 0; j < out.n_shadow; ++j) store_ray(a.rays_out + w++, out.shadow[j]);
+    }
+    if (pc.de_evals) { atomicAdd(&a.counters->de_evals, (unsigned long long)pc.de_evals); atomicAdd(&a.counters->de_iterations, (unsigned long long)pc.de_iters); }
+}
+
+// ------------------------------------------------------------------------------------------
+template <bool STATS>
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace(const SceneView sc, const TraceArgs a) {
+    const uint32_t n = *a.count;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&a.counters->rays, (unsigned long long)n);
+    unsigned long long nodes = 0, leaves = 0, evals = 0, iters = 0;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane_id() == 0) base = atomicAdd(a.cursor, 32u);
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= n) break;
+        const uint32_t i = base + lane_id();
+        if (i < n) {
+            const Ray r = load_ray(a.rays + i);
+            Hit h;
+            TraceStats st;
+            st.nodes = 0; st.leaves = 0; st.de_evals = 0; st.de_iters = 0;
+            trace_ray<STATS>(sc, r, h, STATS ? &st : nullptr);
+            float4* dst = reinterpret_cast<float4*>(a.hits + i);
+            dst[0] = make_float4(h.t, h.u, h.v, __uint_as_float(h.rank));
+            dst[1] = make_float4(__uint_as_float(h.kind), 0.0f, 0.0f, 0.0f);
+            if (STATS) { nodes += st.nodes; leaves += st.leaves; evals += st.de_evals; iters += st.de_iters; }
+        }
+    }
+    if (STATS) {
+        for (int d = 16; d; d >>= 1) {
+            nodes += __shfl_down_sync(FULL, nodes, d); leaves += __shfl_down_sync(FULL, leaves, d);
+            evals += __shfl_down_sync(FULL, evals, d); iters += __shfl_down_sync(FULL, iters, d);
+        }
+        if (lane_id() == 0) {
+            atomicAdd(&a.counters->nodes_visited, nodes); atomicAdd(&a.counters->leaves_tested, leaves);
+            atomicAdd(&a.counters->de_evals, evals); atomicAdd(&a.counters->de_iterations, iters);
+        }
+    }
+}
+
+// pyr_trace seam: pyr_ray (32 B) in, pyr_hit (20 B) out; always closest-hit mode
+struct AbiHit { uint32_t prim_id, kind; float t, u, v; };
+template <bool STATS>
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace_batch(const SceneView sc, const Ray* rays, uint32_t n, AbiHit* hits, uint32_t* cursor,
+                                                               DeviceCounters* counters) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counters->rays, (unsigned long long)n);
+    unsigned long long nodes = 0, leaves = 0, evals = 0, iters = 0;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane_id() == 0) base = atomicAdd(cursor, 32u);
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= n) break;
+        const uint32_t i = base + lane_id();
+        if (i < n) {
+            Ray r = load_ray(rays + i);
+            r.mode = 0; r.limit = 0.0f;
+            Hit h;
+            TraceStats st;
+            st.nodes = 0; st.leaves = 0; st.de_evals = 0; st.de_iters = 0;
+            trace_ray<STATS>(sc, r, h, STATS ? &st : nullptr);
+            AbiHit o;
+            o.kind = h.kind; o.t = h.t; o.u = h.u; o.v = h.v;
+            if (h.kind == KIND_MISS) o.prim_id = 0xFFFFFFFFu;
+            else if (h.kind == KIND_PLANE) o.prim_id = h.rank;
+            else o.prim_id = prim_object(sc.prims[h.rank]);
+            hits[i] = o;
+            if (STATS) { nodes += st.nodes; leaves += st.leaves; evals += st.de_evals; iters += st.de_iters; }
+        }
+    }
+    if (STATS) {
+        for (int d = 16; d; d >>= 1) {
+            nodes += __shfl_down_sync(FULL, nodes, d); leaves += __shfl_down_sync(FULL, leaves, d);
+            evals += __shfl_down_sync(FULL, evals, d); iters += __shfl_down_sync(FULL, iters, d);
+        }
+        if (lane_id() == 0) {
+            atomicAdd(&counters->nodes_visited, nodes); atomicAdd(&counters->leaves_tested, leaves);
+            atomicAdd(&counters->de_evals, evals); atomicAdd(&counters->de_iterations, iters);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void k_film_expose(const SceneView sc, float* film, const float* positions, const float* samples, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    FilmAdd add{film};
+    film_expose(sc.film, positions[2 * i], positions[2 * i + 1], samples[3 * i], samples[3 * i + 1], samples[3 * i + 2], add);
+}
+
+__global__ void k_white_scan(const SceneView sc, float* params) {
+    float white_max, d65_max;
+    white_scan(sc, white_max, d65_max);
+    params[0] = white_max;
+    params[1] = d65_max;
+}
+
+__global__ void k_develop(const SceneView sc, const float* film, const float* params, float step_size, float* xyz_out, uint8_t* srgb_out) {
+    const uint64_t pixels = (uint64_t)sc.film.width * sc.film.height;
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= pixels) return;
+    float xyz[3] = {0.0f, 0.0f, 0.0f};
+    uint8_t rgb[3] = {0, 0, 0};
+    // DevelopedPixels::next stops at `end < len` (film.rs:299): the last pixel stays black
+    if (p + 1 < pixels) {
+        DevelopParams dp;
+        dp.white_max = params[0]; dp.d65_max = params[1]; dp.step_size = step_size; dp.pad = 0;
+        pixel_to_xyz(sc, dp, film, p, xyz);
+        xyz_to_srgb8(xyz, rgb);
+    }
+    if (xyz_out) { xyz_out[3 * p] = xyz[0]; xyz_out[3 * p + 1] = xyz[1]; xyz_out[3 * p + 2] = xyz[2]; }
+    if (srgb_out) { srgb_out[3 * p] = rgb[0]; srgb_out[3 * p + 1] = rgb[1]; srgb_out[3 * p + 2] = rgb[2]; }
+}
+
+// out: position[2], ray o[3] pad d[3] pad (8 floats), wavelengths[16], hero index (as float bits)
+__global__ void k_camera_sample(const SceneView sc, uint64_t seed, uint32_t tile, uint64_t sample, float* out) {
+    const TileRec t = sc.tiles[tile];
+    Rng rng = keyed_rng(seed, t.index, sample);
+    float ox = t.size[0] * rng.gen_f32();
+    float oy = t.size[1] * rng.gen_f32();
+    float px = t.from[0] + ox, py = t.from[1] + oy;
+    float wl[MAX_SPECTRUM_SAMPLES];
+    v3 o, d;
+    uint32_t pick;
+    if (sc.renderer.algorithm == 0) {  // simple.rs:87-107
+        camera_ray(sc.camera, px, py, rng, o, d);
+        pick = sample_wavelengths(sc, rng, wl);
+    } else {                            // bidirectional.rs:105-124
+        pick = sample_wavelengths(sc, rng, wl);
+        camera_ray(sc.camera, px, py, rng, o, d);
+    }
+    out[0] = px; out[1] = py;
+    out[2] = o.x; out[3] = o.y; out[4] = o.z; out[5] = 0.0f; out[6] = d.x; out[7] = d.y; out[8] = d.z; out[9] = 0.0f;
+    for (uint32_t k = 0; k < sc.renderer.spectrum_samples; ++k) out[10 + k] = wl[k];
+    out[10 + MAX_SPECTRUM_SAMPLES] = __uint_as_float(pick);
+}
+
+}  // namespace
+
+#include "bdpt_kernels.inl"
+
+void launch_pool_reset(PathState* paths, uint32_t pool, cudaStream_t s) {
+    if (pool) k_pool_reset<<<(pool + 255) / 256, 256, 0, s>>>(paths, pool);
+}
+void launch_wave_simple(const SceneView& sc, const WaveArgs& a, cudaStream_t s) {
+    k_wave_simple<<<(a.pool + WAVE_THREADS - 1) / WAVE_THREADS, WAVE_THREADS, 0, s>>>(sc, a);
+}
+void launch_trace(const SceneView& sc, const TraceArgs& a, int grid_blocks, cudaStream_t s) {
+    if (a.stats) k_trace<true><<<grid_blocks, TRACE_THREADS, 0, s>>>(sc, a);
+    else k_trace<false><<<grid_blocks, TRACE_THREADS, 0, s>>>(sc, a);
+}
+void launch_trace_batch(const SceneView& sc, const void* rays32, size_t n, void* hits20, uint32_t* cursor, DeviceCounters* counters, int stats,
+                        int grid_blocks, cudaStream_t s) {
+    if (stats) k_trace_batch<true><<<grid_blocks, TRACE_THREADS, 0, s>>>(sc, (const Ray*)rays32, (uint32_t)n, (AbiHit*)hits20, cursor, counters);
+    else k_trace_batch<false><<<grid_blocks, TRACE_THREADS, 0, s>>>(sc, (const Ray*)rays32, (uint32_t)n, (AbiHit*)hits20, cursor, counters);
+}
+void launch_film_expose(const SceneView& sc, float* film, const float* positions, const float* samples, size_t n, cudaStream_t s) {
+    if (n) k_film_expose<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(sc, film, positions, samples, n);
+}
+void launch_white_scan(const SceneView& sc, float* develop_params, cudaStream_t s) { k_white_scan<<<1, 1, 0, s>>>(sc, develop_params); }
+void launch_develop(const SceneView& sc, const float* film, const float* develop_params, float step_size, float* xyz, uint8_t* srgb, cudaStream_t s) {
+    const uint64_t pixels = (uint64_t)sc.film.width * sc.film.height;
+    k_develop<<<(unsigned)((pixels + 127) / 128), 128, 0, s>>>(sc, film, develop_params, step_size, xyz, srgb);
+}
+void launch_camera_sample(const SceneView& sc, uint64_t seed, uint32_t tile, uint64_t sample, float* out, cudaStream_t s) {
+    k_camera_sample<<<1, 1, 0, s>>>(sc, seed, tile, sample, out);
+}
+
+size_t path_state_bytes() { return sizeof(PathState); }
+size_t light_vertex_bytes() { return sizeof(LightVertex); }
+int trace_blocks_per_sm() {
+    int n = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace<false>, TRACE_THREADS, 0);
+    return n > 0 ? n : 1;
+}
+
+}  // namespace pyr

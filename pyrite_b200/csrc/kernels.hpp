@@ -1,0 +1,65 @@
+// Launchers of the sm_100a kernels (kernels.cu), called by the C ABI (abi.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "device_types.h"
+
+namespace pyr {
+
+struct PathState;   // shading.cuh
+struct LightVertex; // bdpt.cuh
+
+// Device-side work counters (one instance per context).
+struct DeviceCounters {
+    unsigned long long rays, path_samples, nodes_visited, leaves_tested, de_evals, de_iterations;
+};
+
+// Everything one wavefront iteration needs besides the scene.
+struct WaveArgs {
+    PathState* paths;
+    uint32_t pool;
+    const Ray* rays_in;        // rays traced in the previous iteration (read by the shade stage)
+    const Hit* hits_in;
+    Ray* rays_out;             // rays emitted by this iteration
+    uint32_t* count_out;       // number of rays emitted (device counter, pre-zeroed)
+    uint32_t* trace_cursor;    // work cursor of the trace kernel (reset here)
+    unsigned long long* next_sample;  // next global path-sample index to start
+    unsigned long long total_samples;
+    const unsigned long long* tile_first;  // n_tiles + 1 prefix sums of per-tile sample counts
+    uint64_t seed;
+    uint32_t sample_offset, sample_stride;
+    float* film;               // (accumulator, weight) pairs
+    DeviceCounters* counters;
+    LightVertex* light_vertices;  // bidirectional: pool * MAX_LIGHT_PATH
+    uint32_t ray_capacity;
+};
+
+struct TraceArgs {
+    const Ray* rays;
+    Hit* hits;
+    const uint32_t* count;   // device-resident ray count
+    uint32_t* cursor;        // dynamic work cursor (zero on entry)
+    DeviceCounters* counters;
+    int stats;
+};
+
+// the wavefront
+void launch_pool_reset(PathState* paths, uint32_t pool, cudaStream_t s);
+void launch_wave_simple(const SceneView& sc, const WaveArgs& a, cudaStream_t s);
+void launch_wave_bidirectional(const SceneView& sc, const WaveArgs& a, cudaStream_t s);
+void launch_trace(const SceneView& sc, const TraceArgs& a, int grid_blocks, cudaStream_t s);
+
+// ABI seams
+void launch_trace_batch(const SceneView& sc, const void* rays32, size_t n, void* hits20, uint32_t* cursor, DeviceCounters* counters, int stats,
+                        int grid_blocks, cudaStream_t s);
+void launch_film_expose(const SceneView& sc, float* film, const float* positions, const float* samples, size_t n, cudaStream_t s);
+void launch_white_scan(const SceneView& sc, float* develop_params, cudaStream_t s);
+void launch_develop(const SceneView& sc, const float* film, const float* develop_params, float step_size, float* xyz, uint8_t* srgb, cudaStream_t s);
+void launch_camera_sample(const SceneView& sc, uint64_t seed, uint32_t tile, uint64_t sample, float* out /* 2 + 8 + 16 + 1 floats */, cudaStream_t s);
+
+size_t path_state_bytes();
+size_t light_vertex_bytes();
+int trace_blocks_per_sm();
+
+}  // namespace pyr

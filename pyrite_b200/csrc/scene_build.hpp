@@ -1,0 +1,47 @@
+// Host scene builder: project IR -> the flat arrays the sm_100a kernels read (device_types.h).
+// This is the product's equivalent of `parse_project` (pyrite/src/main.rs:111-134):
+// Camera::from_project (cameras.rs:30-55), Renderer::from_project (renderer/mod.rs:31-75),
+// World::from_project (world.rs:39-271) with Material::from_project (materials/mod.rs:33-228),
+// ProgramCompiler::compile (program/compiler.rs:48-586) and Bvh::new (spatial/bvh.rs:13-155).
+// It runs once per project on the host; nothing in it is on the per-sample path.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "device_types.h"
+#include "project_ir.hpp"
+
+namespace pyr {
+
+struct BakedScene {
+    std::vector<Node> nodes;
+    std::vector<Prim> prims;            // leaf pre-order ("rank")
+    std::vector<TriShade> tri_shade;    // by rank
+    std::vector<TriFrames> tri_frames;  // by rank; empty unless some material has a normal map
+    std::vector<PlaneRec> planes;
+    std::vector<MarchedRec> marched;
+    std::vector<MaterialRec> materials;
+    std::vector<ComponentRec> components;
+    std::vector<ProgramRec> programs;
+    std::vector<Instr> code;
+    std::vector<SpectrumRec> spectra;
+    std::vector<float> spectrum_data;
+    std::vector<TextureRec> textures;
+    std::vector<float> texels;
+    std::vector<LampRec> lamps;
+    std::vector<TileRec> tiles;
+    std::vector<float> burns, xyz, d65;
+    std::vector<uint32_t> rank_of_object;  // object id -> rank
+    uint32_t n_objects = 0;
+    // header part of SceneView (pointers are filled in after upload)
+    SceneView view{};
+};
+
+// Throws ir::BuildError on a malformed project (missing mesh material, vector used as number...).
+BakedScene build_scene(const ir::Document& doc);
+
+// renderer/algorithm.rs:152-188 `make_tiles` + cameras.rs:57-68 `to_view_area` (row-major order;
+// the reference's centre-out sort only changes scheduling order).
+std::vector<TileRec> make_tiles(uint32_t width, uint32_t height, uint32_t tile_size);
+
+}  // namespace pyr

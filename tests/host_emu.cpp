@@ -1,0 +1,188 @@
+// TEST INFRASTRUCTURE: runs the product's scene builder and the __host__ __device__ stage
+// functions of pyrite_b200/csrc/{core,shading,bdpt}.cuh on the CPU, one path sample at a time, so
+// that the host logic (IR decode, material flattening, bytecode compiler, BVH build, wavefront
+// state machine) can be checked against the oracle in the GPU-less container.  Not shipped and not
+// loaded by the product; built by tests/conftest.py into tests/_build/libhostemu.so.
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../pyrite_b200/csrc/scene_build.hpp"
+#include "../pyrite_b200/csrc/bdpt.cuh"
+
+using namespace pyr;
+
+namespace {
+struct Emu {
+    BakedScene scene;
+    SceneView view;
+    std::vector<float> film;
+    uint64_t rays = 0, nodes = 0, leaves = 0;
+};
+thread_local std::string g_error;
+
+struct HostAdd {
+    float* film;
+    void operator()(uint64_t index, float increment, float weight) const { film[2 * index] += increment; film[2 * index + 1] += weight; }
+};
+}  // namespace
+
+extern "C" {
+
+const char* emu_last_error() { return g_error.c_str(); }
+
+int emu_load(const void* ir_blob, size_t bytes, void** out) {
+    try {
+        auto e = std::make_unique<Emu>();
+        e->scene = build_scene(ir::decode(ir_blob, bytes));
+        BakedScene& b = e->scene;
+        SceneView v = b.view;
+        v.nodes = b.nodes.data(); v.prims = b.prims.data(); v.tri_shade = b.tri_shade.data(); v.tri_frames = b.tri_frames.data();
+        v.planes = b.planes.data(); v.marched = b.marched.data(); v.materials = b.materials.data(); v.components = b.components.data();
+        v.programs = b.programs.data(); v.code = b.code.data(); v.spectra = b.spectra.data(); v.spectrum_data = b.spectrum_data.data();
+        v.textures = b.textures.data(); v.texels = b.texels.data(); v.lamps = b.lamps.data(); v.tiles = b.tiles.data();
+        v.burns = b.burns.data(); v.xyz = b.xyz.data(); v.d65 = b.d65.data();
+        e->view = v;
+        e->film.assign((size_t)v.film.width * v.film.height * v.film.bins * 2, 0.0f);
+        *out = e.release();
+        return 0;
+    } catch (const std::exception& ex) {
+        g_error = ex.what();
+        return 1;
+    }
+}
+void emu_free(void* h) { delete (Emu*)h; }
+
+// sizes: n_objects, n_planes, n_lamps, n_nodes, n_materials, n_programs, n_instr, n_tiles
+void emu_info(void* h, uint32_t* out) {
+    Emu* e = (Emu*)h;
+    out[0] = e->scene.n_objects; out[1] = e->view.n_planes; out[2] = e->view.n_lamps; out[3] = e->view.n_nodes;
+    out[4] = (uint32_t)e->scene.materials.size(); out[5] = (uint32_t)e->scene.programs.size(); out[6] = (uint32_t)e->scene.code.size();
+    out[7] = e->view.n_tiles;
+}
+void emu_leaf_order(void* h, uint32_t* object_ids) {
+    Emu* e = (Emu*)h;
+    for (uint32_t obj = 0; obj < e->scene.n_objects; ++obj) object_ids[e->scene.rank_of_object[obj]] = obj;
+}
+
+struct AbiRay { float o[3], pad0, d[3], pad1; };
+struct AbiHit { uint32_t prim_id, kind; float t, u, v; };
+void emu_trace(void* h, const AbiRay* rays, size_t n, AbiHit* hits, uint64_t* stats3) {
+    Emu* e = (Emu*)h;
+    TraceStats st{0, 0, 0, 0};
+    uint64_t nodes = 0, leaves = 0;
+    for (size_t i = 0; i < n; ++i) {
+        Ray r = make_ray(mk3(rays[i].o[0], rays[i].o[1], rays[i].o[2]), mk3(rays[i].d[0], rays[i].d[1], rays[i].d[2]), 0, 0.0f);
+        Hit hit;
+        st = TraceStats{0, 0, 0, 0};
+        trace_ray<true>(e->view, r, hit, &st);
+        nodes += st.nodes; leaves += st.leaves;
+        AbiHit o;
+        o.kind = hit.kind; o.t = hit.t; o.u = hit.u; o.v = hit.v;
+        o.prim_id = hit.kind == KIND_MISS ? 0xFFFFFFFFu : (hit.kind == KIND_PLANE ? hit.rank : prim_object(e->view.prims[hit.rank]));
+        hits[i] = o;
+    }
+    if (stats3) { stats3[0] = n; stats3[1] = nodes; stats3[2] = leaves; }
+}
+
+// The wavefront state machine, run depth-first for one path sample at a time.
+int emu_render(void* h, uint64_t seed, uint32_t spp_override, uint32_t offset, uint32_t stride, int reset) {
+    Emu* e = (Emu*)h;
+    try {
+        const SceneView& sc = e->view;
+        if (reset) std::fill(e->film.begin(), e->film.end(), 0.0f);
+        HostAdd add{e->film.data()};
+        const uint32_t spp = spp_override ? spp_override : sc.renderer.pixel_samples;
+        if (stride == 0) stride = 1;
+        std::vector<Ray> rays(1 + MAX_LIGHT_PATH + MAX_LIGHT_SAMPLES);
+        std::vector<Hit> hits(rays.size());
+        auto ps = std::make_unique<PathState>();
+        std::vector<LightVertex> lv(MAX_LIGHT_PATH);
+        for (uint32_t t = 0; t < sc.n_tiles; ++t) {
+            const uint64_t iterations = (uint64_t)sc.tiles[t].width * sc.tiles[t].height * spp;
+            for (uint64_t i = offset; i < iterations; i += stride) {
+                ShadeOut out;
+                PathCounters pc{0, 0};
+                if (sc.renderer.algorithm == 0) {
+                    generate_simple(sc, seed, t, i, *ps, out.main);
+                    out.has_main = 1; out.n_shadow = 0; out.alive = 1;
+                    while (out.alive) {
+                        uint32_t n = 0;
+                        if (out.has_main) rays[n++] = out.main;
+                        for (uint32_t j = 0; j < out.n_shadow; ++j) rays[n++] = out.shadow[j];
+                        for (uint32_t j = 0; j < n; ++j) { trace_ray<false>(sc, rays[j], hits[j], nullptr); ++e->rays; }
+                        shade_simple(sc, *ps, rays.data(), hits.data(), out, add, pc);
+                    }
+                } else {
+                    BidirOut bo;
+                    generate_bidirectional(sc, seed, t, i, *ps, lv.data(), bo);
+                    while (bo.alive) {
+                        for (uint32_t j = 0; j < bo.n_rays; ++j) { trace_ray<false>(sc, bo.rays[j], hits[j], nullptr); ++e->rays; rays[j] = bo.rays[j]; }
+                        shade_bidirectional(sc, *ps, lv.data(), rays.data(), hits.data(), bo, add, pc);
+                    }
+                }
+            }
+        }
+        return 0;
+    } catch (const std::exception& ex) {
+        g_error = ex.what();
+        return 1;
+    }
+}
+uint64_t emu_rays(void* h) { return ((Emu*)h)->rays; }
+void emu_film(void* h, float* out) { Emu* e = (Emu*)h; memcpy(out, e->film.data(), e->film.size() * sizeof(float)); }
+void emu_set_film(void* h, const float* in) { Emu* e = (Emu*)h; memcpy(e->film.data(), in, e->film.size() * sizeof(float)); }
+
+void emu_expose(void* h, const float* positions, const float* samples, size_t n) {
+    Emu* e = (Emu*)h;
+    HostAdd add{e->film.data()};
+    for (size_t i = 0; i < n; ++i)
+        film_expose(e->view.film, positions[2 * i], positions[2 * i + 1], samples[3 * i], samples[3 * i + 1], samples[3 * i + 2], add);
+}
+
+void emu_develop(void* h, float step_size, float* xyz_out, uint8_t* srgb_out) {
+    Emu* e = (Emu*)h;
+    const SceneView& sc = e->view;
+    DevelopParams dp{0, 0, step_size, 0};
+    white_scan(sc, dp.white_max, dp.d65_max);
+    const uint64_t pixels = (uint64_t)sc.film.width * sc.film.height;
+    for (uint64_t p = 0; p < pixels; ++p) {
+        float xyz[3] = {0, 0, 0};
+        uint8_t rgb[3] = {0, 0, 0};
+        if (p + 1 < pixels) { pixel_to_xyz(sc, dp, e->film.data(), p, xyz); xyz_to_srgb8(xyz, rgb); }
+        if (xyz_out) for (int c = 0; c < 3; ++c) xyz_out[3 * p + c] = xyz[c];
+        if (srgb_out) for (int c = 0; c < 3; ++c) srgb_out[3 * p + c] = rgb[c];
+    }
+}
+
+// evaluate program `index` (ExecutionContext::run): inputs = wavelength, normal[3], incident[3], tex[2]; out[4]
+void emu_run_program(void* h, int32_t index, const float* inputs, float* out4) {
+    Emu* e = (Emu*)h;
+    VmInputs in;
+    in.wavelength = inputs[0];
+    in.normal = mk3(inputs[1], inputs[2], inputs[3]);
+    in.incident = mk3(inputs[4], inputs[5], inputs[6]);
+    in.tex[0] = inputs[7]; in.tex[1] = inputs[8];
+    f4 R[VM_REGS];
+    f4 v = run_vector(e->view, index, in, R);
+    const ProgramRec p = e->view.programs[index];
+    if (p.is_constant) { out4[0] = p.value; out4[1] = out4[2] = out4[3] = p.value; return; }
+    out4[0] = v.x; out4[1] = v.y; out4[2] = v.z; out4[3] = v.w;
+}
+
+void emu_camera_sample(void* h, uint64_t seed, uint32_t tile, uint64_t sample, float* position2, AbiRay* ray, float* wavelengths, uint32_t* hero) {
+    Emu* e = (Emu*)h;
+    const SceneView& sc = e->view;
+    const TileRec t = sc.tiles[tile];
+    Rng rng = keyed_rng(seed, t.index, sample);
+    float ox = t.size[0] * rng.gen_f32();
+    float oy = t.size[1] * rng.gen_f32();
+    position2[0] = t.from[0] + ox; position2[1] = t.from[1] + oy;
+    v3 o, d;
+    if (sc.renderer.algorithm == 0) { camera_ray(sc.camera, position2[0], position2[1], rng, o, d); *hero = sample_wavelengths(sc, rng, wavelengths); }
+    else { *hero = sample_wavelengths(sc, rng, wavelengths); camera_ray(sc.camera, position2[0], position2[1], rng, o, d); }
+    *ray = AbiRay{{o.x, o.y, o.z}, 0.0f, {d.x, d.y, d.z}, 0.0f};
+}
+
+}  // extern "C"
