@@ -80,14 +80,19 @@ typedef struct pyr_render_params {
     uint32_t pool_paths;    /* paths in flight; 0 = library default */
     uint32_t flags;         /* PYR_RENDER_* */
 } pyr_render_params;
-#define PYR_RENDER_STATS 1u /* also count visited BVH nodes / tested leaves (slower) */
+#define PYR_RENDER_STATS 1u  /* also count visited BVH nodes / tested leaves (slower) */
+#define PYR_RENDER_TIMING 2u /* bracket every trace / shade launch with CUDA events (pyr_counters.*_seconds) */
 
 /* Work done since the last reset.  rays = World::intersect calls (path segments + shadow rays +
  * BDPT connection / visibility rays); path_samples = render_tile loop iterations. */
 typedef struct pyr_counters {
     uint64_t rays, path_samples, nodes_visited, leaves_tested, de_evals, de_iterations;
     uint64_t wavefront_iterations, kernel_launches;
-    double render_seconds; /* device time of the last pyr_render (CUDA events) */
+    double render_seconds; /* device time of the last pyr_render / pyr_trace_device (CUDA events) */
+    /* PYR_RENDER_TIMING: summed device time and launch count of the traversal kernel and of the
+     * shade/regenerate kernel since the last reset */
+    double trace_seconds, shade_seconds;
+    uint64_t trace_launches, shade_launches;
 } pyr_counters;
 
 /* renderer::Progress{progress: u8, message} (renderer/mod.rs:229-232); invoked on the calling
@@ -98,6 +103,9 @@ typedef int (*pyr_progress_cb)(uint8_t progress, const char* message, void* user
  * main.rs:190-204).  Fails with PYR_ERR_CUDA when no usable device exists: there is no CPU path. */
 pyr_status pyr_init(int32_t device, pyr_ctx** out);
 void pyr_shutdown(pyr_ctx* ctx);
+/* Launch all further work of `ctx` on the caller's CUDA stream (a cudaStream_t; NULL = back to the
+ * context's own stream) so that the caller's events and collectives order with it. */
+pyr_status pyr_stream_set(pyr_ctx* ctx, void* cuda_stream);
 
 /* Message for the last failing call on `ctx` (ctx == NULL: last pyr_init failure).  Replaces the
  * reference's error prints (main.rs:68-71,104). */

@@ -54,7 +54,9 @@ template <class T> void upload(DeviceBuffer& b, const std::vector<T>& v, cudaStr
 struct pyr_ctx {
     int device = 0;
     int sm_count = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;      // the stream work is launched on
+    cudaStream_t own_stream = nullptr;  // created by pyr_init
+    std::vector<cudaEvent_t> timing_events;
     std::string error;
     bool loaded = false;
     BakedScene scene;
@@ -71,10 +73,10 @@ struct pyr_ctx {
     unsigned long long* pinned = nullptr;  // [0] ray count, [1] next sample
 
     size_t film_floats() const { return (size_t)view.film.width * view.film.height * view.film.bins * 2; }
-    // scalars: [0] count A, [1] count B, [2] trace cursor, [4..5] next_sample (u64)
-    uint32_t* count(int i) const { return scalars.as<uint32_t>() + i; }
-    uint32_t* cursor() const { return scalars.as<uint32_t>() + 2; }
-    unsigned long long* next_sample() const { return (unsigned long long*)(scalars.as<uint32_t>() + 4); }
+    // scalars: [0..1] counts A {path rays, visibility rays}, [2..3] counts B, [4] trace cursor, [6..7] next_sample (u64)
+    uint32_t* count(int i) const { return scalars.as<uint32_t>() + 2 * i; }
+    uint32_t* cursor() const { return scalars.as<uint32_t>() + 4; }
+    unsigned long long* next_sample() const { return (unsigned long long*)(scalars.as<uint32_t>() + 6); }
 };
 
 namespace {
@@ -161,7 +163,8 @@ pyr_status pyr_init(int32_t device, pyr_ctx** out) {
         cudaDeviceProp prop;
         CU(cudaGetDeviceProperties(&prop, device));
         ctx->sm_count = prop.multiProcessorCount;
-        CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+        ctx->stream = ctx->own_stream;
         CU(cudaEventCreate(&ctx->ev0));
         CU(cudaEventCreate(&ctx->ev1));
         CU(cudaMallocHost((void**)&ctx->pinned, 4 * sizeof(unsigned long long)));
@@ -190,8 +193,16 @@ void pyr_shutdown(pyr_ctx* ctx) {
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    for (cudaEvent_t e : ctx->timing_events) cudaEventDestroy(e);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
+}
+
+pyr_status pyr_stream_set(pyr_ctx* ctx, void* cuda_stream) {
+    return guarded(ctx, [&] {
+        CU(cudaStreamSynchronize(ctx->stream));
+        ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    });
 }
 
 pyr_status pyr_project_load(pyr_ctx* ctx, const void* ir_blob, size_t bytes) {
@@ -341,15 +352,22 @@ pyr_status pyr_render(pyr_ctx* ctx, const pyr_render_params* params, pyr_progres
 
         const int trace_blocks = ctx->sm_count * trace_blocks_per_sm();
         const int stats = (p.flags & PYR_RENDER_STATS) ? 1 : 0;
+        const bool timing = (p.flags & PYR_RENDER_TIMING) != 0;
+        const int BATCH = 4;
+        if (timing)
+            while (ctx->timing_events.size() < (size_t)BATCH * 3) {
+                cudaEvent_t e;
+                CU(cudaEventCreate(&e));
+                ctx->timing_events.push_back(e);
+            }
         CU(cudaEventRecord(ctx->ev0, s));
         int cur = 0;
         unsigned long long iterations = 0, launches = 1;
         bool cancelled = false;
-        const int BATCH = 4;
         for (;;) {
             for (int b = 0; b < BATCH; ++b) {
                 const int nxt = cur ^ 1;
-                CU(cudaMemsetAsync(ctx->count(nxt), 0, sizeof(uint32_t), s));
+                CU(cudaMemsetAsync(ctx->count(nxt), 0, 2 * sizeof(uint32_t), s));
                 WaveArgs a{};
                 a.paths = ctx->paths.as<PathState>();
                 a.pool = pool;
@@ -357,6 +375,7 @@ pyr_status pyr_render(pyr_ctx* ctx, const pyr_render_params* params, pyr_progres
                 a.hits_in = ctx->hits.as<Hit>();
                 a.rays_out = ctx->rays[nxt].as<Ray>();
                 a.count_out = ctx->count(nxt);
+                a.shadow_offset = pool;
                 a.trace_cursor = ctx->cursor();
                 a.next_sample = ctx->next_sample();
                 a.total_samples = total;
@@ -368,24 +387,38 @@ pyr_status pyr_render(pyr_ctx* ctx, const pyr_render_params* params, pyr_progres
                 a.counters = ctx->counters.as<DeviceCounters>();
                 a.light_vertices = ctx->light_vertices.as<LightVertex>();
                 a.ray_capacity = (uint32_t)(ctx->rays[0].bytes / sizeof(Ray));
+                if (timing) CU(cudaEventRecord(ctx->timing_events[3 * b], s));
                 if (R.algorithm == 0) launch_wave_simple(ctx->view, a, s); else launch_wave_bidirectional(ctx->view, a, s);
+                if (timing) CU(cudaEventRecord(ctx->timing_events[3 * b + 1], s));
                 TraceArgs t{};
                 t.rays = ctx->rays[nxt].as<Ray>();
                 t.hits = ctx->hits.as<Hit>();
                 t.count = ctx->count(nxt);
+                t.shadow_offset = pool;
                 t.cursor = ctx->cursor();
                 t.counters = ctx->counters.as<DeviceCounters>();
                 t.stats = stats;
                 launch_trace(ctx->view, t, trace_blocks, s);
+                if (timing) CU(cudaEventRecord(ctx->timing_events[3 * b + 2], s));
                 cur = nxt;
                 ++iterations;
                 launches += 2;
             }
             CU(cudaGetLastError());
-            CU(cudaMemcpyAsync(&ctx->pinned[0], ctx->count(cur), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            CU(cudaMemcpyAsync(&ctx->pinned[0], ctx->count(cur), 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
             CU(cudaMemcpyAsync(&ctx->pinned[1], ctx->next_sample(), sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
             CU(cudaStreamSynchronize(s));
-            const uint32_t pending = (uint32_t)ctx->pinned[0];
+            if (timing)
+                for (int b = 0; b < BATCH; ++b) {
+                    float shade_ms = 0, trace_ms = 0;
+                    CU(cudaEventElapsedTime(&shade_ms, ctx->timing_events[3 * b], ctx->timing_events[3 * b + 1]));
+                    CU(cudaEventElapsedTime(&trace_ms, ctx->timing_events[3 * b + 1], ctx->timing_events[3 * b + 2]));
+                    ctx->host_counters.shade_seconds += shade_ms * 1e-3;
+                    ctx->host_counters.trace_seconds += trace_ms * 1e-3;
+                    ctx->host_counters.shade_launches += 1;
+                    ctx->host_counters.trace_launches += 1;
+                }
+            const uint32_t pending = (uint32_t)(ctx->pinned[0] & 0xffffffffull) + (uint32_t)(ctx->pinned[0] >> 32);
             const unsigned long long started = std::min<unsigned long long>(ctx->pinned[1], total);
             if (pending == 0 && started >= total) break;
             if (cb) {

@@ -351,22 +351,32 @@ PYR_HD float burns_rgb_spectrum(const SceneView& sc, f4 rgb, float wavelength) {
     float rr = rgb.x * r, gg = rgb.y * g, bb = rgb.z * b;
     return (rr + gg) + bb;
 }
-// Runs the program's instructions into R.  `rerun`: the previous call on the same R was the same
-// program with the same inputs except the wavelength, so only wavelength-dependent instructions
-// are executed again (MemoizedContext, execution_context.rs:310-342 - same values either way).
-PYR_HD_NOINLINE void vm_execute(const SceneView& sc, const ProgramRec& p, const VmInputs& in, f4* R, bool rerun) {
-    const Instr* code = sc.code + p.code_offset;
-    for (uint32_t pc = 0; pc < p.n_instr; ++pc) {
-        const Instr I = code[pc];
-        if (rerun && !(I.deps & IN_WAVELENGTH)) continue;
-        float n[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) n[k] = I.is_reg[k] ? R[I.v[k].u & (VM_REGS - 1)].x : I.v[k].f;
+// One instruction as eight 32-bit words (two 16-byte loads on the device).
+struct InstrWords { uint32_t head, regs, deps, resource, v[4]; };
+PYR_HD InstrWords fetch_instr(const Instr* p) {
+    InstrWords w;
+#if defined(__CUDA_ARCH__)
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    const uint4 a = __ldg(q), b = __ldg(q + 1);
+    w.head = a.x; w.regs = a.y; w.deps = a.z; w.resource = a.w;
+    w.v[0] = b.x; w.v[1] = b.y; w.v[2] = b.z; w.v[3] = b.w;
+#else
+    __builtin_memcpy(&w, p, sizeof(w));
+#endif
+    return w;
+}
+// Runs `count` instructions starting at `code` into R (program/execution_context.rs:69-283).
+PYR_HD_NOINLINE void vm_execute(const SceneView& sc, const Instr* code, uint32_t count, const VmInputs& in, f4* R) {
+    for (uint32_t pc = 0; pc < count; ++pc) {
+        const InstrWords I = fetch_instr(code + pc);
+        const uint32_t op = I.head & 0xffu, vtype = (I.head >> 8) & 0xffu;
+#define PYR_NUM(k) (((I.regs >> (8 * (k))) & 1u) ? R[I.v[k] & (VM_REGS - 1)].x : bits_f(I.v[k]))
+#define PYR_REG(k) R[I.v[k] & (VM_REGS - 1)]
         f4 out = mk4(0, 0, 0, 0);
-        switch (I.op) {
-            case OP_NUMBER: out.x = n[0]; break;
-            case OP_VECTOR: out = mk4(n[0], n[1], n[2], n[3]); break;
-            case OP_RGB: out = mk4(n[0], n[1], n[2], 1.0f); break;
+        switch (op) {
+            case OP_NUMBER: out.x = PYR_NUM(0); break;
+            case OP_VECTOR: out = mk4(PYR_NUM(0), PYR_NUM(1), PYR_NUM(2), PYR_NUM(3)); break;
+            case OP_RGB: out = mk4(PYR_NUM(0), PYR_NUM(1), PYR_NUM(2), 1.0f); break;
             case OP_SPECTRUM: out.x = spectrum_get(sc, I.resource, in.wavelength); break;
             case OP_COLOR_TEXTURE: {
                 float c[4];
@@ -380,52 +390,60 @@ PYR_HD_NOINLINE void vm_execute(const SceneView& sc, const ProgramRec& p, const 
                 out.x = c[0];
                 break;
             }
-            case OP_RGB_SPECTRUM: out.x = burns_rgb_spectrum(sc, R[I.v[0].u & (VM_REGS - 1)], in.wavelength); break;
-            case OP_FRESNEL: out.x = fresnel(n[0], n[1], in.normal, in.incident); break;
-            case OP_BLACKBODY: out.x = blackbody(in.wavelength, n[0]); break;
-            case OP_NUM_TO_RGB: out = mk4(n[0], n[0], n[0], 1.0f); break;
-            case OP_NUM_TO_VEC: out = mk4(n[0], n[0], n[0], n[0]); break;
+            case OP_RGB_SPECTRUM: out.x = burns_rgb_spectrum(sc, PYR_REG(0), in.wavelength); break;
+            case OP_FRESNEL: out.x = fresnel(PYR_NUM(0), PYR_NUM(1), in.normal, in.incident); break;
+            case OP_BLACKBODY: out.x = blackbody(in.wavelength, PYR_NUM(0)); break;
+            case OP_NUM_TO_RGB: { float n = PYR_NUM(0); out = mk4(n, n, n, 1.0f); break; }
+            case OP_NUM_TO_VEC: { float n = PYR_NUM(0); out = mk4(n, n, n, n); break; }
             case OP_RGB_TO_VEC: {  // execution_context.rs:183-193
-                f4 c = R[I.v[0].u & (VM_REGS - 1)];
+                f4 c = PYR_REG(0);
                 out = mk4((c.x * 2.0f) - 1.0f, (c.y * 2.0f) - 1.0f, (c.z * 2.0f) - 1.0f, (c.w * 2.0f) - 1.0f);
                 break;
             }
             case OP_BINARY: {  // execution_context.rs:228-268
-                f4 l = R[I.v[0].u & (VM_REGS - 1)], r = R[I.v[1].u & (VM_REGS - 1)];
-                switch (I.binop) {
+                const f4 l = PYR_REG(0), r = PYR_REG(1);
+                switch ((I.head >> 16) & 0xffu) {
                     case 0: out = add4(l, r); break;
                     case 1: out = sub4(l, r); break;
                     case 2: out = mul4(l, r); break;
                     default: out = div4(l, r); break;
                 }
-                if (I.vtype == VT_NUMBER) { out.y = 0; out.z = 0; out.w = 0; }
+                if (vtype == VT_NUMBER) { out.y = 0; out.z = 0; out.w = 0; }
                 break;
             }
             case OP_MIX: {  // execution_context.rs:195-227
-                float amount = fmaxf(fminf(n[0], 1.0f), 0.0f);
-                f4 l = R[I.v[1].u & (VM_REGS - 1)], r = R[I.v[2].u & (VM_REGS - 1)];
-                if (I.vtype == VT_NUMBER) out.x = l.x * (1.0f - amount) + r.x * amount;
+                float amount = fmaxf(fminf(PYR_NUM(0), 1.0f), 0.0f);
+                const f4 l = PYR_REG(1), r = PYR_REG(2);
+                if (vtype == VT_NUMBER) out.x = l.x * (1.0f - amount) + r.x * amount;
                 else out = add4(l, scale4(sub4(r, l), amount));
                 break;
             }
-            case OP_CLAMP: out.x = fmaxf(fminf(n[0], n[2]), n[1]); break;
+            case OP_CLAMP: out.x = fmaxf(fminf(PYR_NUM(0), PYR_NUM(2)), PYR_NUM(1)); break;
             default: break;
         }
-        R[I.out & (VM_REGS - 1)] = out;
+#undef PYR_NUM
+#undef PYR_REG
+        R[(I.head >> 24) & (VM_REGS - 1)] = out;
     }
 }
-// ExecutionContext::run for T = f32 (execution_context.rs:29-56)
+// ExecutionContext::run for T = f32 (execution_context.rs:29-56).  `rerun`: the previous call on
+// the same R was the same program with the same inputs except the wavelength, so only the
+// wavelength-dependent instructions run again (MemoizedContext, execution_context.rs:310-342).
+PYR_HD float run_program(const SceneView& sc, const ProgramRec& p, const VmInputs& in, f4* R, bool rerun) {
+    if (p.is_constant) return p.value;
+    if (rerun) vm_execute(sc, sc.code + p.wl_offset, p.wl_count, in, R);
+    else vm_execute(sc, sc.code + p.code_offset, p.n_instr, in, R);
+    return R[p.out_reg & (VM_REGS - 1)].x;
+}
 PYR_HD float run_number(const SceneView& sc, int32_t program, const VmInputs& in, f4* R, bool rerun = false) {
     const ProgramRec p = sc.programs[program];
-    if (p.is_constant) return p.value;
-    vm_execute(sc, p, in, R, rerun);
-    return R[p.out_reg & (VM_REGS - 1)].x;
+    return run_program(sc, p, in, R, rerun);
 }
 // ... and T = Vector (the compiler already appended the output conversion, compiler.rs:532-567)
 PYR_HD f4 run_vector(const SceneView& sc, int32_t program, const VmInputs& in, f4* R) {
     const ProgramRec p = sc.programs[program];
     if (p.is_constant) return mk4(p.value, p.value, p.value, p.value);
-    vm_execute(sc, p, in, R, false);
+    vm_execute(sc, sc.code + p.code_offset, p.n_instr, in, R);
     return R[p.out_reg & (VM_REGS - 1)];
 }
 PYR_HD bool program_reads_wavelength(const SceneView& sc, int32_t program) {
@@ -600,8 +618,38 @@ PYR_HD bool occludes(uint32_t mode, float t, float limit) { return mode == 1 ? (
 // (spatial/bvh.rs:206-229) but nearest child first, with a stack.  Result = the lexicographic
 // minimum (t, plane-before-leaf, rank) over the leaves whose boxes are hit - the reference's
 // answer whenever no leaf lies closer than its own box's entry distance by rounding.
-template <bool STATS>
-PYR_HD void trace_ray(const SceneView& sc, const Ray& ray, Hit& hit, TraceStats* stats) {
+// 16-byte loads through the read-only path on the device
+PYR_HD Node fetch_node(const Node* p) {
+#if defined(__CUDA_ARCH__)
+    const float4* q = reinterpret_cast<const float4*>(p);
+    const float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
+    Node n;
+    n.n0 = mk4(a.x, a.y, a.z, a.w); n.n1 = mk4(b.x, b.y, b.z, b.w); n.n2 = mk4(c.x, c.y, c.z, c.w); n.n3 = mk4(d.x, d.y, d.z, d.w);
+    return n;
+#else
+    return *p;
+#endif
+}
+PYR_HD Prim fetch_prim(const Prim* p) {
+#if defined(__CUDA_ARCH__)
+    const float4* q = reinterpret_cast<const float4*>(p);
+    const float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+    Prim r;
+    r.a = mk4(a.x, a.y, a.z, a.w); r.b = mk4(b.x, b.y, b.z, b.w); r.c = mk4(c.x, c.y, c.z, c.w);
+    return r;
+#else
+    return *p;
+#endif
+}
+// Traversal stack in thread-local storage (host emulation, fallback)
+struct LocalStack {
+    int slots[BVH_STACK];
+    PYR_HD void put(int i, int v) { slots[i] = v; }
+    PYR_HD int get(int i) const { return slots[i]; }
+};
+
+template <bool STATS, class Stack>
+PYR_HD void trace_ray(const SceneView& sc, const Ray& ray, Hit& hit, TraceStats* stats, Stack& stack) {
     const v3 o = ld3(ray.o), d = ld3(ray.d);
     const uint32_t mode = ray.mode;
     float closest = PYR_INF;
@@ -625,7 +673,6 @@ PYR_HD void trace_ray(const SceneView& sc, const Ray& ray, Hit& hit, TraceStats*
     if (sc.n_prims == 0) return;
     const v3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
 
-    int stack[BVH_STACK];
     int sp = 0;
     int cur;  // child code to process: >= 0 interior node, < 0 leaf
     {
@@ -639,7 +686,7 @@ PYR_HD void trace_ray(const SceneView& sc, const Ray& ray, Hit& hit, TraceStats*
     }
     for (;;) {
         if (cur >= 0) {
-            const Node nd = sc.nodes[cur];
+            const Node nd = fetch_node(sc.nodes + cur);
             float d0, d1;
             bool h0 = slab_test(mk3(nd.n0.x, nd.n0.y, nd.n0.z), mk3(nd.n0.w, nd.n1.x, nd.n1.y), o, inv, d0);
             bool h1 = slab_test(mk3(nd.n1.z, nd.n1.w, nd.n2.x), mk3(nd.n2.y, nd.n2.z, nd.n2.w), o, inv, d1);
@@ -649,14 +696,14 @@ PYR_HD void trace_ray(const SceneView& sc, const Ray& ray, Hit& hit, TraceStats*
             int c0 = (int)f_bits(nd.n3.x), c1 = (int)f_bits(nd.n3.y);
             if (h0 && h1) {
                 if (d1 < d0) { int t = c0; c0 = c1; c1 = t; }
-                stack[sp++] = c1;
+                stack.put(sp++, c1);
                 cur = c0;
                 continue;
             } else if (h0) { cur = c0; continue; }
             else if (h1) { cur = c1; continue; }
         } else {
             const uint32_t rank = (uint32_t)~cur;
-            const Prim pr = sc.prims[rank];
+            const Prim pr = fetch_prim(sc.prims + rank);
             const uint32_t kind = prim_kind(pr);
             if (STATS) ++vl;
             float t = 0, u = 0, v = 0;
@@ -675,12 +722,18 @@ PYR_HD void trace_ray(const SceneView& sc, const Ray& ray, Hit& hit, TraceStats*
         // pop: skip subtrees that the shrinking `closest` has made irrelevant is done at push time only
         // (a stale entry costs one node fetch; its children are culled by the test above)
         if (sp == 0) break;
-        cur = stack[--sp];
+        cur = stack.get(--sp);
     }
     if (STATS) {
         hit.nodes = vn; hit.leaves = vl;
         if (stats) { stats->nodes += vn; stats->leaves += vl; stats->de_evals += de_evals; stats->de_iters += de_iters; }
     }
+}
+
+template <bool STATS>
+PYR_HD void trace_ray(const SceneView& sc, const Ray& ray, Hit& hit, TraceStats* stats) {
+    LocalStack stack;
+    trace_ray<STATS>(sc, ray, hit, stats, stack);
 }
 
 }  // namespace pyr

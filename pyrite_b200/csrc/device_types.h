@@ -21,7 +21,7 @@ constexpr int MAX_RAY_MARCHED = 32;  // ray-marched shapes: candidate bitmask pe
 constexpr int BVH_STACK = 64;
 constexpr int MAX_LIGHT_PATH = 32;   // stored lamp-subpath vertices per path sample (bidirectional)
 
-struct f4 { float x, y, z, w; };
+struct alignas(16) f4 { float x, y, z, w; };
 
 // ---- geometry --------------------------------------------------------------------------
 // One BVH leaf primitive, stored in the reference BVH's leaf pre-order ("rank" order,
@@ -31,27 +31,27 @@ struct f4 { float x, y, z, w; };
 //   sphere:   a = (centre.xyz, radius)  b.x, b.y = texture_scale
 //   marched:  a.x = index into the ray-marched table (uint bits)
 //   c.y = kind (uint bits), c.z = object id (insertion order, world.rs:75,182,229), c.w = material
-struct Prim { f4 a, b, c; };
+struct alignas(16) Prim { f4 a, b, c; };
 
 // Binary BVH node carrying BOTH children's boxes (the box values and the slab arithmetic are the
 // reference's, math.rs:184-207).  64 B = four 16-byte loads.
 //   n0 = (c0.min.xyz, c0.max.x)  n1 = (c0.max.y, c0.max.z, c1.min.x, c1.min.y)
 //   n2 = (c1.min.z, c1.max.xyz)  n3 = (child0, child1, -, -) as int bits; child < 0: leaf, rank = ~child
-struct Node { f4 n0, n1, n2, n3; };
+struct alignas(16) Node { f4 n0, n1, n2, n3; };
 
 // Per-triangle shading data in the same rank order.  64 B.
-struct TriShade { float n1[3], n2[3], n3[3]; float t1[2], t2[2], t3[2]; float area; };
+struct alignas(16) TriShade { float n1[3], n2[3], n3[3]; float t1[2], t2[2], t3[2]; float area; };
 // Tangent-space quaternions of the three vertices (read only by normal-mapped materials). 48 B.
 struct TriFrames { f4 q1, q2, q3; };  // (s, x, y, z)
 
-struct PlaneRec {      // shapes/mod.rs:434-439 + collision::Plane{n, d}
+struct alignas(16) PlaneRec {      // shapes/mod.rs:434-439 + collision::Plane{n, d}
     float n[3], d;
     f4 from_space;     // Normal::from_space quaternion (s, x, y, z)
     float texture_scale[2];
     uint32_t material, pad;
 };
 
-struct MarchedRec {    // shapes/mod.rs:47-51, shapes/distance_estimators.rs, BoundingVolume :586-589
+struct alignas(16) MarchedRec {    // shapes/mod.rs:47-51, shapes/distance_estimators.rs, BoundingVolume :586-589
     uint32_t estimator;       // 0 mandelbulb, 1 quaternion julia
     uint32_t iterations;
     float threshold, power, slice_plane;
@@ -66,14 +66,14 @@ struct MarchedRec {    // shapes/mod.rs:47-51, shapes/distance_estimators.rs, Bo
 // ---- materials / programs ----------------------------------------------------------------
 enum BsdfType : uint32_t { BSDF_EMISSIVE = 0, BSDF_DIFFUSE = 1, BSDF_MIRROR = 2, BSDF_REFRACTIVE = 3 };
 
-struct ComponentRec {   // materials/mod.rs:230-235, 315-340
+struct alignas(16) ComponentRec {   // materials/mod.rs:230-235, 315-340
     uint32_t bsdf;
     int32_t color_program;
     int32_t probability_program;  // -1 = None
     float selection_compensation;
     float ior, env_ior, dispersion, env_dispersion;
 };
-struct MaterialRec {    // materials/mod.rs:26-30, 83-87
+struct alignas(16) MaterialRec {    // materials/mod.rs:26-30, 83-87
     uint32_t comp_offset, n_components, emissive_offset, n_emissive;
     int32_t normal_map_program;   // -1 = None
     uint32_t pad[3];
@@ -101,7 +101,7 @@ enum Op : uint8_t {
 enum ValueType : uint8_t { VT_NUMBER = 0, VT_VECTOR = 1, VT_RGB = 2 };
 enum InputBits : uint8_t { IN_WAVELENGTH = 1, IN_NORMAL = 16, IN_INCIDENT = 32, IN_TEXTURE = 64 };  // program/mod.rs:150-158
 
-struct Instr {
+struct alignas(16) Instr {
     uint8_t op, vtype, binop, out;    // binop: 0 add 1 sub 2 mul 3 div
     uint8_t is_reg[4];                // operand a..d: 1 = register index in v[i].u, 0 = constant in v[i].f
     uint8_t deps, pad[3];             // InputBits this instruction depends on (transitively)
@@ -112,20 +112,22 @@ static_assert(sizeof(Instr) == 32, "Instr must be 32 bytes");
 
 constexpr int VM_REGS = 16;
 
-struct ProgramRec {
+struct alignas(16) ProgramRec {
     uint32_t is_constant;
     float value;
     uint32_t code_offset, n_instr;
     uint32_t out_reg;
     uint32_t reads;           // union of deps
-    uint32_t pad[2];
+    // the wavelength-dependent instructions again, contiguously: what a memoised re-run executes
+    // (MemoizedContext, program/execution_context.rs:310-342)
+    uint32_t wl_offset, wl_count;
 };
 
-struct SpectrumRec { uint32_t is_curve; float lo, hi; uint32_t offset, n, pad[3]; };  // curve: (x, y) pairs at offset
-struct TextureRec { uint32_t width, height, channels, pad; uint64_t offset; uint64_t pad2; };
+struct alignas(16) SpectrumRec { uint32_t is_curve; float lo, hi; uint32_t offset, n, pad[3]; };  // curve: (x, y) pairs at offset
+struct alignas(16) TextureRec { uint32_t width, height, channels, pad; uint64_t offset; uint64_t pad2; };
 
 enum LampKind : uint32_t { LAMP_DIRECTIONAL = 0, LAMP_POINT = 1, LAMP_SHAPE = 2 };
-struct LampRec {       // lamp.rs:11-19
+struct alignas(16) LampRec {       // lamp.rs:11-19
     uint32_t kind;
     int32_t color_program;
     float v[3];         // direction | position
@@ -141,7 +143,7 @@ struct CameraRec {     // cameras.rs:20-27
     uint32_t inv_ok;
 };
 
-struct TileRec { float from[2], size[2]; uint32_t width, height, index, pad; };
+struct alignas(16) TileRec { float from[2], size[2]; uint32_t width, height, index, pad; };
 
 // ---- the resolved renderer (renderer/mod.rs:18-28) ----------------------------------------
 struct RendererRec {

@@ -112,7 +112,8 @@ __global__ void __launch_bounds__(WAVE_THREADS) k_wave_simple(const SceneView sc
 
     bool alive = valid && (ps.flags & PS_ALIVE);
     if (alive) {
-        shade_simple(sc, ps, a.rays_in + ps.ray_base, a.hits_in + ps.ray_base, out, add, pc);
+        shade_simple(sc, ps, a.rays_in + ps.ray_base, a.hits_in + ps.ray_base, a.rays_in + a.shadow_offset + ps.shadow_base,
+                     a.hits_in + a.shadow_offset + ps.shadow_base, out, add, pc);
         alive = out.alive != 0;
         if (!alive) ps.flags = 0;
     }
@@ -125,35 +126,52 @@ __global__ void __launch_bounds__(WAVE_THREADS) k_wave_simple(const SceneView sc
         out.has_main = 1; out.n_shadow = 0; out.alive = 1;
         alive = true;
     }
-    const uint32_t n = alive ? out.has_main + out.n_shadow : 0u;
-    const uint32_t base = queue_reserve(a.count_out, n);
-    if (n) {
-        ps.ray_base = base;
-        uint32_t w = base;
-        if (out.has_main) store_ray(a.rays_out + w++, out.main);
-        for (uint32_t j = 0; j < out.n_shadow; ++j) store_ray(a.rays_out + w++, out.shadow[j]);
+    // path rays and visibility rays go to separate queue regions so that trace packets are homogeneous
+    const uint32_t n_main = alive ? out.has_main : 0u, n_shadow = alive ? out.n_shadow : 0u;
+    const uint32_t main_at = queue_reserve(a.count_out, n_main);
+    const uint32_t shadow_at = queue_reserve(a.count_out + 1, n_shadow);
+    if (n_main) { ps.ray_base = main_at; store_ray(a.rays_out + main_at, out.main); }
+    if (n_shadow) {
+        ps.shadow_base = shadow_at;
+        for (uint32_t j = 0; j < n_shadow; ++j) store_ray(a.rays_out + a.shadow_offset + shadow_at + j, out.shadow[j]);
     }
     if (pc.de_evals) { atomicAdd(&a.counters->de_evals, (unsigned long long)pc.de_evals); atomicAdd(&a.counters->de_iterations, (unsigned long long)pc.de_iters); }
 }
 
 // ------------------------------------------------------------------------------------------
+// Traversal stack: the first SHARED_STACK entries live in shared memory ([entry][thread], no bank
+// conflicts), deeper entries (rare) in local memory.
+constexpr int SHARED_STACK = 24;
+struct SharedStack {
+    int* base;  // &smem[threadIdx.x]
+    int deep[BVH_STACK - SHARED_STACK];
+    __device__ __forceinline__ void put(int i, int v) { if (i < SHARED_STACK) base[i * TRACE_THREADS] = v; else deep[i - SHARED_STACK] = v; }
+    __device__ __forceinline__ int get(int i) const { return i < SHARED_STACK ? base[i * TRACE_THREADS] : deep[i - SHARED_STACK]; }
+};
+
 template <bool STATS>
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace(const SceneView sc, const TraceArgs a) {
-    const uint32_t n = *a.count;
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&a.counters->rays, (unsigned long long)n);
+    __shared__ int smem_stack[SHARED_STACK * TRACE_THREADS];
+    SharedStack stack;
+    stack.base = smem_stack + threadIdx.x;
+    const uint32_t n_main = a.count[0], n_shadow = a.count[1];
+    const uint32_t main_packets = (n_main + 31u) >> 5, packets = main_packets + ((n_shadow + 31u) >> 5);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&a.counters->rays, (unsigned long long)n_main + n_shadow);
     unsigned long long nodes = 0, leaves = 0, evals = 0, iters = 0;
     for (;;) {
-        uint32_t base = 0;
-        if (lane_id() == 0) base = atomicAdd(a.cursor, 32u);
-        base = __shfl_sync(FULL, base, 0);
-        if (base >= n) break;
-        const uint32_t i = base + lane_id();
-        if (i < n) {
+        uint32_t packet = 0;
+        if (lane_id() == 0) packet = atomicAdd(a.cursor, 1u);
+        packet = __shfl_sync(FULL, packet, 0);
+        if (packet >= packets) break;
+        const bool is_main = packet < main_packets;
+        const uint32_t local = (is_main ? packet : packet - main_packets) * 32u + lane_id();
+        if (local < (is_main ? n_main : n_shadow)) {
+            const uint32_t i = is_main ? local : a.shadow_offset + local;
             const Ray r = load_ray(a.rays + i);
             Hit h;
             TraceStats st;
             st.nodes = 0; st.leaves = 0; st.de_evals = 0; st.de_iters = 0;
-            trace_ray<STATS>(sc, r, h, STATS ? &st : nullptr);
+            trace_ray<STATS>(sc, r, h, STATS ? &st : nullptr, stack);
             float4* dst = reinterpret_cast<float4*>(a.hits + i);
             dst[0] = make_float4(h.t, h.u, h.v, __uint_as_float(h.rank));
             dst[1] = make_float4(__uint_as_float(h.kind), 0.0f, 0.0f, 0.0f);
@@ -177,6 +195,9 @@ struct AbiHit { uint32_t prim_id, kind; float t, u, v; };
 template <bool STATS>
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace_batch(const SceneView sc, const Ray* rays, uint32_t n, AbiHit* hits, uint32_t* cursor,
                                                                DeviceCounters* counters) {
+    __shared__ int smem_stack[SHARED_STACK * TRACE_THREADS];
+    SharedStack stack;
+    stack.base = smem_stack + threadIdx.x;
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counters->rays, (unsigned long long)n);
     unsigned long long nodes = 0, leaves = 0, evals = 0, iters = 0;
     for (;;) {
@@ -191,7 +212,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_batch(const SceneView s
             Hit h;
             TraceStats st;
             st.nodes = 0; st.leaves = 0; st.de_evals = 0; st.de_iters = 0;
-            trace_ray<STATS>(sc, r, h, STATS ? &st : nullptr);
+            trace_ray<STATS>(sc, r, h, STATS ? &st : nullptr, stack);
             AbiHit o;
             o.kind = h.kind; o.t = h.t; o.u = h.u; o.v = h.v;
             if (h.kind == KIND_MISS) o.prim_id = 0xFFFFFFFFu;

@@ -21,8 +21,9 @@ struct WaveArgs {
     uint32_t pool;
     const Ray* rays_in;        // rays traced in the previous iteration (read by the shade stage)
     const Hit* hits_in;
-    Ray* rays_out;             // rays emitted by this iteration
-    uint32_t* count_out;       // number of rays emitted (device counter, pre-zeroed)
+    Ray* rays_out;             // rays emitted by this iteration: path rays in [0, pool), visibility rays from `shadow_offset`
+    uint32_t* count_out;       // [0] path rays, [1] visibility rays emitted (device counters, pre-zeroed)
+    uint32_t shadow_offset;    // first index of the visibility-ray region in rays / hits
     uint32_t* trace_cursor;    // work cursor of the trace kernel (reset here)
     unsigned long long* next_sample;  // next global path-sample index to start
     unsigned long long total_samples;
@@ -38,8 +39,9 @@ struct WaveArgs {
 struct TraceArgs {
     const Ray* rays;
     Hit* hits;
-    const uint32_t* count;   // device-resident ray count
-    uint32_t* cursor;        // dynamic work cursor (zero on entry)
+    const uint32_t* count;   // device-resident ray counts: [0] path rays, [1] visibility rays
+    uint32_t shadow_offset;
+    uint32_t* cursor;        // dynamic work cursor in 32-ray packets (zero on entry)
     DeviceCounters* counters;
     int stats;
 };

@@ -296,6 +296,10 @@ int32_t compile_program(Document& doc, BakedScene& out, const Ex& root, bool vec
         rec.out_reg = o.reg;
         rec.reads = em.reads;
         out.code.insert(out.code.end(), em.body.begin(), em.body.end());
+        rec.wl_offset = (uint32_t)out.code.size();
+        for (const Instr& i : em.body)
+            if (i.deps & IN_WAVELENGTH) out.code.push_back(i);
+        rec.wl_count = (uint32_t)out.code.size() - rec.wl_offset;
     }
     out.programs.push_back(rec);
     return (int32_t)out.programs.size() - 1;

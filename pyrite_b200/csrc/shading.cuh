@@ -23,7 +23,8 @@ struct PathState {
     uint32_t tile, flags;
     uint32_t bounce, light_events, n_pending, ray_base;
     float pending_brdf;
-    uint32_t pad[3];
+    uint32_t shadow_base;      // index of this path's first visibility ray in the shadow region
+    uint32_t pad[2];
     float wl[MAX_SPECTRUM_SAMPLES];      // [0] = hero wavelength, then the additional ones (simple.rs:105-107)
     float bright[MAX_SPECTRUM_SAMPLES];  // Sample::brightness
     float refl[MAX_SPECTRUM_SAMPLES];    // the running reflectance of renderer/algorithm.rs:14-100
@@ -381,24 +382,33 @@ PYR_HD LampSample lamp_sample(const SceneView& sc, const LampRec& lamp, Rng& rng
 }
 
 // ---------------------------------------------------------------- the contribute fold (renderer/algorithm.rs:14-100)
+// values[k] = color(wl[k]) for k < n: the program record is fetched once and the memoised re-run
+// is used for k > 0
+PYR_HD void eval_spectral(const SceneView& sc, int32_t color, const VmInputs& base, const float* wl, uint32_t n, float* values, f4* R) {
+    const ProgramRec p = sc.programs[color];
+    if (p.is_constant) { for (uint32_t k = 0; k < n; ++k) values[k] = p.value; return; }
+    VmInputs in = base;
+    for (uint32_t k = 0; k < n; ++k) {
+        in.wavelength = wl[k];
+        values[k] = run_program(sc, p, in, R, k > 0);
+    }
+}
 // brightness[k] += color(wl[k]) * probability * reflectance[k] for k < n
 PYR_HD void add_emission(const SceneView& sc, PathState& ps, uint32_t n, int32_t color, v3 incident, v3 normal, const float* tex,
                          float probability, f4* R) {
     VmInputs in;
-    in.incident = incident; in.normal = normal; in.tex[0] = tex[0]; in.tex[1] = tex[1];
-    for (uint32_t k = 0; k < n; ++k) {
-        in.wavelength = ps.wl[k];
-        ps.bright[k] += run_number(sc, color, in, R, k > 0) * probability * ps.refl[k];
-    }
+    in.wavelength = 0.0f; in.incident = incident; in.normal = normal; in.tex[0] = tex[0]; in.tex[1] = tex[1];
+    float c[MAX_SPECTRUM_SAMPLES];
+    eval_spectral(sc, color, in, ps.wl, n, c, R);
+    for (uint32_t k = 0; k < n; ++k) ps.bright[k] += c[k] * probability * ps.refl[k];
 }
 PYR_HD void mul_reflectance(const SceneView& sc, PathState& ps, uint32_t n, int32_t color, v3 incident, v3 normal, const float* tex,
                             float probability, f4* R) {
     VmInputs in;
-    in.incident = incident; in.normal = normal; in.tex[0] = tex[0]; in.tex[1] = tex[1];
-    for (uint32_t k = 0; k < n; ++k) {
-        in.wavelength = ps.wl[k];
-        ps.refl[k] *= run_number(sc, color, in, R, k > 0) * probability;
-    }
+    in.wavelength = 0.0f; in.incident = incident; in.normal = normal; in.tex[0] = tex[0]; in.tex[1] = tex[1];
+    float c[MAX_SPECTRUM_SAMPLES];
+    eval_spectral(sc, color, in, ps.wl, n, c, R);
+    for (uint32_t k = 0; k < n; ++k) ps.refl[k] *= c[k] * probability;
 }
 
 struct PathCounters { uint32_t de_evals, de_iters; };
@@ -468,21 +478,37 @@ PYR_HD void expose_path(const SceneView& sc, const PathState& ps, Add& add) {
 // One wavefront step of the camera-to-light integrator for one path sample: fold the previous
 // bounce's direct light (its visibility rays are now traced), then process the closest hit of the
 // path ray exactly as one iteration of `trace`'s loop (tracer.rs:221-343) followed by
-// `contribute` for that bounce (algorithm.rs:14-100).  `rays` / `hits`: this path's rays of the
-// finished trace pass - the path ray first (if PS_HAS_MAIN), then `n_pending` visibility rays.
+// `contribute` for that bounce (algorithm.rs:14-100).  `main_ray` / `main_hit`: the path ray of the
+// finished trace pass (valid if PS_HAS_MAIN); `shadow_rays` / `shadow_hits`: its `n_pending`
+// visibility rays.
 template <class Add>
-PYR_HD void shade_simple(const SceneView& sc, PathState& ps, const Ray* rays, const Hit* hits, ShadeOut& out, Add& add, PathCounters& pc) {
+PYR_HD void shade_simple(const SceneView& sc, PathState& ps, const Ray* main_ray, const Hit* main_hit, const Ray* shadow_rays,
+                         const Hit* shadow_hits, ShadeOut& out, Add& add, PathCounters& pc) {
     f4 R[VM_REGS];
     const uint32_t S = sc.renderer.spectrum_samples;
     out.alive = 0; out.has_main = 0; out.n_shadow = 0;
-    const uint32_t shadow_base = (ps.flags & PS_HAS_MAIN) ? 1u : 0u;
 
     if (ps.flags & PS_PENDING_FOLD) {
         const uint32_t n = (ps.flags & PS_USE_ADDITIONAL) ? S : 1u;
+        // The light samples of one event come from one lamp; when its colour program reads nothing but
+        // the wavelength, colour(wl[k]) is the same for all of them and is evaluated once.
+        int32_t cached_program = -1;
+        uint32_t cached_n = 0;
+        float c[MAX_SPECTRUM_SAMPLES];
         for (uint32_t j = 0; j < ps.n_pending; ++j) {
-            if (hits[shadow_base + j].kind != KIND_MISS) continue;  // blocked
+            if (shadow_hits[j].kind != KIND_MISS) continue;  // blocked
             const PendingLight pl = ps.pend[j];
-            add_emission(sc, ps, pl.dispersed ? 1u : n, pl.color_program, ld3(rays[shadow_base + j].d), ld3(pl.normal), pl.tex, pl.probability, R);
+            const uint32_t m = pl.dispersed ? 1u : n;
+            if (pl.color_program != cached_program || m > cached_n) {
+                VmInputs in;
+                in.wavelength = 0.0f; in.incident = ld3(shadow_rays[j].d); in.normal = ld3(pl.normal); in.tex[0] = pl.tex[0]; in.tex[1] = pl.tex[1];
+                eval_spectral(sc, pl.color_program, in, ps.wl, m, c, R);
+                const ProgramRec p = sc.programs[pl.color_program];
+                const bool wavelength_only = p.is_constant || !(p.reads & (IN_NORMAL | IN_INCIDENT | IN_TEXTURE));
+                cached_program = wavelength_only ? pl.color_program : -1;
+                cached_n = m;
+            }
+            for (uint32_t k = 0; k < m; ++k) ps.bright[k] += c[k] * pl.probability * ps.refl[k];
         }
         for (uint32_t k = 0; k < n; ++k) ps.refl[k] *= ps.pending_brdf;
         ps.flags &= ~PS_PENDING_FOLD;
@@ -490,8 +516,8 @@ PYR_HD void shade_simple(const SceneView& sc, PathState& ps, const Ray* rays, co
     }
     if (!(ps.flags & PS_HAS_MAIN)) { expose_path(sc, ps, add); return; }
 
-    const v3 o = ld3(rays[0].o), d = ld3(rays[0].d);
-    const Hit h = hits[0];
+    const v3 o = ld3(main_ray->o), d = ld3(main_ray->d);
+    const Hit h = *main_hit;
     const float wavelength = ps.wl[0];
     if (h.kind == KIND_MISS) {  // tracer.rs:322-342
         int32_t color = sc.sky_program;

@@ -3,7 +3,7 @@ configs C1-C5, written with the Python mirror of the Lua DSL (pyrite_b200.projec
 
 Assets come from tests/golden/ (fixtures generated from the reference's own test assets by
 tests/golden/make_fixtures.py).  `dragon.obj` is absent from the reference
-(.MISSING_LARGE_BLOBS), so `dragon_mesh()` builds a deterministic 871,414-triangle stand-in
+(.MISSING_LARGE_BLOBS), so `dragon_mesh()` builds a deterministic 871,200-triangle stand-in
 (SURVEY.md §8d C2).
 """
 from __future__ import annotations
@@ -37,9 +37,11 @@ def _image(name: str) -> Image:
 
 # --------------------------------------------------------------------------- synthetic meshes
 @lru_cache(maxsize=4)
-def dragon_mesh(n_along: int = 10627, n_around: int = 41, seed: int = 0xD8A60) -> Mesh:
+def dragon_mesh(n_along: int = 1980, n_around: int = 220, seed: int = 0xD8A60) -> Mesh:
     """Closed, noise-displaced (2,3) torus-knot tube: 2 * n_along * n_around triangles
-    (defaults: 871,414), object name `dragon`, smooth vertex normals, no UVs.  Model-space
+    (defaults: 871,200 near-isotropic triangles, edge lengths about 0.05 x 0.07 - a scanned mesh
+    such as the Stanford dragon has well-shaped triangles, so the stand-in avoids slivers),
+    object name `dragon`, smooth vertex normals, no UVs.  Model-space
     bounding box about 8 x 19 x 14 standing on z = 0 (so that dragon.lua's mesh transform keeps
     it inside the scene's walls)."""
     rs = np.random.RandomState(seed)

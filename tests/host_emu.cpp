@@ -109,10 +109,10 @@ int emu_render(void* h, uint64_t seed, uint32_t spp_override, uint32_t offset, u
                     out.has_main = 1; out.n_shadow = 0; out.alive = 1;
                     while (out.alive) {
                         uint32_t n = 0;
-                        if (out.has_main) rays[n++] = out.main;
+                        if (out.has_main) rays[n++] = out.main; else n = 1;
                         for (uint32_t j = 0; j < out.n_shadow; ++j) rays[n++] = out.shadow[j];
-                        for (uint32_t j = 0; j < n; ++j) { trace_ray<false>(sc, rays[j], hits[j], nullptr); ++e->rays; }
-                        shade_simple(sc, *ps, rays.data(), hits.data(), out, add, pc);
+                        for (uint32_t j = out.has_main ? 0 : 1; j < n; ++j) { trace_ray<false>(sc, rays[j], hits[j], nullptr); ++e->rays; }
+                        shade_simple(sc, *ps, rays.data(), hits.data(), rays.data() + 1, hits.data() + 1, out, add, pc);
                     }
                 } else {
                     BidirOut bo;

@@ -1,0 +1,18 @@
+#!/usr/bin/env python3
+"""One short render of the C2 dragon scene (default 2 spp) - the command profiled under ncu."""
+import sys
+from pathlib import Path
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from pyrite_b200 import api, project, scenes
+
+spp = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+scene = sys.argv[2] if len(sys.argv) > 2 else "dragon"
+kw = dict(spp=256) if scene == "dragon" else {}
+ir = project.serialize_project(scenes.SCENES[scene](**kw))
+with api.Renderer(0) as r:
+    r.load(ir)
+    secs = r.render(seed=1, spp=spp, timing=True)
+    c = r.counters()
+    print(f"{scene}: {spp} spp in {secs * 1e3:.1f} ms, {c['rays'] / secs / 1e6:.0f} Mrays/s, trace {c['trace_seconds'] * 1e3:.1f} ms shade {c['shade_seconds'] * 1e3:.1f} ms, "
+          f"{c['wavefront_iterations']} iterations")
