@@ -327,9 +327,14 @@ pyr_status pyr_render(pyr_ctx* ctx, const pyr_render_params* params, pyr_progres
         const uint32_t spp = p.spp_override ? p.spp_override : R.pixel_samples;
         const uint32_t stride = p.sample_stride ? p.sample_stride : 1u;
         const uint32_t offset = p.sample_offset;
-        if (R.algorithm == 0 && R.light_samples > 0 && ctx->view.n_lamps == 0)
-            throw ir::BuildError("the scene has no lamps: World::pick_lamp would panic (world.rs:303); set light_samples = 0");
-        if (R.algorithm == 1 && ctx->view.n_lamps == 0) throw ir::BuildError("the bidirectional renderer needs at least one lamp (world.rs:303)");
+        if (ctx->view.n_lamps == 0) {
+            // World::pick_lamp panics on an empty lamp list (`gen_range(0..0)`, world.rs:301-305); the reference reaches it
+            // from trace_direct at the first diffuse bounce (even with light_samples = 0) and from every bidirectional sample
+            bool any_diffuse = false;
+            for (const ComponentRec& c : ctx->scene.components) any_diffuse = any_diffuse || c.bsdf == BSDF_DIFFUSE;
+            if (R.algorithm == 1 || any_diffuse)
+                throw ir::BuildError("the scene has no lamps: World::pick_lamp would panic (world.rs:301-305)");
+        }
         cudaStream_t s = ctx->stream;
 
         // per-tile sample counts for this shard: i = offset, offset + stride, ... < area * spp

@@ -419,6 +419,7 @@ struct PathCounters { uint32_t de_evals, de_iters; };
 // before (and regardless of) the visibility result (the oracle has the same switch).
 PYR_HD void next_event(const SceneView& sc, PathState& ps, float wavelength, v3 ray_in, v3 position, v3 normal, ShadeOut& out, f4* R) {
     const uint32_t samples = sc.renderer.light_samples;
+    if (sc.n_lamps == 0) return;  // unreachable: pyr_render refuses such scenes (the reference would panic here)
     const uint32_t lamp_index = (uint32_t)ps.rng.gen_range_usize(sc.n_lamps);  // World::pick_lamp (world.rs:301-305)
     const float lamp_probability = 1.0f / (float)sc.n_lamps;
     const LampRec lamp = sc.lamps[lamp_index];

@@ -1,0 +1,114 @@
+"""Shared fixtures.  `-m "not gpu"` runs here (no GPU): the oracle, the host logic through the CPU
+emulation of the device code, the ABI surface.  `-m gpu` runs on a B200: parity through the C ABI."""
+import os
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def _has_gpu():
+    try:
+        import torch
+
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    if _has_gpu():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device in this container")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+# small versions of every named scene (SURVEY.md §4 example projects + BASELINE configs)
+def small_scene_kwargs():
+    from pyrite_b200 import scenes
+
+    return {
+        "cornell": dict(width=64, height=64, spp=4),
+        "spheres": dict(width=64, height=48, spp=4),
+        "diamonds": dict(width=64, height=48, spp=4),
+        "textures": dict(width=64, height=48, spp=4),
+        "rgb_emission": dict(width=64, height=48, spp=4),
+        "snowflake": dict(width=64, height=48, spp=4),
+        "fractals": dict(width=48, height=32, spp=2),
+        "dragon": dict(width=64, height=48, spp=4, mesh=scenes.dragon_mesh(300, 24)),
+    }
+
+
+SCENE_NAMES = ["cornell", "spheres", "diamonds", "textures", "rgb_emission", "snowflake", "fractals", "dragon"]
+MESH_SCENES = ["cornell", "diamonds", "textures", "snowflake", "dragon", "spheres", "rgb_emission"]
+
+_ir_cache = {}
+
+
+def scene_ir(name, **override):
+    from pyrite_b200 import project, scenes
+
+    key = (name, tuple(sorted((k, v) for k, v in override.items() if not hasattr(v, "position"))))
+    if key not in _ir_cache:
+        kw = dict(small_scene_kwargs()[name])
+        kw.update(override)
+        _ir_cache[key] = project.serialize_project(scenes.SCENES[name](**kw))
+    return _ir_cache[key]
+
+
+@pytest.fixture(scope="session")
+def oracle_factory():
+    from oracle_lib import Oracle
+
+    made = {}
+
+    def make(name, **override):
+        key = (name, tuple(sorted(override.items())))
+        if key not in made:
+            made[key] = Oracle(scene_ir(name, **override))
+        return made[key]
+
+    return make
+
+
+@pytest.fixture(scope="session")
+def emu_factory():
+    from emu_lib import Emu
+    from oracle_lib import Oracle
+
+    def make(name, **override):
+        ir = scene_ir(name, **override)
+        o = Oracle(ir)
+        return Emu(ir, (o.info.height, o.info.width, o.info.bins)), o
+
+    return make
+
+
+@pytest.fixture(scope="session")
+def gpu_renderer_factory():
+    from pyrite_b200 import api
+
+    live = []
+
+    def make(name, **override):
+        r = api.Renderer(0)
+        r.load(scene_ir(name, **override))
+        live.append(r)
+        return r
+
+    yield make
+    for r in live:
+        r.close()
+
+
+os.environ.setdefault("OMP_NUM_THREADS", "4")

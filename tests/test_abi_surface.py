@@ -1,0 +1,66 @@
+"""The C-ABI library builds, loads, and exports every symbol include/pyrite_b200.h declares (no compute)."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def declared_symbols():
+    text = (ROOT / "include" / "pyrite_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pyr_[a-z_0-9]+)\s*\(", text)) - {"pyr_progress_cb"})
+
+
+def test_library_exports_every_declared_symbol():
+    from pyrite_b200 import api
+
+    lib = api.load_library()
+    names = declared_symbols()
+    assert len(names) >= 19
+    for n in names:
+        assert hasattr(lib, n), f"{n} is declared in include/pyrite_b200.h but not exported"
+    assert sorted(api.EXPORTS) == names, "pyrite_b200.api.EXPORTS and the header disagree"
+
+
+def test_struct_layouts_match_the_header():
+    from pyrite_b200 import api
+
+    assert api.RAY_DTYPE.itemsize == 32 and api.HIT_DTYPE.itemsize == 20
+    assert ctypes.sizeof(api.ProjectInfo) == 16 * 4
+    assert ctypes.sizeof(api.RenderParams) == 32
+    assert ctypes.sizeof(api.Counters) == 8 * 8 + 3 * 8 + 2 * 8
+
+
+def test_version_string_names_the_target():
+    from pyrite_b200 import api
+
+    assert b"sm_100a" in api.load_library().pyr_version()
+
+
+def test_init_fails_loudly_without_a_gpu():
+    import torch
+
+    from pyrite_b200 import api
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(api.PyriteError) as e:
+        api.Renderer(0)
+    assert e.value.status == 2 and "no CPU path" in str(e.value)
+
+
+def test_missing_library_is_an_import_error(tmp_path):
+    from pyrite_b200 import api
+
+    with pytest.raises(ImportError):
+        api.load_library(tmp_path / "nope.so")
+
+
+def test_product_never_imports_the_oracle():
+    pkg = ROOT / "pyrite_b200"
+    for p in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")) + list(pkg.rglob("*.cpp")) + list(pkg.rglob("*.hpp")):
+        text = p.read_text()
+        assert "oracle_lib" not in text and "liboracle" not in text and "pyro_" not in text, f"{p} references the oracle"

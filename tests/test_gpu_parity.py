@@ -1,0 +1,223 @@
+"""Parity of the CUDA path (through the C ABI, pyrite_b200.api) with the oracle on a B200.
+
+Bars (BASELINE.json north_star / SURVEY.md §8d):
+  * BVH hit / primitive ids bit-exact on identical ray batches, edge-grazing ties counted; hit
+    distances within 1e-5 relative (triangles, spheres, planes: in practice bit-exact, the kernels
+    are compiled without FMA contraction);
+  * films on identical per-path RNG streams: mean luminance (CIE Y) within 1e-3 relative and
+    per-pixel RMSE(Y)/mean(Y) <= 1e-2 for mesh scenes.  Scenes whose shading calls libm
+    transcendentals per hit (normal-mapped / sphere-UV textures, sphere-traced fractals) differ from
+    glibc by ULPs on the device, which flips rare visibility / march-termination events; their bars
+    are: textures mean <= 1e-2 and <= 5 % of the pixels off by more than 5 % of the mean; fractals
+    mean <= 1e-2 and RMSE <= 1.5 x the RMSE between two independent-seed oracle renders.
+"""
+import numpy as np
+import pytest
+from conftest import SCENE_NAMES, scene_ir
+
+pytestmark = pytest.mark.gpu
+
+EXACT_SCENES = ["cornell", "spheres", "diamonds", "textures", "rgb_emission", "snowflake", "dragon"]
+
+
+@pytest.mark.parametrize("name", SCENE_NAMES)
+def test_leaf_order_and_info(name, gpu_renderer_factory, oracle_factory):
+    r, o = gpu_renderer_factory(name), oracle_factory(name)
+    assert np.array_equal(r.bvh_leaf_order(), o.bvh_leaf_order())
+    gi, oi = r.info, o.info
+    for f in ("width", "height", "bins", "algorithm", "pixel_samples", "bounces", "light_samples", "spectrum_samples", "light_bounces",
+              "tile_size", "n_objects", "n_planes", "n_lights", "n_bvh_nodes", "n_materials"):
+        assert getattr(gi, f) == getattr(oi, f), f
+
+
+@pytest.mark.parametrize("name", EXACT_SCENES)
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_ray_batches(name, kind, gpu_renderer_factory, oracle_factory):
+    r, o = gpu_renderer_factory(name), oracle_factory(name)
+    rays = o.gen_rays(kind, 200_000, seed=20 + kind)
+    want, _ = o.trace(rays)
+    got = r.trace(rays)
+    same = (want["prim_id"] == got["prim_id"]) & (want["kind"] == got["kind"])
+    ties = int((~same).sum())
+    print(f"{name} batch {kind}: {ties} id mismatches of {len(rays)}")
+    assert ties == 0, f"{ties} hit ids differ (edge-grazing ties are expected to be 0 for these batches)"
+    hit = want["kind"] != 0
+    rel = np.abs(want["t"][hit] - got["t"][hit]) / np.abs(want["t"][hit])
+    assert rel.size == 0 or rel.max() <= 1e-5
+    assert np.allclose(want["u"], got["u"], atol=1e-6) and np.allclose(want["v"], got["v"], atol=1e-6)
+
+
+def test_ray_marched_batches_within_tolerance(gpu_renderer_factory, oracle_factory):
+    # sphere tracing calls powf / acosf / atan2f / sinf / cosf / logf per step: tolerance-based parity only
+    r, o = gpu_renderer_factory("fractals"), oracle_factory("fractals")
+    rays = o.gen_rays(0, 100_000, seed=1)
+    want, _ = o.trace(rays)
+    got = r.trace(rays)
+    same = (want["prim_id"] == got["prim_id"]) & (want["kind"] == got["kind"])
+    assert (~same).mean() <= 2e-3
+    hit = (want["kind"] != 0) & same
+    rel = np.abs(want["t"][hit] - got["t"][hit]) / np.abs(want["t"][hit])
+    assert np.median(rel) <= 1e-6 and np.mean(rel > 1e-3) <= 5e-3
+
+
+def test_edge_cases(gpu_renderer_factory, oracle_factory):
+    r, o = gpu_renderer_factory("cornell"), oracle_factory("cornell")
+    from pyrite_b200 import api
+
+    assert len(r.trace(np.zeros(0, api.RAY_DTYPE))) == 0   # empty batch
+    rays = o.gen_rays(0, 33, seed=5)            # ragged: not a multiple of the 32-ray packet
+    assert np.array_equal(o.trace(rays)[0]["prim_id"], r.trace(rays)["prim_id"])
+    rays = o.gen_rays(1, 1, seed=6)
+    assert np.array_equal(o.trace(rays)[0]["prim_id"], r.trace(rays)["prim_id"])
+    rays = o.gen_rays(0, 64, seed=7)
+    rays["d"] = -rays["d"]                       # looking away from the box: all misses
+    got = r.trace(rays)
+    want = o.trace(rays)[0]
+    assert np.array_equal(want["kind"], got["kind"]) and np.array_equal(want["prim_id"], got["prim_id"])
+    rays["d"][:, :] = [0, 0, 1]                  # axis-aligned directions: 1/0 = inf in the slab test
+    assert np.array_equal(o.trace(rays)[0]["prim_id"], r.trace(rays)["prim_id"])
+    rays["d"][:, :] = np.nan                     # NaN directions must not hang or crash
+    assert np.array_equal(o.trace(rays)[0]["kind"], r.trace(rays)["kind"])
+
+
+def luminance_stats(xo, xg):
+    yo, yg = xo[..., 1].astype(np.float64), xg[..., 1].astype(np.float64)
+    mean = yo.mean()
+    return abs(yg.mean() - mean) / mean, np.sqrt(np.mean((yo - yg) ** 2)) / mean, float(np.mean(np.abs(yo - yg) > 0.05 * mean))
+
+
+@pytest.mark.parametrize("name", SCENE_NAMES)
+def test_films_on_identical_streams(name, gpu_renderer_factory, oracle_factory):
+    spp = {"fractals": 8}.get(name, 16)
+    r, o = gpu_renderer_factory(name), oracle_factory(name)
+    r.render(seed=5, spp=spp)
+    o.render(seed=5, spp=spp)
+    fg, fo = r.film(), o.film()
+    if name != "fractals":
+        assert np.array_equal(fg[..., 1], fo[..., 1]), "per-bin weights (sample counts) differ"
+    xg, sg = r.develop()
+    xo, so = o.develop()
+    dmean, rmse, off = luminance_stats(xo, xg)
+    print(f"{name}: mean-Y rel err {dmean:.2e}, RMSE/mean {rmse:.2e}, pixels off by >5% {off:.2%}")
+    if name == "fractals":
+        # the ray-marched normal is a difference of nearly equal distance estimates (shapes/mod.rs:387-405), so device-vs-glibc
+        # ULPs decorrelate the bounce directions: compare against the oracle's own noise floor (independent-seed mode)
+        o.render(seed=6, spp=spp)
+        xo2, _ = o.develop()
+        _, floor, _ = luminance_stats(xo, xo2)
+        print(f"fractals: oracle-vs-oracle noise floor RMSE/mean {floor:.2e}")
+        assert dmean <= 1e-2 and rmse <= 1.5 * floor
+    elif name == "textures":
+        assert dmean <= 1e-2 and off <= 0.05
+    else:
+        assert dmean <= 1e-3 and rmse <= 1e-2
+        assert np.mean(np.abs(sg.astype(int) - so.astype(int)) > 1) <= 0.01
+    c = r.counters()
+    assert c["path_samples"] > 0 and c["rays"] > 0 and c["kernel_launches"] > 0
+
+
+def test_sample_pass_sharding_is_additive(gpu_renderer_factory):
+    r = gpu_renderer_factory("cornell")
+    r.render(seed=9, spp=4)
+    whole = r.film()
+    r.render(seed=9, spp=4, sample_offset=0, sample_stride=2, reset_film=True)
+    r.render(seed=9, spp=4, sample_offset=1, sample_stride=2, reset_film=False)
+    parts = r.film()
+    assert np.array_equal(whole[..., 1], parts[..., 1])
+    assert np.allclose(whole[..., 0], parts[..., 0], rtol=1e-4, atol=1e-5)
+
+
+def test_film_expose_and_develop(gpu_renderer_factory, oracle_factory):
+    r, o = gpu_renderer_factory("cornell"), oracle_factory("cornell")
+    rs = np.random.RandomState(4)
+    n = 100_000
+    pos = rs.uniform(-1.2, 1.2, (n, 2)).astype(np.float32)
+    smp = np.stack([rs.uniform(0, 5, n), rs.uniform(380, 779.99, n), rs.uniform(0.1, 1, n)], axis=1).astype(np.float32)
+    r.clear_film()
+    o.set_film(np.zeros(r.film_shape, np.float32))
+    r.expose(pos, smp)
+    o.expose(pos, smp)
+    fg, fo = r.film(), o.film()
+    assert np.array_equal(fg[..., 1] > 0, fo[..., 1] > 0)
+    assert np.allclose(fg, fo, rtol=1e-5, atol=1e-6)
+    film = rs.uniform(0, 2, r.film_shape).astype(np.float32)
+    r.set_film(film)
+    o.set_film(film)
+    for step in (2.0, 30.0):
+        xg, sg = r.develop(step)
+        xo, so = o.develop(step)
+        assert np.allclose(xg, xo, rtol=2e-5, atol=1e-6)
+        assert np.abs(sg.astype(int) - so.astype(int)).max() <= 1
+        assert np.all(xg[-1, -1] == 0)  # film.rs:299 quirk
+
+
+def test_camera_seam(gpu_renderer_factory, oracle_factory):
+    for name in ("cornell", "diamonds"):
+        r, o = gpu_renderer_factory(name), oracle_factory(name)
+        for tile, sample in [(0, 0), (1, 17), (3, 4095)]:
+            pg, rg, wg, hg = r.camera_sample(3, tile, sample)
+            po, ro, wo, ho = o.camera_sample(3, tile, sample)
+            assert np.array_equal(pg, po) and hg == ho and np.array_equal(wg, wo)
+            assert np.allclose(rg["o"], ro["o"], rtol=1e-6, atol=1e-7) and np.allclose(rg["d"], ro["d"], rtol=1e-6, atol=1e-7)
+
+
+def test_errors(gpu_renderer_factory):
+    from pyrite_b200 import api
+    from pyrite_b200 import project as P
+
+    r = api.Renderer(0)
+    with pytest.raises(api.PyriteError) as e:
+        r.render()
+    assert e.value.status == 3  # PYR_ERR_STATE: no project loaded
+    with pytest.raises(api.PyriteError) as e:
+        r.load(b"garbage!" * 4)
+    assert e.value.status == 1
+    ir = P.serialize_project({"image": {"width": 8, "height": 8}, "renderer": P.renderer.simple(pixel_samples=1),
+                              "camera": P.camera.perspective(fov=40, transform=P.transform.look_at(**{"from": P.vector(0, 0, 5), "to": P.vector(0, 0, 0)})),
+                              "world": {"objects": [P.shape.sphere(position=P.vector(), radius=1, material={"surface": P.material.diffuse(color=1)})]}})
+    r.load(ir)
+    with pytest.raises(api.PyriteError, match="no lamps"):
+        r.render()
+    seen = []
+    r.load(scene_ir("cornell"))
+    with pytest.raises(api.PyriteError, match="cancel"):
+        r.render(spp=64, pool_paths=1024, progress=lambda pct, msg: seen.append(pct) or True)
+    assert seen
+    r.close()
+
+
+def test_full_size_properties(gpu_renderer_factory):
+    """BASELINE-size geometry (871,200 triangles): size-independent properties instead of the oracle."""
+    from pyrite_b200 import api, project, scenes
+
+    r = api.Renderer(0)
+    r.load(project.serialize_project(scenes.dragon(width=480, height=270, spp=1)))
+    order = r.bvh_leaf_order()
+    assert np.array_equal(np.sort(order), np.arange(r.info.n_objects))      # a permutation: every triangle is a leaf exactly once
+    rs = np.random.RandomState(2)
+    n = 1 << 20
+    o = np.tile(np.array([[-40, -30, 20]], np.float32), (n, 1))
+    tgt = np.stack([rs.uniform(-4, 4, n), rs.uniform(-9, 9, n), rs.uniform(0, 14, n)], axis=1)
+    d = tgt - o
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    rays = np.zeros(n, api.RAY_DTYPE)
+    rays["o"], rays["d"] = o, d
+    a = r.trace(rays)
+    b = r.trace(rays)
+    assert np.array_equal(a, b)                                               # idempotent / deterministic
+    hit = a["kind"] == 2
+    assert hit.mean() > 0.2
+    # re-tracing from just in front of each hit point must hit the same primitive at the remaining distance
+    p = o[hit] + d[hit] * (a["t"][hit] * 0.5)[:, None]
+    rays2 = np.zeros(int(hit.sum()), api.RAY_DTYPE)
+    rays2["o"], rays2["d"] = p, d[hit]
+    c = r.trace(rays2)
+    agree = c["prim_id"] == a["prim_id"][hit]
+    assert agree.mean() > 0.999
+    assert np.allclose(c["t"][agree], (a["t"][hit] * 0.5)[agree], rtol=1e-3)
+    # stats pass returns the same hits and non-zero counters
+    s = r.trace(rays[:4096], stats=True)
+    assert np.array_equal(s, a[:4096])
+    cn = r.counters()
+    assert cn["nodes_visited"] > 0 and cn["leaves_tested"] > 0
+    r.close()

@@ -1,0 +1,108 @@
+"""Product host logic + device stage functions, emulated on the CPU, against the oracle.
+The emulation (tests/host_emu.cpp) compiles the product's scene builder and the very same
+__host__ __device__ code the kernels run, without FMA, so results must be bit-identical."""
+import numpy as np
+import pytest
+from conftest import SCENE_NAMES, scene_ir
+
+from pyrite_b200 import project as P
+
+
+@pytest.mark.parametrize("name", SCENE_NAMES)
+def test_scene_build_matches_oracle(name, emu_factory):
+    emu, oracle = emu_factory(name)
+    i = oracle.info
+    assert emu.info["n_objects"] == i.n_objects and emu.info["n_planes"] == i.n_planes and emu.info["n_lamps"] == i.n_lights
+    assert emu.info["n_materials"] == i.n_materials
+    assert emu.info["n_nodes"] == max(i.n_objects - 1, 0) and i.n_bvh_nodes == max(2 * i.n_objects - 1, 0)
+    assert np.array_equal(emu.leaf_order(), oracle.bvh_leaf_order()), "BVH leaf pre-order (the tie rule) differs"
+
+
+@pytest.mark.parametrize("name", SCENE_NAMES)
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_ray_batches_bit_exact(name, kind, emu_factory):
+    emu, oracle = emu_factory(name)
+    rays = oracle.gen_rays(kind, 4000, seed=10 + kind)
+    want, cw = oracle.trace(rays)
+    got, cg = emu.trace(rays)
+    for f in ("prim_id", "kind", "t", "u", "v"):
+        assert np.array_equal(want[f], got[f]), f"{name} batch {kind}: field {f} differs"
+    assert cg["leaves"] <= cw["leaves"] * 1.6 + 100  # nearest-first order must not test many more leaves than the reference order
+
+
+@pytest.mark.parametrize("name", SCENE_NAMES)
+def test_film_bit_exact_on_identical_streams(name, emu_factory):
+    emu, oracle = emu_factory(name)
+    oracle.render(seed=5, threads=2)
+    emu.render(seed=5)
+    fo, fe = oracle.film(), emu.film()
+    assert np.array_equal(fo[..., 1], fe[..., 1])
+    assert np.allclose(fo[..., 0], fe[..., 0], rtol=1e-5, atol=1e-6)  # float add order inside one bin only
+    xo, so = oracle.develop()
+    xe, se = emu.develop()
+    assert np.allclose(xo, xe, rtol=1e-5, atol=1e-7)
+    assert np.abs(so.astype(int) - se.astype(int)).max() <= 1
+
+
+def test_sharded_render_equals_single(emu_factory):
+    emu, oracle = emu_factory("cornell")
+    emu.render(seed=9)
+    whole = emu.film()
+    emu.render(seed=9, sample_offset=0, sample_stride=2, reset_film=True)
+    emu.render(seed=9, sample_offset=1, sample_stride=2, reset_film=False)
+    parts = emu.film()
+    assert np.array_equal(whole[..., 1], parts[..., 1])
+    assert np.allclose(whole[..., 0], parts[..., 0], rtol=1e-5, atol=1e-6)
+
+
+def test_camera_samples_match(emu_factory):
+    for name in ("cornell", "diamonds"):  # pinhole and thin lens
+        emu, oracle = emu_factory(name)
+        for tile, sample in [(0, 0), (1, 17), (3, 4095)]:
+            po, ro, wo, ho = oracle.camera_sample(3, tile, sample)
+            pe, re_, we, he = emu.camera_sample(3, tile, sample, oracle.info.spectrum_samples)
+            assert np.array_equal(po, pe) and ho == he and np.array_equal(wo, we)
+            assert np.array_equal(ro["o"], re_["o"]) and np.array_equal(ro["d"], re_["d"])
+
+
+def test_builder_errors():
+    from emu_lib import Emu, EmuError
+
+    pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    tri = np.array([[[0, -1, -1], [1, -1, -1], [2, -1, -1]]], np.int32)
+    mesh = P.Mesh(pos, np.zeros((0, 2)), np.zeros((0, 3)), [("a", tri)])
+    base = {"image": {"width": 8, "height": 8}, "renderer": P.renderer.simple(pixel_samples=1),
+            "camera": P.camera.perspective(fov=40, transform=P.transform.look_at(**{"from": P.vector(0, 0, 5), "to": P.vector(0, 0, 0)}))}
+    with pytest.raises(EmuError, match="missing material"):
+        Emu(P.serialize_project(dict(base, world={"objects": [P.shape.mesh(file=mesh, materials={})]})), (8, 8, 64))
+    with pytest.raises(EmuError, match="vector"):
+        Emu(P.serialize_project(dict(base, world={"objects": [P.shape.sphere(position=P.vector(), radius=1, material={
+            "surface": P.material.diffuse(color=P.vector(1, 1, 1))})]})), (8, 8, 64))
+    with pytest.raises(EmuError, match="photon"):
+        Emu(P.serialize_project(dict(base, renderer=P.renderer.photon_mapping(pixel_samples=1), world={"objects": []})), (8, 8, 64))
+    with pytest.raises(EmuError):
+        Emu(b"\x00" * 16, (8, 8, 64))
+    with pytest.raises(EmuError, match="truncated"):
+        Emu(scene_ir("cornell")[:-8], (64, 64, 64))
+
+
+def test_empty_and_degenerate_scenes():
+    from emu_lib import Emu
+    from oracle_lib import Oracle
+
+    base = {"image": {"width": 8, "height": 8}, "renderer": P.renderer.simple(pixel_samples=2, light_samples=0),
+            "camera": P.camera.perspective(fov=40, transform=P.transform.look_at(**{"from": P.vector(0, 0, 5), "to": P.vector(0, 0, 0)}))}
+    ir = P.serialize_project(dict(base, world={"sky": 2.0, "objects": []}))        # no geometry at all: every ray sees the sky
+    emu, o = Emu(ir, (8, 8, 64)), Oracle(ir)
+    emu.render(seed=1); o.render(seed=1)
+    assert np.array_equal(emu.film(), o.film()) and emu.film()[..., 1].sum() > 0
+    # coincident triangles (zero-extent centroid hull -> the builder's halving branch, bvh.rs:67-93)
+    pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    tri = np.repeat(np.array([[[0, -1, -1], [1, -1, -1], [2, -1, -1]]], np.int32), 5, axis=0)
+    mesh = P.Mesh(pos, np.zeros((0, 2)), np.zeros((0, 3)), [("a", tri)])
+    ir = P.serialize_project(dict(base, world={"sky": 1.0, "objects": [P.shape.mesh(file=mesh, materials={"a": {"surface": P.material.mirror(color=1)}})]}))
+    emu, o = Emu(ir, (8, 8, 64)), Oracle(ir)
+    assert np.array_equal(emu.leaf_order(), o.bvh_leaf_order())
+    rays = np.zeros(1, dtype=[("o", np.float32, 3), ("pad0", np.float32), ("d", np.float32, 3), ("pad1", np.float32)])
+    rays["o"] = [[0.2, 0.2, 1]]; rays["d"] = [[0, 0, -1]]
+    assert emu.trace(rays)[0]["prim_id"][0] == o.trace(rays)[0]["prim_id"][0] == o.bvh_leaf_order()[0]
