@@ -64,7 +64,8 @@ struct pyr_ctx {
     DeviceBuffer nodes, prims, tri_shade, tri_frames, planes, marched, materials, components, programs, code, spectra, spectrum_data,
         textures, texels, lamps, tiles, burns, xyz, d65;
     DeviceBuffer film, develop_params, counters, scalars, tile_first;
-    DeviceBuffer paths, rays[2], hits, light_vertices;
+    DeviceBuffer paths, rays[2], hits, light_vertices, cam_vertices;
+    uint32_t shadow_per_path = 1;
     DeviceBuffer scratch_a, scratch_b;
     uint32_t pool = 0;
     bool develop_params_valid = false;
@@ -119,15 +120,31 @@ void ensure_develop_params(pyr_ctx* ctx) {
 
 void ensure_pool(pyr_ctx* ctx, uint32_t pool) {
     if (pool == ctx->pool && ctx->paths.p) return;
-    const uint32_t per_path = 1 + std::max<uint32_t>(ctx->view.renderer.light_samples, 1);
-    const bool bidir = ctx->view.renderer.algorithm == 1;
-    const size_t ray_cap = (size_t)pool * (bidir ? std::max<uint32_t>(per_path, MAX_LIGHT_PATH + 1) : per_path);
+    const RendererRec& R = ctx->view.renderer;
+    const bool bidir = R.algorithm == 1;
+    ctx->shadow_per_path = bidir ? (uint32_t)bdpt_stage_rays() : std::max<uint32_t>(R.light_samples, 1);
+    const size_t ray_cap = (size_t)pool * (1 + ctx->shadow_per_path);
     ctx->paths.ensure((size_t)pool * path_state_bytes());
     ctx->rays[0].ensure(ray_cap * sizeof(Ray));
     ctx->rays[1].ensure(ray_cap * sizeof(Ray));
     ctx->hits.ensure(ray_cap * sizeof(Hit));
-    if (bidir) ctx->light_vertices.ensure((size_t)pool * MAX_LIGHT_PATH * light_vertex_bytes());
+    if (bidir) {
+        ctx->light_vertices.ensure((size_t)pool * (R.light_bounces + 1) * light_vertex_bytes());
+        ctx->cam_vertices.ensure((size_t)pool * std::max<uint32_t>(R.bounces, 1) * cam_vertex_bytes());
+    }
     ctx->pool = pool;
+}
+
+// paths in flight: the library default is 2^20, reduced so that the bidirectional integrator's per-path
+// vertex storage stays within ~6 GB
+uint32_t default_pool(const pyr_ctx* ctx) {
+    const RendererRec& R = ctx->view.renderer;
+    if (R.algorithm != 1) return 1u << 20;
+    const size_t per_path = path_state_bytes() + (size_t)(R.light_bounces + 1) * light_vertex_bytes() +
+                            (size_t)std::max<uint32_t>(R.bounces, 1) * cam_vertex_bytes() + (size_t)(1 + bdpt_stage_rays()) * (2 * sizeof(Ray) + sizeof(Hit));
+    size_t pool = (size_t)6 << 30;
+    pool /= per_path;
+    return (uint32_t)std::min<size_t>(std::max<size_t>(pool, 4096), (size_t)1 << 20);
 }
 
 }  // namespace
@@ -187,7 +204,7 @@ void pyr_shutdown(pyr_ctx* ctx) {
     DeviceBuffer* all[] = {&ctx->nodes, &ctx->prims, &ctx->tri_shade, &ctx->tri_frames, &ctx->planes, &ctx->marched, &ctx->materials,
                            &ctx->components, &ctx->programs, &ctx->code, &ctx->spectra, &ctx->spectrum_data, &ctx->textures, &ctx->texels,
                            &ctx->lamps, &ctx->tiles, &ctx->burns, &ctx->xyz, &ctx->d65, &ctx->film, &ctx->develop_params, &ctx->counters,
-                           &ctx->scalars, &ctx->tile_first, &ctx->paths, &ctx->rays[0], &ctx->rays[1], &ctx->hits, &ctx->light_vertices,
+                           &ctx->scalars, &ctx->tile_first, &ctx->paths, &ctx->rays[0], &ctx->rays[1], &ctx->hits, &ctx->light_vertices, &ctx->cam_vertices,
                            &ctx->scratch_a, &ctx->scratch_b};
     for (DeviceBuffer* b : all) b->release();
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -347,7 +364,7 @@ pyr_status pyr_render(pyr_ctx* ctx, const pyr_render_params* params, pyr_progres
         const unsigned long long total = first.back();
         upload(ctx->tile_first, first, s);
 
-        uint32_t pool = p.pool_paths ? p.pool_paths : (1u << 20);
+        uint32_t pool = p.pool_paths ? p.pool_paths : default_pool(ctx);
         if ((unsigned long long)pool > total) pool = (uint32_t)std::max<unsigned long long>(total, 1);
         pool = (pool + 127u) & ~127u;
         ensure_pool(ctx, pool);
@@ -391,6 +408,9 @@ pyr_status pyr_render(pyr_ctx* ctx, const pyr_render_params* params, pyr_progres
                 a.film = ctx->film.as<float>();
                 a.counters = ctx->counters.as<DeviceCounters>();
                 a.light_vertices = ctx->light_vertices.as<LightVertex>();
+                a.cam_vertices = ctx->cam_vertices.as<CamVertex>();
+                a.light_stride = R.light_bounces + 1;
+                a.cam_stride = std::max<uint32_t>(R.bounces, 1);
                 a.ray_capacity = (uint32_t)(ctx->rays[0].bytes / sizeof(Ray));
                 if (timing) CU(cudaEventRecord(ctx->timing_events[3 * b], s));
                 if (R.algorithm == 0) launch_wave_simple(ctx->view, a, s); else launch_wave_bidirectional(ctx->view, a, s);

@@ -1,13 +1,35 @@
-// Bidirectional integrator (renderer/bidirectional.rs) - device-side stage logic.
+// Bidirectional integrator (pyrite/src/renderer/bidirectional.rs:73-398) as a per-path-sample state
+// machine for the wavefront pipeline.  One `render_tile` iteration runs through four phases, each
+// wavefront iteration tracing the rays the phase asked for:
+//
+//   PH_LAMP     the lamp subpath: Lamp::sample_ray (lamp.rs:84-113), the emission vertex
+//               (bidirectional.rs:128-174) and `trace(.., light_bounces, light_samples = 0)`, one path ray
+//               per iteration; vertices are stored in HBM (LightVertex, light_bounces + 1 per path)
+//   PH_CAMERA   the camera subpath: the same `trace` as the camera-to-light integrator (camera_step),
+//               folding `contribute` as it goes and storing the state at every diffuse vertex (CamVertex)
+//   PH_CONNECT  connect_paths (bidirectional.rs:310-398): for each stored camera vertex, visibility rays to
+//               the non-specular lamp vertices, in chunks of at most BDPT_STAGE rays per iteration; the
+//               weight 1 / (len(camera_path) * len(lamp_path)) is only known once the camera path has ended,
+//               which is why connections are made after it
+//   PH_SPLAT    light tracing (bidirectional.rs:253-306): Camera::is_visible (cameras.rs:99-158) for every
+//               diffuse lamp vertex, exposing at the projected film position
+//
+// The RNG draw order of the reference is kept: sample point, wavelengths, hero pick, camera ray, lamp
+// pick, lamp ray, emissive component, lamp subpath, camera subpath, then the lens samples of is_visible.
 #pragma once
 #include "shading.cuh"
 
 namespace pyr {
 
-// One stored vertex of the lamp subpath (tracer.rs:157-167 `Bounce`, without direct light).
-struct LightVertex {
+constexpr int BDPT_STAGE = 16;  // visibility rays staged per path per iteration
+
+enum : uint32_t { PH_LAMP = 0, PH_CAMERA = 1, PH_CONNECT = 2, PH_SPLAT = 3 };
+enum : uint32_t { VT_DIFFUSE = 0, VT_SPECULAR = 1, VT_EMISSION = 2 };
+
+// One stored vertex of the lamp subpath (tracer.rs:157-167 `Bounce`; lamp paths carry no direct light). 80 B.
+struct alignas(16) LightVertex {
     float position[3];
-    uint32_t type;        // 0 diffuse, 1 specular, 2 emission
+    uint32_t type;
     float normal[3];
     int32_t color_program;
     float incident[3];
@@ -17,13 +39,439 @@ struct LightVertex {
     float tex[2];
     uint32_t pad[2];
 };
+// A diffuse camera-subpath vertex with the sample state right after its `contribute`. 160 B.
+struct alignas(16) CamVertex {
+    float position[3];
+    float brdf;           // bounce.ty.brdf(..) = 2 |out . normal|
+    float normal[3];
+    uint32_t use_additional;
+    float bright[MAX_SPECTRUM_SAMPLES];
+    float refl[MAX_SPECTRUM_SAMPLES];
+};
 
 struct BidirOut {
-    uint32_t alive, n_rays;
-    Ray rays[1 + MAX_LIGHT_PATH];
+    uint32_t alive, has_main, n_shadow, pad;
+    Ray main;
+    Ray shadow[BDPT_STAGE];
 };
-PYR_HD void generate_bidirectional(const SceneView&, uint64_t, uint32_t, uint64_t, PathState&, LightVertex*, BidirOut& bo) { bo.alive = 0; bo.n_rays = 0; }
+
+struct BidirCtx {
+    LightVertex* lv;   // this path's lamp vertices
+    CamVertex* cv;     // this path's stored camera vertices
+};
+
+PYR_HD void st3(float* dst, v3 v) { dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; }
+PYR_HD float vertex_brdf(const LightVertex& v) {  // BounceType::brdf: lambertian(_, normal, out) = 2 |out . normal|
+    return v.type == VT_DIFFUSE ? 2.0f * fabsf(dot(ld3(v.out), ld3(v.normal))) : 1.0f;
+}
+
+// `contribute` (renderer/algorithm.rs:14-100) of a lamp-subpath bounce on a detached sample state
+PYR_HD void contribute_vertex(const SceneView& sc, const LightVertex& v, const float* wl, uint32_t n, float* bright, float* refl, f4* R) {
+    VmInputs in;
+    in.wavelength = 0.0f; in.incident = ld3(v.incident); in.normal = ld3(v.normal); in.tex[0] = v.tex[0]; in.tex[1] = v.tex[1];
+    float c[MAX_SPECTRUM_SAMPLES];
+    eval_spectral(sc, v.color_program, in, wl, n, c, R);
+    if (v.type == VT_EMISSION) {
+        for (uint32_t k = 0; k < n; ++k) bright[k] += c[k] * v.probability * refl[k];
+    } else {
+        for (uint32_t k = 0; k < n; ++k) refl[k] *= c[k] * v.probability;
+        const float brdf = vertex_brdf(v);
+        for (uint32_t k = 0; k < n; ++k) refl[k] *= brdf;
+    }
+}
+// the fold over lamp_path[first..] shared by connect_paths (:373-389) and light tracing (:276-292)
+PYR_HD void fold_lamp_tail(const SceneView& sc, const LightVertex* lv, uint32_t first, uint32_t n_light, const float* wl, bool& use_additional,
+                           float* bright, float* refl, float brdf_in, f4* R) {
+    const uint32_t S = sc.renderer.spectrum_samples;
+    for (uint32_t k = first; k < n_light; ++k) {
+        const LightVertex v = lv[k];
+        use_additional = !v.dispersed && use_additional;
+        const uint32_t n = use_additional ? S : 1u;
+        contribute_vertex(sc, v, wl, n, bright, refl, R);
+        if (k == first) for (uint32_t j = 0; j < n; ++j) refl[j] *= brdf_in;
+    }
+}
+
+// Camera::ray_towards inputs for the lens sample of Camera::is_visible (cameras.rs:122-131)
+PYR_HD v3 lens_origin(const CameraRec& cam, Rng& rng) {
+    if (cam.aperture > 0.0f) {
+        float sqrt_r = sqrtf(cam.aperture * rng.gen_f32());
+        float psi = PYR_PI * 2.0f * rng.gen_f32();
+        return mk3(sqrt_r * cosf(psi), sqrt_r * sinf(psi), 0.0f);
+    }
+    return mk3(0, 0, 0);
+}
+
+struct CameraHooks {
+    BidirCtx cx;
+    PYR_HD void contribute_done(PathState& ps) {
+        if (!ps.cam_store_pending) return;
+        CamVertex& c = cx.cv[ps.n_cam_stored - 1];
+        c.use_additional = (ps.flags & PS_USE_ADDITIONAL) ? 1u : 0u;
+        for (int k = 0; k < MAX_SPECTRUM_SAMPLES; ++k) { c.bright[k] = ps.bright[k]; c.refl[k] = ps.refl[k]; }
+        ps.cam_store_pending = 0;
+    }
+    PYR_HD void pushed_emission(PathState& ps) { ps.n_cam += 1; }
+    PYR_HD void pushed_surface(PathState& ps, bool diffuse, v3 position, v3 normal, float brdf) {
+        ps.n_cam += 1;
+        if (!diffuse) return;  // connect_paths returns at once for specular bounces (:320-323)
+        CamVertex& c = cx.cv[ps.n_cam_stored++];
+        st3(c.position, position); st3(c.normal, normal);
+        c.brdf = brdf;
+        ps.cam_store_pending = 1;
+    }
+};
+
+// -------------------------------------------------------------------------------- phase transitions
+PYR_HD void begin_camera(PathState& ps, BidirOut& out) {
+    ps.phase = PH_CAMERA;
+    ps.flags |= PS_HAS_MAIN | PS_SAMPLE_LIGHT | PS_USE_ADDITIONAL;
+    ps.flags &= ~PS_PENDING_FOLD;
+    ps.bounce = 0; ps.light_events = 0; ps.n_pending = 0; ps.pending_brdf = 1.0f;
+    out.has_main = 1;
+    out.main = make_ray(ld3(ps.cam_o), ld3(ps.cam_d), 0, 0.0f);
+    out.alive = 1;
+}
+
+// The end of the lamp subpath: utils::pairs fix-up (skips the last pair, utils.rs:5-13), drop a trailing
+// emission vertex, reverse (bidirectional.rs:187-202).
+PYR_HD void finish_lamp_path(PathState& ps, LightVertex* lv) {
+    uint32_t n = ps.n_light;
+    if (n >= 2)
+        for (uint32_t pos = 0; pos + 2 < n; ++pos) {
+            LightVertex& to = lv[pos];
+            LightVertex& from = lv[pos + 1];
+            to.incident[0] = -from.incident[0]; to.incident[1] = -from.incident[1]; to.incident[2] = -from.incident[2];
+            if (from.type == VT_DIFFUSE) { from.out[0] = from.incident[0]; from.out[1] = from.incident[1]; from.out[2] = from.incident[2]; }
+        }
+    if (n > 1 && lv[n - 1].type == VT_EMISSION) n -= 1;
+    for (uint32_t i = 0; i < n / 2; ++i) { LightVertex t = lv[i]; lv[i] = lv[n - 1 - i]; lv[n - 1 - i] = t; }
+    ps.n_light = n;
+}
+
+// Stage the visibility rays of connect_paths for camera vertex `conn_cam`, lamp vertices from `conn_light`.
+// Returns the number staged and leaves the next lamp index in ps.conn_next.
+PYR_HD uint32_t stage_connections(const PathState& ps, const BidirCtx& cx, uint32_t from_light, Ray* rays, uint32_t* lamp_index, uint32_t& next) {
+    const CamVertex& c = cx.cv[ps.conn_cam];
+    const v3 from = ld3(c.position), cn = ld3(c.normal);
+    uint32_t n = 0, i = from_light;
+    for (; i < ps.n_light && n < (uint32_t)BDPT_STAGE; ++i) {
+        const LightVertex& v = cx.lv[i];
+        if (v.type == VT_SPECULAR) continue;
+        v3 direction = ld3(v.position) - from;
+        float sq_distance = length2(direction);
+        float distance = sqrtf(sq_distance);
+        v3 dir = direction / distance;
+        if (dot(cn, dir) <= 0.0f) continue;
+        if (dot(ld3(v.normal), -dir) <= 0.0f) continue;
+        if (rays) rays[n] = make_ray(from, dir, 2, distance - DIST_EPSILON);  // blocked <=> a hit closer than distance - eps
+        if (lamp_index) lamp_index[n] = i;
+        ++n;
+    }
+    next = i;
+    return n;
+}
+
+// Advance the connect phase until some rays are staged or every camera vertex is done.
+PYR_HD bool advance_connect(PathState& ps, const BidirCtx& cx, BidirOut& out) {
+    while (ps.conn_cam < ps.n_cam_stored) {
+        uint32_t next;
+        uint32_t n = stage_connections(ps, cx, ps.conn_light, out.shadow, nullptr, next);
+        if (n) { ps.conn_next = next; out.n_shadow = n; out.alive = 1; return true; }
+        ps.conn_cam += 1;
+        ps.conn_light = 0;
+    }
+    return false;
+}
+
+// Camera::is_visible up to the visibility ray, for lamp vertices from `conn_light` (cameras.rs:99-142).
+// `rng` advances exactly as the reference's does; `origins` receives the lens sample per staged ray.
+PYR_HD uint32_t stage_visibility(const SceneView& sc, const PathState& ps, const BidirCtx& cx, Rng& rng, uint32_t from_light, Ray* rays,
+                                 uint32_t* lamp_index, v3* lens, uint32_t& next) {
+    uint32_t n = 0, i = from_light;
+    if (!sc.camera.inv_ok) { next = ps.n_light; return 0; }
+    for (; i < ps.n_light && n < (uint32_t)BDPT_STAGE; ++i) {
+        const LightVertex& v = cx.lv[i];
+        if (v.type != VT_DIFFUSE) continue;
+        const v3 target = ld3(v.position);
+        v3 local_target = transform_point(sc.camera.inv, target);
+        if (local_target.z >= 0.0f) continue;
+        const v3 origin = lens_origin(sc.camera, rng);
+        const v3 world_origin = transform_point(sc.camera.m, origin);
+        const v3 direction = target - world_origin;
+        const float distance = length(direction);
+        if (rays) rays[n] = make_ray(world_origin, direction / distance, 2, distance - DIST_EPSILON);
+        if (lamp_index) lamp_index[n] = i;
+        if (lens) lens[n] = origin;
+        ++n;
+    }
+    next = i;
+    return n;
+}
+
+PYR_HD bool advance_splat(const SceneView& sc, PathState& ps, const BidirCtx& cx, BidirOut& out) {
+    while (ps.conn_light < ps.n_light) {
+        ps.rng_saved = ps.rng;
+        uint32_t next;
+        uint32_t n = stage_visibility(sc, ps, cx, ps.rng, ps.conn_light, out.shadow, nullptr, nullptr, next);
+        if (n) { ps.conn_next = next; out.n_shadow = n; out.alive = 1; return true; }
+        ps.conn_light = next;
+    }
+    return false;
+}
+
+// After the camera path has ended: expose it, then start connecting (or splatting, or finish).
 template <class Add>
-PYR_HD void shade_bidirectional(const SceneView&, PathState&, LightVertex*, const Ray*, const Hit*, BidirOut& bo, Add&, PathCounters&) { bo.alive = 0; bo.n_rays = 0; }
+PYR_HD void end_camera_path(const SceneView& sc, PathState& ps, const BidirCtx& cx, BidirOut& out, Add& add) {
+    expose_path(sc, ps, add);  // bidirectional.rs:245-251
+    ps.conn_cam = 0; ps.conn_light = 0;
+    if (ps.n_light > 0) {
+        ps.phase = PH_CONNECT;
+        if (advance_connect(ps, cx, out)) return;
+        ps.phase = PH_SPLAT;
+        ps.conn_light = 0;
+        if (advance_splat(sc, ps, cx, out)) return;
+    }
+    out.alive = 0;
+}
+
+// -------------------------------------------------------------------------------- generation
+// The start of one `render_tile` iteration (bidirectional.rs:105-176).
+PYR_HD void generate_bidirectional(const SceneView& sc, uint64_t seed, uint32_t tile, uint64_t sample, PathState& ps, const BidirCtx& cx, BidirOut& out) {
+    f4 R[VM_REGS];
+    const TileRec t = sc.tiles[tile];
+    Rng rng = keyed_rng(seed, t.index, sample);
+    float ox = t.size[0] * rng.gen_f32();
+    float oy = t.size[1] * rng.gen_f32();
+    ps.pos[0] = t.from[0] + ox;
+    ps.pos[1] = t.from[1] + oy;
+    const uint32_t S = sc.renderer.spectrum_samples;
+    uint32_t pick = sample_wavelengths(sc, rng, ps.wl);
+    hero_first(ps.wl, S, pick);
+    for (int k = 0; k < MAX_SPECTRUM_SAMPLES; ++k) { ps.bright[k] = 0.0f; ps.refl[k] = 1.0f; }
+    const float wavelength = ps.wl[0];
+    v3 co, cd;
+    camera_ray(sc.camera, ps.pos[0], ps.pos[1], rng, co, cd);
+    st3(ps.cam_o, co); st3(ps.cam_d, cd);
+    ps.tile = tile;
+    ps.flags = 0;
+    ps.n_light = 0; ps.n_cam = 0; ps.n_cam_stored = 0; ps.lamp_bounces = 0; ps.conn_cam = 0; ps.conn_light = 0; ps.conn_next = 0;
+    ps.cam_store_pending = 0; ps.light_events = 0; ps.n_pending = 0; ps.bounce = 0;
+    out.alive = 0; out.has_main = 0; out.n_shadow = 0;
+
+    // World::pick_lamp + Lamp::sample_ray
+    const uint32_t lamp_index = (uint32_t)rng.gen_range_usize(sc.n_lamps);
+    const float lamp_probability = 1.0f / (float)sc.n_lamps;
+    const LampRec lamp = sc.lamps[lamp_index];
+    bool have = false;
+    v3 origin = mk3(0, 0, 0), direction = mk3(0, 0, 0), normal = mk3(0, 0, 0);
+    float weight = 0.0f, material_probability = 1.0f, tex[2] = {0.0f, 0.0f};
+    int32_t color = -1;
+    bool dispersed = false;
+    if (lamp.kind == LAMP_POINT) {
+        direction = sample_sphere(rng);
+        origin = ld3(lamp.v);
+        weight = 4.0f * PYR_PI;
+        color = lamp.color_program;
+        normal = direction;
+        have = true;
+    } else if (lamp.kind == LAMP_SHAPE) {
+        const Prim pr = sc.prims[lamp.rank];
+        float u, v;
+        prim_sample_point(pr, rng, origin, u, v);
+        Surface s;
+        prim_point_surface(sc, pr, lamp.rank, origin, u, v, s);
+        direction = sample_hemisphere(rng, s.normal);
+        weight = prim_surface_area(sc, pr, lamp.rank);
+        const MaterialRec m = sc.materials[s.material];
+        const ComponentRec comp = sc.components[m.emissive_offset + rng.gen_index_u32(m.n_emissive)];  // choose_emissive
+        VmInputs in;
+        in.wavelength = wavelength; in.normal = s.normal; in.incident = -direction; in.tex[0] = s.tex[0]; in.tex[1] = s.tex[1];
+        material_probability = component_probability(sc, comp, in, R, dispersed);
+        color = comp.color_program;
+        normal = s.normal;
+        tex[0] = s.tex[0]; tex[1] = s.tex[1];
+        have = true;
+    }
+    ps.rng = rng;
+    if (!have) {  // a directional lamp has no sample_ray (lamp.rs:86): empty lamp path
+        begin_camera(ps, out);
+        return;
+    }
+    origin = origin + normal * DIST_EPSILON;
+    LightVertex first;
+    st3(first.position, origin); first.type = VT_EMISSION;
+    st3(first.normal, normal); first.color_program = color;
+    first.incident[0] = first.incident[1] = first.incident[2] = 0.0f;
+    first.probability = weight / (lamp_probability * material_probability);
+    first.out[0] = first.out[1] = first.out[2] = 0.0f;
+    first.dispersed = dispersed ? 1u : 0u;
+    first.tex[0] = tex[0]; first.tex[1] = tex[1]; first.pad[0] = first.pad[1] = 0;
+    cx.lv[0] = first;
+    ps.n_light = 1;
+    if (sc.renderer.light_bounces == 0) {
+        finish_lamp_path(ps, cx.lv);
+        begin_camera(ps, out);
+        return;
+    }
+    ps.phase = PH_LAMP;
+    out.has_main = 1;
+    out.main = make_ray(origin, direction, 0, 0.0f);
+    out.alive = 1;
+}
+
+// -------------------------------------------------------------------------------- the per-iteration step
+// One iteration of `trace(&mut lamp_path, .., light_bounces, 0)` (tracer.rs:221-343 with light_samples = 0:
+// sample_light stays true, trace_direct still draws its lamp pick for the first two diffuse events).
+PYR_HD bool lamp_step(const SceneView& sc, PathState& ps, const BidirCtx& cx, const Ray& ray, const Hit& h, BidirOut& out, PathCounters& pc) {
+    f4 R[VM_REGS];
+    const v3 o = ld3(ray.o), d = ld3(ray.d);
+    const float wavelength = ps.wl[0];
+    LightVertex nv;
+    nv.pad[0] = nv.pad[1] = 0;
+    st3(nv.incident, d);
+    nv.out[0] = nv.out[1] = nv.out[2] = 0.0f;
+    if (h.kind == KIND_MISS) {
+        nv.type = VT_EMISSION; nv.dispersed = 0;
+        nv.color_program = directional_color(sc, d, sc.sky_program);
+        st3(nv.position, d * PYR_INF); st3(nv.normal, -d);
+        nv.tex[0] = nv.tex[1] = 0.0f; nv.probability = 1.0f;
+        cx.lv[ps.n_light++] = nv;
+        return false;
+    }
+    Surface s;
+    hit_surface(sc, o, d, h, s, pc.de_evals, pc.de_iters);
+    const v3 normal = apply_normal_map(sc, s, d, R);
+    const MaterialRec mat = sc.materials[s.material];
+    const ComponentRec comp = sc.components[mat.comp_offset + ps.rng.gen_index_u32(mat.n_components)];
+    VmInputs pin;
+    pin.wavelength = wavelength; pin.normal = normal; pin.incident = d; pin.tex[0] = s.tex[0]; pin.tex[1] = s.tex[1];
+    bool normal_dispersed;
+    const float component_prob = component_probability(sc, comp, pin, R, normal_dispersed);
+    const Scatter sct = scatter(comp, d, normal, wavelength, ps.rng);
+    st3(nv.position, s.position); st3(nv.normal, normal);
+    nv.tex[0] = s.tex[0]; nv.tex[1] = s.tex[1];
+    nv.color_program = comp.color_program;
+    if (sct.emitted) {
+        nv.type = VT_EMISSION; nv.dispersed = normal_dispersed ? 1u : 0u; nv.probability = component_prob;
+        cx.lv[ps.n_light++] = nv;
+        return false;
+    }
+    if (ps.light_events < 2 && sct.has_brdf) {
+        ps.light_events += 1;
+        (void)ps.rng.gen_range_usize(sc.n_lamps);  // trace_direct's World::pick_lamp, with zero samples
+    }
+    nv.type = sct.has_brdf ? VT_DIFFUSE : VT_SPECULAR;
+    st3(nv.out, sct.out);
+    nv.dispersed = (sct.dispersed || normal_dispersed) ? 1u : 0u;
+    nv.probability = sct.probability * component_prob;
+    cx.lv[ps.n_light++] = nv;
+    ps.lamp_bounces += 1;
+    if (ps.lamp_bounces < sc.renderer.light_bounces) {
+        out.has_main = 1;
+        out.main = make_ray(s.position, sct.out, 0, 0.0f);
+        out.alive = 1;
+        return true;
+    }
+    return false;
+}
+
+template <class Add>
+PYR_HD void shade_bidirectional(const SceneView& sc, PathState& ps, const BidirCtx& cx, const Ray* main_ray, const Hit* main_hit,
+                                const Ray* shadow_rays, const Hit* shadow_hits, BidirOut& out, Add& add, PathCounters& pc) {
+    out.alive = 0; out.has_main = 0; out.n_shadow = 0;
+    const uint32_t S = sc.renderer.spectrum_samples;
+    if (ps.phase == PH_LAMP) {
+        if (lamp_step(sc, ps, cx, *main_ray, *main_hit, out, pc)) return;
+        finish_lamp_path(ps, cx.lv);
+        ps.light_events = 0;
+        begin_camera(ps, out);
+        return;
+    }
+    if (ps.phase == PH_CAMERA) {
+        ShadeOut so;
+        CameraHooks hooks{cx};
+        const bool more = camera_step(sc, ps, main_ray, main_hit, shadow_rays, shadow_hits, so, pc, hooks);
+        if (more) {
+            out.alive = 1; out.has_main = so.has_main; out.main = so.main; out.n_shadow = so.n_shadow;
+            for (uint32_t j = 0; j < so.n_shadow; ++j) out.shadow[j] = so.shadow[j];
+            return;
+        }
+        end_camera_path(sc, ps, cx, out, add);
+        return;
+    }
+    f4 R[VM_REGS];
+    uint32_t lamp_index[BDPT_STAGE];
+    float bright[MAX_SPECTRUM_SAMPLES], refl[MAX_SPECTRUM_SAMPLES];
+    if (ps.phase == PH_CONNECT) {  // evaluate the connections whose visibility rays were just traced
+        uint32_t next;
+        const uint32_t n = stage_connections(ps, cx, ps.conn_light, nullptr, lamp_index, next);
+        const CamVertex c = cx.cv[ps.conn_cam];
+        const v3 from = ld3(c.position), cn = ld3(c.normal);
+        const float weight = 1.0f / (float)(ps.n_cam * ps.n_light);  // bidirectional.rs:217-218
+        for (uint32_t j = 0; j < n; ++j) {
+            if (shadow_hits[j].kind != KIND_MISS) continue;
+            const LightVertex v = cx.lv[lamp_index[j]];
+            v3 direction = ld3(v.position) - from;
+            float sq_distance = length2(direction);
+            float distance = sqrtf(sq_distance);
+            v3 dir = direction / distance;
+            float cos_out = fabsf(dot(cn, dir));
+            float cos_in = fabsf(dot(ld3(v.normal), -dir));
+            float brdf_out = (2.0f * fabsf(dot(dir, cn))) / c.brdf;
+            float scale = cos_in * cos_out * brdf_out / (2.0f * PYR_PI * sq_distance);
+            float brdf_in = vertex_brdf(v) / vertex_brdf(v);
+            for (uint32_t k = 0; k < S; ++k) { bright[k] = c.bright[k]; refl[k] = c.refl[k] * scale; }
+            bool use_additional = c.use_additional != 0;
+            fold_lamp_tail(sc, cx.lv, lamp_index[j], ps.n_light, ps.wl, use_additional, bright, refl, brdf_in, R);
+            film_expose(sc.film, ps.pos[0], ps.pos[1], bright[0], ps.wl[0], weight, add);
+            if (use_additional)
+                for (uint32_t k = 1; k < S; ++k) film_expose(sc.film, ps.pos[0], ps.pos[1], bright[k], ps.wl[k], weight, add);
+        }
+        ps.conn_light = ps.conn_next;
+        if (ps.conn_light >= ps.n_light) { ps.conn_cam += 1; ps.conn_light = 0; }
+        if (advance_connect(ps, cx, out)) return;
+        ps.phase = PH_SPLAT;
+        ps.conn_light = 0;
+        if (advance_splat(sc, ps, cx, out)) return;
+        out.alive = 0;
+        return;
+    }
+    // PH_SPLAT: evaluate the light-traced samples (bidirectional.rs:253-306)
+    {
+        v3 lens[BDPT_STAGE];
+        Rng replay = ps.rng_saved;
+        uint32_t next;
+        const uint32_t n = stage_visibility(sc, ps, cx, replay, ps.conn_light, nullptr, lamp_index, lens, next);
+        const float weight = 1.0f / (float)ps.n_light;
+        for (uint32_t j = 0; j < n; ++j) {
+            if (shadow_hits[j].kind != KIND_MISS) continue;
+            const LightVertex v = cx.lv[lamp_index[j]];
+            const v3 target = ld3(v.position);
+            v3 local_target = transform_point(sc.camera.inv, target);
+            const v3 origin = lens[j];
+            local_target.z += sc.camera.focus_distance;
+            const float dist = local_target.z;
+            local_target = local_target - (origin * dist) / sc.camera.focus_distance;
+            local_target.z -= sc.camera.focus_distance;
+            const v3 view_plane_target = (-local_target) / local_target.z;
+            const float px = view_plane_target.x * sc.camera.view_plane, py = (-view_plane_target.y) * sc.camera.view_plane;
+            if (!(px > -1.0f && px < 1.0f && py > -1.0f && py < 1.0f)) continue;
+            const v3 world_origin = ld3(shadow_rays[j].o);
+            const float sq_distance = length2(world_origin - target);
+            const float scale = 1.0f / sq_distance;
+            const float brdf_in = vertex_brdf(v) / vertex_brdf(v);
+            for (uint32_t k = 0; k < S; ++k) { bright[k] = 0.0f; refl[k] = scale; }
+            bool use_additional = true;
+            fold_lamp_tail(sc, cx.lv, lamp_index[j], ps.n_light, ps.wl, use_additional, bright, refl, brdf_in, R);
+            film_expose(sc.film, px, py, bright[0], ps.wl[0], weight, add);
+            if (use_additional)
+                for (uint32_t k = 1; k < S; ++k) film_expose(sc.film, px, py, bright[k], ps.wl[k], weight, add);
+        }
+        ps.conn_light = ps.conn_next;
+        if (advance_splat(sc, ps, cx, out)) return;
+        out.alive = 0;
+    }
+}
 
 }  // namespace pyr

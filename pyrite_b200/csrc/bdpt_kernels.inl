@@ -1,2 +1,51 @@
-// included by kernels.cu inside namespace pyr
-void launch_wave_bidirectional(const SceneView&, const WaveArgs&, cudaStream_t) {}
+// included by kernels.cu inside namespace pyr: the bidirectional wavefront kernel
+namespace {
+
+__global__ void __launch_bounds__(WAVE_THREADS) k_wave_bidirectional(const SceneView sc, const WaveArgs a) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = slot < a.pool;
+    if (slot == 0) *a.trace_cursor = 0;
+    const uint32_t s = valid ? slot : 0;
+    PathState& ps = a.paths[s];
+    BidirCtx cx;
+    cx.lv = a.light_vertices + (size_t)s * a.light_stride;
+    cx.cv = a.cam_vertices + (size_t)s * a.cam_stride;
+    FilmAdd add{a.film};
+    BidirOut out;
+    out.alive = 0; out.has_main = 0; out.n_shadow = 0;
+    PathCounters pc;
+    pc.de_evals = 0; pc.de_iters = 0;
+
+    bool alive = valid && (ps.flags & PS_ALIVE);
+    if (alive) {
+        shade_bidirectional(sc, ps, cx, a.rays_in + ps.ray_base, a.hits_in + ps.ray_base, a.rays_in + a.shadow_offset + ps.shadow_base,
+                            a.hits_in + a.shadow_offset + ps.shadow_base, out, add, pc);
+        alive = out.alive != 0;
+        if (alive) ps.flags |= PS_ALIVE; else ps.flags = 0;
+    }
+    unsigned long long g = 0;
+    if (claim_sample(a.next_sample, a.total_samples, valid && !alive, g)) {
+        uint32_t tile; unsigned long long k;
+        locate_sample(a.tile_first, sc.n_tiles, g, tile, k);
+        generate_bidirectional(sc, a.seed, tile, (uint64_t)a.sample_offset + k * a.sample_stride, ps, cx, out);
+        ps.flags |= PS_ALIVE;
+        alive = true;
+    }
+    const uint32_t n_main = alive ? out.has_main : 0u, n_shadow = alive ? out.n_shadow : 0u;
+    const uint32_t main_at = queue_reserve(a.count_out, n_main);
+    const uint32_t shadow_at = queue_reserve(a.count_out + 1, n_shadow);
+    if (n_main) { ps.ray_base = main_at; store_ray(a.rays_out + main_at, out.main); }
+    if (n_shadow) {
+        ps.shadow_base = shadow_at;
+        for (uint32_t j = 0; j < n_shadow; ++j) store_ray(a.rays_out + a.shadow_offset + shadow_at + j, out.shadow[j]);
+    }
+    if (pc.de_evals) { atomicAdd(&a.counters->de_evals, (unsigned long long)pc.de_evals); atomicAdd(&a.counters->de_iterations, (unsigned long long)pc.de_iters); }
+}
+
+}  // namespace
+
+void launch_wave_bidirectional(const SceneView& sc, const WaveArgs& a, cudaStream_t s) {
+    k_wave_bidirectional<<<(a.pool + WAVE_THREADS - 1) / WAVE_THREADS, WAVE_THREADS, 0, s>>>(sc, a);
+}
+size_t cam_vertex_bytes() { return sizeof(CamVertex); }
+int bdpt_stage_rays() { return BDPT_STAGE; }

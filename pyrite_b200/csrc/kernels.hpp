@@ -9,6 +9,7 @@ namespace pyr {
 
 struct PathState;   // shading.cuh
 struct LightVertex; // bdpt.cuh
+struct CamVertex;
 
 // Device-side work counters (one instance per context).
 struct DeviceCounters {
@@ -32,7 +33,9 @@ struct WaveArgs {
     uint32_t sample_offset, sample_stride;
     float* film;               // (accumulator, weight) pairs
     DeviceCounters* counters;
-    LightVertex* light_vertices;  // bidirectional: pool * MAX_LIGHT_PATH
+    LightVertex* light_vertices;  // bidirectional: pool * light_stride lamp-subpath vertices
+    CamVertex* cam_vertices;      // bidirectional: pool * cam_stride stored camera-subpath vertices
+    uint32_t light_stride, cam_stride;
     uint32_t ray_capacity;
 };
 
@@ -62,6 +65,8 @@ void launch_camera_sample(const SceneView& sc, uint64_t seed, uint32_t tile, uin
 
 size_t path_state_bytes();
 size_t light_vertex_bytes();
+size_t cam_vertex_bytes();
+int bdpt_stage_rays();
 int trace_blocks_per_sm();
 
 }  // namespace pyr

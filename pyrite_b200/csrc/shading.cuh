@@ -29,6 +29,11 @@ struct PathState {
     float bright[MAX_SPECTRUM_SAMPLES];  // Sample::brightness
     float refl[MAX_SPECTRUM_SAMPLES];    // the running reflectance of renderer/algorithm.rs:14-100
     PendingLight pend[MAX_LIGHT_SAMPLES];
+    // bidirectional integrator only (bdpt.cuh)
+    uint32_t phase, n_light, n_cam, n_cam_stored, lamp_bounces, conn_cam, conn_light, conn_next;
+    float cam_o[3], cam_d[3];
+    uint32_t cam_store_pending, pad2;
+    Rng rng_saved;
 };
 
 struct ShadeOut {
@@ -482,9 +487,18 @@ PYR_HD void expose_path(const SceneView& sc, const PathState& ps, Add& add) {
 // `contribute` for that bounce (algorithm.rs:14-100).  `main_ray` / `main_hit`: the path ray of the
 // finished trace pass (valid if PS_HAS_MAIN); `shadow_rays` / `shadow_hits`: its `n_pending`
 // visibility rays.
-template <class Add>
-PYR_HD void shade_simple(const SceneView& sc, PathState& ps, const Ray* main_ray, const Hit* main_hit, const Ray* shadow_rays,
-                         const Hit* shadow_hits, ShadeOut& out, Add& add, PathCounters& pc) {
+//
+// `hooks` lets the bidirectional integrator observe the camera subpath it shares with this one
+// (bidirectional.rs:205 calls the same `trace`): every pushed `Bounce`, and the moment the
+// `contribute` of a bounce is complete.  Returns false when the path has ended.
+struct NoHooks {
+    PYR_HD void contribute_done(PathState&) {}
+    PYR_HD void pushed_emission(PathState&) {}
+    PYR_HD void pushed_surface(PathState&, bool, v3, v3, float) {}
+};
+template <class Hooks>
+PYR_HD bool camera_step(const SceneView& sc, PathState& ps, const Ray* main_ray, const Hit* main_hit, const Ray* shadow_rays,
+                        const Hit* shadow_hits, ShadeOut& out, PathCounters& pc, Hooks& hooks) {
     f4 R[VM_REGS];
     const uint32_t S = sc.renderer.spectrum_samples;
     out.alive = 0; out.has_main = 0; out.n_shadow = 0;
@@ -514,8 +528,9 @@ PYR_HD void shade_simple(const SceneView& sc, PathState& ps, const Ray* main_ray
         for (uint32_t k = 0; k < n; ++k) ps.refl[k] *= ps.pending_brdf;
         ps.flags &= ~PS_PENDING_FOLD;
         ps.n_pending = 0;
+        hooks.contribute_done(ps);
     }
-    if (!(ps.flags & PS_HAS_MAIN)) { expose_path(sc, ps, add); return; }
+    if (!(ps.flags & PS_HAS_MAIN)) return false;
 
     const v3 o = ld3(main_ray->o), d = ld3(main_ray->d);
     const Hit h = *main_hit;
@@ -525,8 +540,8 @@ PYR_HD void shade_simple(const SceneView& sc, PathState& ps, const Ray* main_ray
         if (ps.flags & PS_SAMPLE_LIGHT) color = directional_color(sc, d, color);
         const float tex0[2] = {0.0f, 0.0f};
         add_emission(sc, ps, (ps.flags & PS_USE_ADDITIONAL) ? S : 1u, color, d, -d, tex0, 1.0f, R);
-        expose_path(sc, ps, add);
-        return;
+        hooks.pushed_emission(ps);
+        return false;
     }
     Surface s;
     hit_surface(sc, o, d, h, s, pc.de_evals, pc.de_iters);
@@ -542,9 +557,9 @@ PYR_HD void shade_simple(const SceneView& sc, PathState& ps, const Ray* main_ray
         if (ps.flags & PS_SAMPLE_LIGHT) {
             if (normal_dispersed) ps.flags &= ~PS_USE_ADDITIONAL;
             add_emission(sc, ps, (ps.flags & PS_USE_ADDITIONAL) ? S : 1u, comp.color_program, d, normal, s.tex, component_prob, R);
+            hooks.pushed_emission(ps);
         }
-        expose_path(sc, ps, add);
-        return;
+        return false;
     }
     if (ps.light_events < 2) {
         if (!sct.has_brdf || sc.renderer.light_samples == 0) ps.flags |= PS_SAMPLE_LIGHT; else ps.flags &= ~PS_SAMPLE_LIGHT;
@@ -561,6 +576,7 @@ PYR_HD void shade_simple(const SceneView& sc, PathState& ps, const Ray* main_ray
     ps.flags |= PS_PENDING_FOLD;
     ps.n_pending = out.n_shadow;
     ps.bounce += 1;
+    hooks.pushed_surface(ps, sct.has_brdf, s.position, normal, ps.pending_brdf);
     if (ps.bounce < sc.renderer.bounces) {
         ps.flags |= PS_HAS_MAIN;
         out.has_main = 1;
@@ -568,9 +584,22 @@ PYR_HD void shade_simple(const SceneView& sc, PathState& ps, const Ray* main_ray
     } else {
         ps.flags &= ~PS_HAS_MAIN;
     }
-    if (out.has_main || out.n_shadow) { out.alive = 1; return; }
-    expose_path(sc, ps, add);  // out of bounces with nothing pending
+    if (out.has_main || out.n_shadow) { out.alive = 1; return true; }
+    // out of bounces with nothing pending: this bounce's `contribute` is complete now
+    for (uint32_t k = 0; k < ((ps.flags & PS_USE_ADDITIONAL) ? S : 1u); ++k) ps.refl[k] *= ps.pending_brdf;
+    ps.flags &= ~PS_PENDING_FOLD;
+    hooks.contribute_done(ps);
+    return false;
 }
+
+// The camera-to-light integrator (renderer/simple.rs:78-140): when the path ends, expose it.
+template <class Add>
+PYR_HD void shade_simple(const SceneView& sc, PathState& ps, const Ray* main_ray, const Hit* main_hit, const Ray* shadow_rays,
+                         const Hit* shadow_hits, ShadeOut& out, Add& add, PathCounters& pc) {
+    NoHooks hooks;
+    if (!camera_step(sc, ps, main_ray, main_hit, shadow_rays, shadow_hits, out, pc, hooks)) expose_path(sc, ps, add);
+}
+
 
 // ---------------------------------------------------------------- develop (main.rs:190-238, 313-418)
 struct DevelopParams { float white_max, d65_max, step_size; uint32_t pad; };

@@ -184,13 +184,15 @@ def dragon(width=1920, height=1080, spp=256, integrator="simple", glass=False, m
     }
 
 
-def diamonds(width=512, height=300, spp=200, bounces=256):
+def diamonds(width=512, height=300, spp=200, bounces=256, integrator="simple", light_bounces=8):
     """pyrite/test/diamonds/diamonds.lua (BASELINE config C3 at 1920x1080)."""
     diamond = {"surface": material.refractive(ior=2.37782, dispersion=0.01371, color=1)}
     plexi = {"surface": material.mirror(color=mix(0, 0.2, fresnel(1.1)))}
     return {
         "image": {"width": width, "height": height},
-        "renderer": renderer.simple(pixel_samples=spp, spectrum_samples=1, spectrum_bins=50, tile_size=32, bounces=bounces),
+        "renderer": (renderer.simple(pixel_samples=spp, spectrum_samples=1, spectrum_bins=50, tile_size=32, bounces=bounces)
+                     if integrator == "simple" else
+                     renderer.bidirectional(pixel_samples=spp, spectrum_samples=1, spectrum_bins=50, tile_size=32, bounces=bounces, light_bounces=light_bounces)),
         "camera": camera.perspective(fov=12.5, transform=transform.look_at(**{"from": vector(-6.55068, -8.55076, 4.0),
                                                                                 "to": vector(0.1, 0, 0.1), "up": vector(z=1)}),
                                      focus_distance=11.08, aperture=0.02),
@@ -203,13 +205,14 @@ def diamonds(width=512, height=300, spp=200, bounces=256):
     }
 
 
-def spheres(width=512, height=256, spp=600):
+def spheres(width=512, height=256, spp=600, integrator="simple"):
     """pyrite/test/spheres/spheres.lua"""
     ball = shape.sphere(radius=1.5, position=vector(0, 1.4, 10))
     return {
         "image": {"width": width, "height": height},
         "camera": camera.perspective(fov=53, transform=transform.look_at(**{"from": vector(0, 1, 0), "to": vector(0, 1, 1)})),
-        "renderer": renderer.simple(pixel_samples=spp, spectrum_samples=10, spectrum_bins=50, tile_size=32, light_samples=4),
+        "renderer": (renderer.simple if integrator == "simple" else renderer.bidirectional)(
+            pixel_samples=spp, spectrum_samples=10, spectrum_bins=50, tile_size=32, light_samples=4),
         "world": {"objects": [
             shape.sphere(radius=50.0, position=vector(0, -50, 10), material={"surface": material.diffuse(color=1)}),
             ball.with_(position=ball.position.with_(y=1.5), material={"surface": material.emissive(color=light_source.d65 * 3)}),

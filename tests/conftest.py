@@ -46,10 +46,19 @@ def small_scene_kwargs():
         "snowflake": dict(width=64, height=48, spp=4),
         "fractals": dict(width=48, height=32, spp=2),
         "dragon": dict(width=64, height=48, spp=4, mesh=scenes.dragon_mesh(300, 24)),
+        # bidirectional integrator
+        "bd_cornell": dict(_scene="cornell", integrator="bidirectional", width=48, height=48, spp=4),
+        "bd_cornell_fractal": dict(_scene="cornell", integrator="bidirectional", fractal=True, width=48, height=48, spp=2),
+        "bd_glass_dragon": dict(_scene="dragon", integrator="bidirectional", glass=True, bounces=12, light_bounces=20, width=48, height=32, spp=4,
+                                mesh=scenes.dragon_mesh(300, 24)),
+        "bd_diamonds": dict(_scene="diamonds", integrator="bidirectional", bounces=16, width=48, height=32, spp=4),
+        "bd_spheres": dict(_scene="spheres", integrator="bidirectional", width=48, height=32, spp=4),
+        "bd_c5": dict(_scene="bdpt_cornell_dragon", width=48, height=32, spp=2, mesh=scenes.dragon_mesh(300, 24)),
     }
 
 
 SCENE_NAMES = ["cornell", "spheres", "diamonds", "textures", "rgb_emission", "snowflake", "fractals", "dragon"]
+BIDIR_NAMES = ["bd_cornell", "bd_cornell_fractal", "bd_glass_dragon", "bd_diamonds", "bd_spheres", "bd_c5"]
 MESH_SCENES = ["cornell", "diamonds", "textures", "snowflake", "dragon", "spheres", "rgb_emission"]
 
 _ir_cache = {}
@@ -62,7 +71,8 @@ def scene_ir(name, **override):
     if key not in _ir_cache:
         kw = dict(small_scene_kwargs()[name])
         kw.update(override)
-        _ir_cache[key] = project.serialize_project(scenes.SCENES[name](**kw))
+        fn = scenes.SCENES[kw.pop("_scene", name)]
+        _ir_cache[key] = project.serialize_project(fn(**kw))
     return _ir_cache[key]
 
 

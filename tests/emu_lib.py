@@ -95,9 +95,11 @@ class Emu:
         return hits, {"rays": int(st[0]), "nodes": int(st[1]), "leaves": int(st[2])}
 
     def render(self, seed=1, spp=0, sample_offset=0, sample_stride=1, reset_film=True):
+        before = int(self.L.emu_rays(self.h))
         if self.L.emu_render(self.h, seed, spp, sample_offset, sample_stride, int(reset_film)) != 0:
             raise EmuError(self.L.emu_last_error().decode())
-        return int(self.L.emu_rays(self.h))
+        self.rays_last = int(self.L.emu_rays(self.h)) - before
+        return self.rays_last
 
     def film(self):
         out = np.empty(self.shape + (2,), np.float32)

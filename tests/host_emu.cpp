@@ -95,10 +95,12 @@ int emu_render(void* h, uint64_t seed, uint32_t spp_override, uint32_t offset, u
         HostAdd add{e->film.data()};
         const uint32_t spp = spp_override ? spp_override : sc.renderer.pixel_samples;
         if (stride == 0) stride = 1;
-        std::vector<Ray> rays(1 + MAX_LIGHT_PATH + MAX_LIGHT_SAMPLES);
+        std::vector<Ray> rays(1 + BDPT_STAGE);
         std::vector<Hit> hits(rays.size());
         auto ps = std::make_unique<PathState>();
-        std::vector<LightVertex> lv(MAX_LIGHT_PATH);
+        std::vector<LightVertex> lv(sc.renderer.light_bounces + 1);
+        std::vector<CamVertex> cv(sc.renderer.bounces > 0 ? sc.renderer.bounces : 1);
+        BidirCtx cx{lv.data(), cv.data()};
         for (uint32_t t = 0; t < sc.n_tiles; ++t) {
             const uint64_t iterations = (uint64_t)sc.tiles[t].width * sc.tiles[t].height * spp;
             for (uint64_t i = offset; i < iterations; i += stride) {
@@ -116,10 +118,11 @@ int emu_render(void* h, uint64_t seed, uint32_t spp_override, uint32_t offset, u
                     }
                 } else {
                     BidirOut bo;
-                    generate_bidirectional(sc, seed, t, i, *ps, lv.data(), bo);
+                    generate_bidirectional(sc, seed, t, i, *ps, cx, bo);
                     while (bo.alive) {
-                        for (uint32_t j = 0; j < bo.n_rays; ++j) { trace_ray<false>(sc, bo.rays[j], hits[j], nullptr); ++e->rays; rays[j] = bo.rays[j]; }
-                        shade_bidirectional(sc, *ps, lv.data(), rays.data(), hits.data(), bo, add, pc);
+                        if (bo.has_main) { rays[0] = bo.main; trace_ray<false>(sc, rays[0], hits[0], nullptr); ++e->rays; }
+                        for (uint32_t j = 0; j < bo.n_shadow; ++j) { rays[1 + j] = bo.shadow[j]; trace_ray<false>(sc, rays[1 + j], hits[1 + j], nullptr); ++e->rays; }
+                        shade_bidirectional(sc, *ps, cx, rays.data(), hits.data(), rays.data() + 1, hits.data() + 1, bo, add, pc);
                     }
                 }
             }
