@@ -97,7 +97,7 @@ PYR_HD v3 lens_origin(const CameraRec& cam, Rng& rng) {
     if (cam.aperture > 0.0f) {
         float sqrt_r = sqrtf(cam.aperture * rng.gen_f32());
         float psi = PYR_PI * 2.0f * rng.gen_f32();
-        return mk3(sqrt_r * cosf(psi), sqrt_r * sinf(psi), 0.0f);
+        return mk3(sqrt_r * m_cos(psi), sqrt_r * m_sin(psi), 0.0f);
     }
     return mk3(0, 0, 0);
 }

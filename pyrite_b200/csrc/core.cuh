@@ -18,6 +18,28 @@ namespace pyr {
 #define PYR_INF __builtin_inff()
 #endif
 
+// ---------------------------------------------------------------- libm
+// The reference's f32::sin / cos / acos / atan2 / exp / powf resolve to glibc's float functions, which
+// are correctly rounded in all but rare cases; CUDA's float versions are 1-2 ULP.  On the device the
+// shading-side calls are therefore evaluated in double and rounded once, which reproduces glibc's
+// result for almost every argument and keeps films comparable pixel by pixel.  (The distance
+// estimators keep the float functions: they are the FP32/SFU-bound inner loop of sphere tracing.)
+#if defined(__CUDA_ARCH__)
+PYR_HD float m_sin(float x) { return (float)sin((double)x); }
+PYR_HD float m_cos(float x) { return (float)cos((double)x); }
+PYR_HD float m_acos(float x) { return (float)acos((double)x); }
+PYR_HD float m_atan2(float y, float x) { return (float)atan2((double)y, (double)x); }
+PYR_HD float m_exp(float x) { return (float)exp((double)x); }
+PYR_HD float m_pow(float x, float y) { return (float)pow((double)x, (double)y); }
+#else
+PYR_HD float m_sin(float x) { return sinf(x); }
+PYR_HD float m_cos(float x) { return cosf(x); }
+PYR_HD float m_acos(float x) { return acosf(x); }
+PYR_HD float m_atan2(float y, float x) { return atan2f(y, x); }
+PYR_HD float m_exp(float x) { return expf(x); }
+PYR_HD float m_pow(float x, float y) { return powf(x, y); }
+#endif
+
 // ---------------------------------------------------------------- vectors (cgmath 0.17 order)
 struct v3 { float x, y, z; };
 PYR_HD v3 mk3(float x, float y, float z) { v3 r; r.x = x; r.y = y; r.z = z; return r; }
@@ -221,15 +243,15 @@ PYR_HD v3 sample_cone(Rng& rng, v3 direction, float cos_half) {  // math.rs:125-
     float r1 = PYR_PI * 2.0f * rng.gen_f32();
     float r2 = cos_half + (1.0f - cos_half) * rng.gen_f32();
     float oneminus = sqrtf(1.0f - r2 * r2);
-    return (o1 * cosf(r1) * oneminus + o2 * sinf(r1) * oneminus) + direction * r2;
+    return (o1 * m_cos(r1) * oneminus + o2 * m_sin(r1) * oneminus) + direction * r2;
 }
 PYR_HD float solid_angle(float cos_half) { return cos_half >= 1.0f ? 0.0f : 2.0f * PYR_PI * (1.0f - cos_half); }  // math.rs:139-145
 PYR_HD v3 sample_sphere(Rng& rng) {  // math.rs:147-153
     float u = rng.gen_f32();
     float v = rng.gen_f32();
     float theta = 2.0f * PYR_PI * u;
-    float phi = acosf(2.0f * v - 1.0f);
-    return mk3(sinf(phi) * cosf(theta), sinf(phi) * sinf(theta), cosf(phi));
+    float phi = m_acos(2.0f * v - 1.0f);
+    return mk3(m_sin(phi) * m_cos(theta), m_sin(phi) * m_sin(theta), m_cos(phi));
 }
 PYR_HD v3 sample_hemisphere(Rng& rng, v3 direction) {  // math.rs:155-164
     v3 s = sample_sphere(rng);
@@ -260,7 +282,7 @@ PYR_HD float blackbody(float wavelength, float temperature) {  // math.rs:177-18
     float a4 = a2 * a2;
     float p5 = 1.0f / (wavelength * a4);
     float power_term = 3.74183e-16f * p5;
-    return power_term / (expf(1.4388e-2f / (wavelength * temperature)) - 1.0f);
+    return power_term / (m_exp(1.4388e-2f / (wavelength * temperature)) - 1.0f);
 }
 
 // ---------------------------------------------------------------- spectra and textures

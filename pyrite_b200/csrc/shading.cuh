@@ -74,7 +74,7 @@ PYR_HD void camera_ray(const CameraRec& cam, float tx, float ty, Rng& rng, v3& o
     if (cam.aperture > 0.0f) {
         float sqrt_r = sqrtf(cam.aperture * rng.gen_f32());
         float psi = PYR_PI * 2.0f * rng.gen_f32();
-        origin = mk3(sqrt_r * cosf(psi), sqrt_r * sinf(psi), 0.0f);
+        origin = mk3(sqrt_r * m_cos(psi), sqrt_r * m_sin(psi), 0.0f);
         direction = target - origin;
     }
     origin_out = transform_point(cam.m, origin);
@@ -145,17 +145,17 @@ PYR_HD void triangle_surface(const SceneView& sc, uint32_t rank, float u, float 
 }
 PYR_HD void sphere_surface(const Prim& pr, v3 position, bool want_frame, Surface& s) {
     v3 normal = normalize(position - prim_v1(pr));
-    float latitude = acosf(normal.y);
-    float longitude = atan2f(normal.x, normal.z);
+    float latitude = m_acos(normal.y);
+    float longitude = m_atan2(normal.x, normal.z);
     s.normal = normal;
     float tx = longitude * PYR_FRAC_1_PI * 0.5f, ty = 1.0f - (latitude * PYR_FRAC_1_PI);
     s.tex[0] = tx / pr.b.x;
     s.tex[1] = ty / pr.b.y;
     if (want_frame) {
         // Matrix3::from_angle_y(longitude) * Matrix3::from_angle_x(latitude - pi/2)
-        float sy = sinf(longitude), cy = cosf(longitude);
+        float sy = m_sin(longitude), cy = m_cos(longitude);
         float a = latitude - PYR_PI * 0.5f;
-        float sx = sinf(a), cx = cosf(a);
+        float sx = m_sin(a), cx = m_cos(a);
         v3 yc0 = mk3(cy, 0, -sy), yc1 = mk3(0, 1, 0), yc2 = mk3(sy, 0, cy);     // columns of Ry
         v3 xc0 = mk3(1, 0, 0), xc1 = mk3(0, cx, sx), xc2 = mk3(0, -sx, cx);     // columns of Rx
         v3 r0 = mk3(yc0.x, yc1.x, yc2.x), r1 = mk3(yc0.y, yc1.y, yc2.y), r2 = mk3(yc0.z, yc1.z, yc2.z);  // rows of Ry
@@ -677,7 +677,7 @@ PYR_HD void xyz_to_srgb8(const float* xyz, uint8_t* out) {
         float v = lin[c];
         if (!(v > 0.0f)) v = 0.0f;
         if (v > 1.0f) v = 1.0f;
-        float e = v <= 0.0031308f ? 12.92f * v : 1.055f * powf(v, 1.0f / 2.4f) - 0.055f;
+        float e = v <= 0.0031308f ? 12.92f * v : 1.055f * m_pow(v, 1.0f / 2.4f) - 0.055f;
         float s = e * 255.0f + 0.5f;
         out[c] = (uint8_t)(s < 0.0f ? 0.0f : (s > 255.0f ? 255.0f : s));
     }

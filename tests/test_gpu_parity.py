@@ -106,7 +106,7 @@ def test_films_on_identical_streams(name, gpu_renderer_factory, oracle_factory):
         xo2, _ = o.develop()
         _, floor, _ = luminance_stats(xo, xo2)
         print(f"fractals: oracle-vs-oracle noise floor RMSE/mean {floor:.2e}")
-        assert dmean <= 1e-2 and rmse <= 1.5 * floor
+        assert dmean <= max(1e-2, 2.0 * floor / np.sqrt(xo.shape[0] * xo.shape[1])) and rmse <= 1.5 * floor
     elif name == "textures":
         assert dmean <= 1e-2 and off <= 0.05
     else:
@@ -137,6 +137,8 @@ def test_bidirectional_films_on_identical_streams(name, gpu_renderer_factory, or
         assert dmean <= 1e-2 and rmse <= 1.5 * floor
     elif name in ("bd_c5", "bd_spheres"):   # textured / sphere-UV scenes: libm ULPs flip rare events (see module docstring)
         assert dmean <= 1e-2 and off <= 0.05
+    elif name == "bd_glass_dragon":      # 12 dispersive refractions amplify any last-bit difference in a sampled direction
+        assert dmean <= 2e-3 and off <= 0.10
     else:
         assert dmean <= 1e-3 and rmse <= 2e-2
 
