@@ -64,7 +64,7 @@ struct pyr_ctx {
     DeviceBuffer nodes, prims, tri_shade, tri_frames, planes, marched, materials, components, programs, code, spectra, spectrum_data,
         textures, texels, lamps, tiles, burns, xyz, d65;
     DeviceBuffer film, develop_params, counters, scalars, tile_first;
-    DeviceBuffer paths, rays[2], hits, light_vertices, cam_vertices;
+    DeviceBuffer paths, pend, bidir, rays[2], hits, light_vertices, cam_vertices;
     uint32_t shadow_per_path = 1;
     DeviceBuffer scratch_a, scratch_b;
     uint32_t pool = 0;
@@ -125,6 +125,8 @@ void ensure_pool(pyr_ctx* ctx, uint32_t pool) {
     ctx->shadow_per_path = bidir ? (uint32_t)bdpt_stage_rays() : std::max<uint32_t>(R.light_samples, 1);
     const size_t ray_cap = (size_t)pool * (1 + ctx->shadow_per_path);
     ctx->paths.ensure((size_t)pool * path_state_bytes());
+    ctx->pend.ensure((size_t)pool * MAX_LIGHT_SAMPLES * pending_light_bytes());
+    if (bidir) ctx->bidir.ensure((size_t)pool * bidir_state_bytes());
     ctx->rays[0].ensure(ray_cap * sizeof(Ray));
     ctx->rays[1].ensure(ray_cap * sizeof(Ray));
     ctx->hits.ensure(ray_cap * sizeof(Hit));
@@ -140,7 +142,7 @@ void ensure_pool(pyr_ctx* ctx, uint32_t pool) {
 uint32_t default_pool(const pyr_ctx* ctx) {
     const RendererRec& R = ctx->view.renderer;
     if (R.algorithm != 1) return 1u << 20;
-    const size_t per_path = path_state_bytes() + (size_t)(R.light_bounces + 1) * light_vertex_bytes() +
+    const size_t per_path = path_state_bytes() + MAX_LIGHT_SAMPLES * pending_light_bytes() + bidir_state_bytes() + (size_t)(R.light_bounces + 1) * light_vertex_bytes() +
                             (size_t)std::max<uint32_t>(R.bounces, 1) * cam_vertex_bytes() + (size_t)(1 + bdpt_stage_rays()) * (2 * sizeof(Ray) + sizeof(Hit));
     size_t pool = (size_t)6 << 30;
     pool /= per_path;
@@ -204,7 +206,7 @@ void pyr_shutdown(pyr_ctx* ctx) {
     DeviceBuffer* all[] = {&ctx->nodes, &ctx->prims, &ctx->tri_shade, &ctx->tri_frames, &ctx->planes, &ctx->marched, &ctx->materials,
                            &ctx->components, &ctx->programs, &ctx->code, &ctx->spectra, &ctx->spectrum_data, &ctx->textures, &ctx->texels,
                            &ctx->lamps, &ctx->tiles, &ctx->burns, &ctx->xyz, &ctx->d65, &ctx->film, &ctx->develop_params, &ctx->counters,
-                           &ctx->scalars, &ctx->tile_first, &ctx->paths, &ctx->rays[0], &ctx->rays[1], &ctx->hits, &ctx->light_vertices, &ctx->cam_vertices,
+                           &ctx->scalars, &ctx->tile_first, &ctx->paths, &ctx->pend, &ctx->bidir, &ctx->rays[0], &ctx->rays[1], &ctx->hits, &ctx->light_vertices, &ctx->cam_vertices,
                            &ctx->scratch_a, &ctx->scratch_b};
     for (DeviceBuffer* b : all) b->release();
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -370,7 +372,7 @@ pyr_status pyr_render(pyr_ctx* ctx, const pyr_render_params* params, pyr_progres
         ensure_pool(ctx, pool);
         if (p.reset_film) CU(cudaMemsetAsync(ctx->film.p, 0, ctx->film_floats() * sizeof(float), s));
         CU(cudaMemsetAsync(ctx->scalars.p, 0, 16 * sizeof(uint32_t), s));
-        launch_pool_reset(ctx->paths.as<PathState>(), pool, s);
+        launch_pool_reset(ctx->paths.as<PathCore>(), pool, s);
 
         const int trace_blocks = ctx->sm_count * trace_blocks_per_sm();
         const int stats = (p.flags & PYR_RENDER_STATS) ? 1 : 0;
@@ -391,7 +393,9 @@ pyr_status pyr_render(pyr_ctx* ctx, const pyr_render_params* params, pyr_progres
                 const int nxt = cur ^ 1;
                 CU(cudaMemsetAsync(ctx->count(nxt), 0, 2 * sizeof(uint32_t), s));
                 WaveArgs a{};
-                a.paths = ctx->paths.as<PathState>();
+                a.paths = ctx->paths.as<PathCore>();
+                a.pend = ctx->pend.as<PendingLight>();
+                a.bidir = ctx->bidir.as<BidirState>();
                 a.pool = pool;
                 a.rays_in = ctx->rays[cur].as<Ray>();
                 a.hits_in = ctx->hits.as<Hit>();

@@ -105,38 +105,38 @@ PYR_HD v3 lens_origin(const CameraRec& cam, Rng& rng) {
 struct CameraHooks {
     BidirCtx cx;
     PYR_HD void contribute_done(PathState& ps) {
-        if (!ps.cam_store_pending) return;
-        CamVertex& c = cx.cv[ps.n_cam_stored - 1];
+        if (!ps.bd->cam_store_pending) return;
+        CamVertex& c = cx.cv[ps.bd->n_cam_stored - 1];
         c.use_additional = (ps.flags & PS_USE_ADDITIONAL) ? 1u : 0u;
         for (int k = 0; k < MAX_SPECTRUM_SAMPLES; ++k) { c.bright[k] = ps.bright[k]; c.refl[k] = ps.refl[k]; }
-        ps.cam_store_pending = 0;
+        ps.bd->cam_store_pending = 0;
     }
-    PYR_HD void pushed_emission(PathState& ps) { ps.n_cam += 1; }
+    PYR_HD void pushed_emission(PathState& ps) { ps.bd->n_cam += 1; }
     PYR_HD void pushed_surface(PathState& ps, bool diffuse, v3 position, v3 normal, float brdf) {
-        ps.n_cam += 1;
+        ps.bd->n_cam += 1;
         if (!diffuse) return;  // connect_paths returns at once for specular bounces (:320-323)
-        CamVertex& c = cx.cv[ps.n_cam_stored++];
+        CamVertex& c = cx.cv[ps.bd->n_cam_stored++];
         st3(c.position, position); st3(c.normal, normal);
         c.brdf = brdf;
-        ps.cam_store_pending = 1;
+        ps.bd->cam_store_pending = 1;
     }
 };
 
 // -------------------------------------------------------------------------------- phase transitions
 PYR_HD void begin_camera(PathState& ps, BidirOut& out) {
-    ps.phase = PH_CAMERA;
+    ps.bd->phase = PH_CAMERA;
     ps.flags |= PS_HAS_MAIN | PS_SAMPLE_LIGHT | PS_USE_ADDITIONAL;
     ps.flags &= ~PS_PENDING_FOLD;
     ps.bounce = 0; ps.light_events = 0; ps.n_pending = 0; ps.pending_brdf = 1.0f;
     out.has_main = 1;
-    out.main = make_ray(ld3(ps.cam_o), ld3(ps.cam_d), 0, 0.0f);
+    out.main = make_ray(ld3(ps.bd->cam_o), ld3(ps.bd->cam_d), 0, 0.0f);
     out.alive = 1;
 }
 
 // The end of the lamp subpath: utils::pairs fix-up (skips the last pair, utils.rs:5-13), drop a trailing
 // emission vertex, reverse (bidirectional.rs:187-202).
 PYR_HD void finish_lamp_path(PathState& ps, LightVertex* lv) {
-    uint32_t n = ps.n_light;
+    uint32_t n = ps.bd->n_light;
     if (n >= 2)
         for (uint32_t pos = 0; pos + 2 < n; ++pos) {
             LightVertex& to = lv[pos];
@@ -146,16 +146,16 @@ PYR_HD void finish_lamp_path(PathState& ps, LightVertex* lv) {
         }
     if (n > 1 && lv[n - 1].type == VT_EMISSION) n -= 1;
     for (uint32_t i = 0; i < n / 2; ++i) { LightVertex t = lv[i]; lv[i] = lv[n - 1 - i]; lv[n - 1 - i] = t; }
-    ps.n_light = n;
+    ps.bd->n_light = n;
 }
 
 // Stage the visibility rays of connect_paths for camera vertex `conn_cam`, lamp vertices from `conn_light`.
-// Returns the number staged and leaves the next lamp index in ps.conn_next.
+// Returns the number staged and leaves the next lamp index in ps.bd->conn_next.
 PYR_HD uint32_t stage_connections(const PathState& ps, const BidirCtx& cx, uint32_t from_light, Ray* rays, uint32_t* lamp_index, uint32_t& next) {
-    const CamVertex& c = cx.cv[ps.conn_cam];
+    const CamVertex& c = cx.cv[ps.bd->conn_cam];
     const v3 from = ld3(c.position), cn = ld3(c.normal);
     uint32_t n = 0, i = from_light;
-    for (; i < ps.n_light && n < (uint32_t)BDPT_STAGE; ++i) {
+    for (; i < ps.bd->n_light && n < (uint32_t)BDPT_STAGE; ++i) {
         const LightVertex& v = cx.lv[i];
         if (v.type == VT_SPECULAR) continue;
         v3 direction = ld3(v.position) - from;
@@ -174,12 +174,12 @@ PYR_HD uint32_t stage_connections(const PathState& ps, const BidirCtx& cx, uint3
 
 // Advance the connect phase until some rays are staged or every camera vertex is done.
 PYR_HD bool advance_connect(PathState& ps, const BidirCtx& cx, BidirOut& out) {
-    while (ps.conn_cam < ps.n_cam_stored) {
+    while (ps.bd->conn_cam < ps.bd->n_cam_stored) {
         uint32_t next;
-        uint32_t n = stage_connections(ps, cx, ps.conn_light, out.shadow, nullptr, next);
-        if (n) { ps.conn_next = next; out.n_shadow = n; out.alive = 1; return true; }
-        ps.conn_cam += 1;
-        ps.conn_light = 0;
+        uint32_t n = stage_connections(ps, cx, ps.bd->conn_light, out.shadow, nullptr, next);
+        if (n) { ps.bd->conn_next = next; out.n_shadow = n; out.alive = 1; return true; }
+        ps.bd->conn_cam += 1;
+        ps.bd->conn_light = 0;
     }
     return false;
 }
@@ -189,8 +189,8 @@ PYR_HD bool advance_connect(PathState& ps, const BidirCtx& cx, BidirOut& out) {
 PYR_HD uint32_t stage_visibility(const SceneView& sc, const PathState& ps, const BidirCtx& cx, Rng& rng, uint32_t from_light, Ray* rays,
                                  uint32_t* lamp_index, v3* lens, uint32_t& next) {
     uint32_t n = 0, i = from_light;
-    if (!sc.camera.inv_ok) { next = ps.n_light; return 0; }
-    for (; i < ps.n_light && n < (uint32_t)BDPT_STAGE; ++i) {
+    if (!sc.camera.inv_ok) { next = ps.bd->n_light; return 0; }
+    for (; i < ps.bd->n_light && n < (uint32_t)BDPT_STAGE; ++i) {
         const LightVertex& v = cx.lv[i];
         if (v.type != VT_DIFFUSE) continue;
         const v3 target = ld3(v.position);
@@ -210,12 +210,12 @@ PYR_HD uint32_t stage_visibility(const SceneView& sc, const PathState& ps, const
 }
 
 PYR_HD bool advance_splat(const SceneView& sc, PathState& ps, const BidirCtx& cx, BidirOut& out) {
-    while (ps.conn_light < ps.n_light) {
-        ps.rng_saved = ps.rng;
+    while (ps.bd->conn_light < ps.bd->n_light) {
+        ps.bd->rng_saved = ps.rng;
         uint32_t next;
-        uint32_t n = stage_visibility(sc, ps, cx, ps.rng, ps.conn_light, out.shadow, nullptr, nullptr, next);
-        if (n) { ps.conn_next = next; out.n_shadow = n; out.alive = 1; return true; }
-        ps.conn_light = next;
+        uint32_t n = stage_visibility(sc, ps, cx, ps.rng, ps.bd->conn_light, out.shadow, nullptr, nullptr, next);
+        if (n) { ps.bd->conn_next = next; out.n_shadow = n; out.alive = 1; return true; }
+        ps.bd->conn_light = next;
     }
     return false;
 }
@@ -224,12 +224,12 @@ PYR_HD bool advance_splat(const SceneView& sc, PathState& ps, const BidirCtx& cx
 template <class Add>
 PYR_HD void end_camera_path(const SceneView& sc, PathState& ps, const BidirCtx& cx, BidirOut& out, Add& add) {
     expose_path(sc, ps, add);  // bidirectional.rs:245-251
-    ps.conn_cam = 0; ps.conn_light = 0;
-    if (ps.n_light > 0) {
-        ps.phase = PH_CONNECT;
+    ps.bd->conn_cam = 0; ps.bd->conn_light = 0;
+    if (ps.bd->n_light > 0) {
+        ps.bd->phase = PH_CONNECT;
         if (advance_connect(ps, cx, out)) return;
-        ps.phase = PH_SPLAT;
-        ps.conn_light = 0;
+        ps.bd->phase = PH_SPLAT;
+        ps.bd->conn_light = 0;
         if (advance_splat(sc, ps, cx, out)) return;
     }
     out.alive = 0;
@@ -252,11 +252,11 @@ PYR_HD void generate_bidirectional(const SceneView& sc, uint64_t seed, uint32_t 
     const float wavelength = ps.wl[0];
     v3 co, cd;
     camera_ray(sc.camera, ps.pos[0], ps.pos[1], rng, co, cd);
-    st3(ps.cam_o, co); st3(ps.cam_d, cd);
+    st3(ps.bd->cam_o, co); st3(ps.bd->cam_d, cd);
     ps.tile = tile;
     ps.flags = 0;
-    ps.n_light = 0; ps.n_cam = 0; ps.n_cam_stored = 0; ps.lamp_bounces = 0; ps.conn_cam = 0; ps.conn_light = 0; ps.conn_next = 0;
-    ps.cam_store_pending = 0; ps.light_events = 0; ps.n_pending = 0; ps.bounce = 0;
+    ps.bd->n_light = 0; ps.bd->n_cam = 0; ps.bd->n_cam_stored = 0; ps.bd->lamp_bounces = 0; ps.bd->conn_cam = 0; ps.bd->conn_light = 0; ps.bd->conn_next = 0;
+    ps.bd->cam_store_pending = 0; ps.light_events = 0; ps.n_pending = 0; ps.bounce = 0;
     out.alive = 0; out.has_main = 0; out.n_shadow = 0;
 
     // World::pick_lamp + Lamp::sample_ray
@@ -308,13 +308,13 @@ PYR_HD void generate_bidirectional(const SceneView& sc, uint64_t seed, uint32_t 
     first.dispersed = dispersed ? 1u : 0u;
     first.tex[0] = tex[0]; first.tex[1] = tex[1]; first.pad[0] = first.pad[1] = 0;
     cx.lv[0] = first;
-    ps.n_light = 1;
+    ps.bd->n_light = 1;
     if (sc.renderer.light_bounces == 0) {
         finish_lamp_path(ps, cx.lv);
         begin_camera(ps, out);
         return;
     }
-    ps.phase = PH_LAMP;
+    ps.bd->phase = PH_LAMP;
     out.has_main = 1;
     out.main = make_ray(origin, direction, 0, 0.0f);
     out.alive = 1;
@@ -336,7 +336,7 @@ PYR_HD bool lamp_step(const SceneView& sc, PathState& ps, const BidirCtx& cx, co
         nv.color_program = directional_color(sc, d, sc.sky_program);
         st3(nv.position, d * PYR_INF); st3(nv.normal, -d);
         nv.tex[0] = nv.tex[1] = 0.0f; nv.probability = 1.0f;
-        cx.lv[ps.n_light++] = nv;
+        cx.lv[ps.bd->n_light++] = nv;
         return false;
     }
     Surface s;
@@ -354,7 +354,7 @@ PYR_HD bool lamp_step(const SceneView& sc, PathState& ps, const BidirCtx& cx, co
     nv.color_program = comp.color_program;
     if (sct.emitted) {
         nv.type = VT_EMISSION; nv.dispersed = normal_dispersed ? 1u : 0u; nv.probability = component_prob;
-        cx.lv[ps.n_light++] = nv;
+        cx.lv[ps.bd->n_light++] = nv;
         return false;
     }
     if (ps.light_events < 2 && sct.has_brdf) {
@@ -365,9 +365,9 @@ PYR_HD bool lamp_step(const SceneView& sc, PathState& ps, const BidirCtx& cx, co
     st3(nv.out, sct.out);
     nv.dispersed = (sct.dispersed || normal_dispersed) ? 1u : 0u;
     nv.probability = sct.probability * component_prob;
-    cx.lv[ps.n_light++] = nv;
-    ps.lamp_bounces += 1;
-    if (ps.lamp_bounces < sc.renderer.light_bounces) {
+    cx.lv[ps.bd->n_light++] = nv;
+    ps.bd->lamp_bounces += 1;
+    if (ps.bd->lamp_bounces < sc.renderer.light_bounces) {
         out.has_main = 1;
         out.main = make_ray(s.position, sct.out, 0, 0.0f);
         out.alive = 1;
@@ -381,14 +381,14 @@ PYR_HD void shade_bidirectional(const SceneView& sc, PathState& ps, const BidirC
                                 const Ray* shadow_rays, const Hit* shadow_hits, BidirOut& out, Add& add, PathCounters& pc) {
     out.alive = 0; out.has_main = 0; out.n_shadow = 0;
     const uint32_t S = sc.renderer.spectrum_samples;
-    if (ps.phase == PH_LAMP) {
+    if (ps.bd->phase == PH_LAMP) {
         if (lamp_step(sc, ps, cx, *main_ray, *main_hit, out, pc)) return;
         finish_lamp_path(ps, cx.lv);
         ps.light_events = 0;
         begin_camera(ps, out);
         return;
     }
-    if (ps.phase == PH_CAMERA) {
+    if (ps.bd->phase == PH_CAMERA) {
         ShadeOut so;
         CameraHooks hooks{cx};
         const bool more = camera_step(sc, ps, main_ray, main_hit, shadow_rays, shadow_hits, so, pc, hooks);
@@ -403,12 +403,12 @@ PYR_HD void shade_bidirectional(const SceneView& sc, PathState& ps, const BidirC
     f4 R[VM_REGS];
     uint32_t lamp_index[BDPT_STAGE];
     float bright[MAX_SPECTRUM_SAMPLES], refl[MAX_SPECTRUM_SAMPLES];
-    if (ps.phase == PH_CONNECT) {  // evaluate the connections whose visibility rays were just traced
+    if (ps.bd->phase == PH_CONNECT) {  // evaluate the connections whose visibility rays were just traced
         uint32_t next;
-        const uint32_t n = stage_connections(ps, cx, ps.conn_light, nullptr, lamp_index, next);
-        const CamVertex c = cx.cv[ps.conn_cam];
+        const uint32_t n = stage_connections(ps, cx, ps.bd->conn_light, nullptr, lamp_index, next);
+        const CamVertex c = cx.cv[ps.bd->conn_cam];
         const v3 from = ld3(c.position), cn = ld3(c.normal);
-        const float weight = 1.0f / (float)(ps.n_cam * ps.n_light);  // bidirectional.rs:217-218
+        const float weight = 1.0f / (float)(ps.bd->n_cam * ps.bd->n_light);  // bidirectional.rs:217-218
         for (uint32_t j = 0; j < n; ++j) {
             if (shadow_hits[j].kind != KIND_MISS) continue;
             const LightVertex v = cx.lv[lamp_index[j]];
@@ -423,16 +423,16 @@ PYR_HD void shade_bidirectional(const SceneView& sc, PathState& ps, const BidirC
             float brdf_in = vertex_brdf(v) / vertex_brdf(v);
             for (uint32_t k = 0; k < S; ++k) { bright[k] = c.bright[k]; refl[k] = c.refl[k] * scale; }
             bool use_additional = c.use_additional != 0;
-            fold_lamp_tail(sc, cx.lv, lamp_index[j], ps.n_light, ps.wl, use_additional, bright, refl, brdf_in, R);
+            fold_lamp_tail(sc, cx.lv, lamp_index[j], ps.bd->n_light, ps.wl, use_additional, bright, refl, brdf_in, R);
             film_expose(sc.film, ps.pos[0], ps.pos[1], bright[0], ps.wl[0], weight, add);
             if (use_additional)
                 for (uint32_t k = 1; k < S; ++k) film_expose(sc.film, ps.pos[0], ps.pos[1], bright[k], ps.wl[k], weight, add);
         }
-        ps.conn_light = ps.conn_next;
-        if (ps.conn_light >= ps.n_light) { ps.conn_cam += 1; ps.conn_light = 0; }
+        ps.bd->conn_light = ps.bd->conn_next;
+        if (ps.bd->conn_light >= ps.bd->n_light) { ps.bd->conn_cam += 1; ps.bd->conn_light = 0; }
         if (advance_connect(ps, cx, out)) return;
-        ps.phase = PH_SPLAT;
-        ps.conn_light = 0;
+        ps.bd->phase = PH_SPLAT;
+        ps.bd->conn_light = 0;
         if (advance_splat(sc, ps, cx, out)) return;
         out.alive = 0;
         return;
@@ -440,10 +440,10 @@ PYR_HD void shade_bidirectional(const SceneView& sc, PathState& ps, const BidirC
     // PH_SPLAT: evaluate the light-traced samples (bidirectional.rs:253-306)
     {
         v3 lens[BDPT_STAGE];
-        Rng replay = ps.rng_saved;
+        Rng replay = ps.bd->rng_saved;
         uint32_t next;
-        const uint32_t n = stage_visibility(sc, ps, cx, replay, ps.conn_light, nullptr, lamp_index, lens, next);
-        const float weight = 1.0f / (float)ps.n_light;
+        const uint32_t n = stage_visibility(sc, ps, cx, replay, ps.bd->conn_light, nullptr, lamp_index, lens, next);
+        const float weight = 1.0f / (float)ps.bd->n_light;
         for (uint32_t j = 0; j < n; ++j) {
             if (shadow_hits[j].kind != KIND_MISS) continue;
             const LightVertex v = cx.lv[lamp_index[j]];
@@ -463,12 +463,12 @@ PYR_HD void shade_bidirectional(const SceneView& sc, PathState& ps, const BidirC
             const float brdf_in = vertex_brdf(v) / vertex_brdf(v);
             for (uint32_t k = 0; k < S; ++k) { bright[k] = 0.0f; refl[k] = scale; }
             bool use_additional = true;
-            fold_lamp_tail(sc, cx.lv, lamp_index[j], ps.n_light, ps.wl, use_additional, bright, refl, brdf_in, R);
+            fold_lamp_tail(sc, cx.lv, lamp_index[j], ps.bd->n_light, ps.wl, use_additional, bright, refl, brdf_in, R);
             film_expose(sc.film, px, py, bright[0], ps.wl[0], weight, add);
             if (use_additional)
                 for (uint32_t k = 1; k < S; ++k) film_expose(sc.film, px, py, bright[k], ps.wl[k], weight, add);
         }
-        ps.conn_light = ps.conn_next;
+        ps.bd->conn_light = ps.bd->conn_next;
         if (advance_splat(sc, ps, cx, out)) return;
         out.alive = 0;
     }

@@ -6,7 +6,12 @@ __global__ void __launch_bounds__(WAVE_THREADS) k_wave_bidirectional(const Scene
     const bool valid = slot < a.pool;
     if (slot == 0) *a.trace_cursor = 0;
     const uint32_t s = valid ? slot : 0;
-    PathState& ps = a.paths[s];
+    PathState ps;
+    static_cast<PathCore&>(ps) = a.paths[s];
+    ps.pend = a.pend + (size_t)s * MAX_LIGHT_SAMPLES;
+    BidirState bd = a.bidir[s];
+    ps.bd = &bd;
+    const uint32_t flags_in = ps.flags;
     BidirCtx cx;
     cx.lv = a.light_vertices + (size_t)s * a.light_stride;
     cx.cv = a.cam_vertices + (size_t)s * a.cam_stride;
@@ -39,6 +44,7 @@ __global__ void __launch_bounds__(WAVE_THREADS) k_wave_bidirectional(const Scene
         ps.shadow_base = shadow_at;
         for (uint32_t j = 0; j < n_shadow; ++j) store_ray(a.rays_out + a.shadow_offset + shadow_at + j, out.shadow[j]);
     }
+    if (valid && (alive || (flags_in & PS_ALIVE))) { a.paths[slot] = static_cast<const PathCore&>(ps); a.bidir[slot] = bd; }
     if (pc.de_evals) { atomicAdd(&a.counters->de_evals, (unsigned long long)pc.de_evals); atomicAdd(&a.counters->de_iterations, (unsigned long long)pc.de_iters); }
 }
 

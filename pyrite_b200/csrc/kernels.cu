@@ -93,7 +93,7 @@ __device__ __forceinline__ Ray load_ray(const Ray* src) {
     return r;
 }
 
-__global__ void k_pool_reset(PathState* paths, uint32_t pool) {
+__global__ void k_pool_reset(PathCore* paths, uint32_t pool) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < pool) paths[i].flags = 0;
 }
@@ -103,7 +103,11 @@ __global__ void __launch_bounds__(WAVE_THREADS) k_wave_simple(const SceneView sc
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = slot < a.pool;
     if (slot == 0) *a.trace_cursor = 0;
-    PathState& ps = a.paths[valid ? slot : 0];
+    PathState ps;
+    static_cast<PathCore&>(ps) = a.paths[valid ? slot : 0];
+    ps.pend = a.pend + (size_t)(valid ? slot : 0) * MAX_LIGHT_SAMPLES;
+    ps.bd = nullptr;
+    const uint32_t flags_in = ps.flags;
     FilmAdd add{a.film};
     ShadeOut out;
     out.alive = 0; out.has_main = 0; out.n_shadow = 0;
@@ -135,6 +139,7 @@ __global__ void __launch_bounds__(WAVE_THREADS) k_wave_simple(const SceneView sc
         ps.shadow_base = shadow_at;
         for (uint32_t j = 0; j < n_shadow; ++j) store_ray(a.rays_out + a.shadow_offset + shadow_at + j, out.shadow[j]);
     }
+    if (valid && (alive || (flags_in & PS_ALIVE))) a.paths[slot] = static_cast<const PathCore&>(ps);
     if (pc.de_evals) { atomicAdd(&a.counters->de_evals, (unsigned long long)pc.de_evals); atomicAdd(&a.counters->de_iterations, (unsigned long long)pc.de_iters); }
 }
 
@@ -293,7 +298,7 @@ __global__ void k_camera_sample(const SceneView sc, uint64_t seed, uint32_t tile
 
 #include "bdpt_kernels.inl"
 
-void launch_pool_reset(PathState* paths, uint32_t pool, cudaStream_t s) {
+void launch_pool_reset(PathCore* paths, uint32_t pool, cudaStream_t s) {
     if (pool) k_pool_reset<<<(pool + 255) / 256, 256, 0, s>>>(paths, pool);
 }
 void launch_wave_simple(const SceneView& sc, const WaveArgs& a, cudaStream_t s) {
@@ -320,7 +325,9 @@ void launch_camera_sample(const SceneView& sc, uint64_t seed, uint32_t tile, uin
     k_camera_sample<<<1, 1, 0, s>>>(sc, seed, tile, sample, out);
 }
 
-size_t path_state_bytes() { return sizeof(PathState); }
+size_t path_state_bytes() { return sizeof(PathCore); }
+size_t pending_light_bytes() { return sizeof(PendingLight); }
+size_t bidir_state_bytes() { return sizeof(BidirState); }
 size_t light_vertex_bytes() { return sizeof(LightVertex); }
 int trace_blocks_per_sm() {
     int n = 0;

@@ -7,7 +7,9 @@
 
 namespace pyr {
 
-struct PathState;   // shading.cuh
+struct PathCore;    // shading.cuh
+struct PendingLight;
+struct BidirState;
 struct LightVertex; // bdpt.cuh
 struct CamVertex;
 
@@ -18,7 +20,9 @@ struct DeviceCounters {
 
 // Everything one wavefront iteration needs besides the scene.
 struct WaveArgs {
-    PathState* paths;
+    PathCore* paths;
+    PendingLight* pend;        // pool * MAX_LIGHT_SAMPLES
+    BidirState* bidir;         // bidirectional only
     uint32_t pool;
     const Ray* rays_in;        // rays traced in the previous iteration (read by the shade stage)
     const Hit* hits_in;
@@ -50,7 +54,7 @@ struct TraceArgs {
 };
 
 // the wavefront
-void launch_pool_reset(PathState* paths, uint32_t pool, cudaStream_t s);
+void launch_pool_reset(PathCore* paths, uint32_t pool, cudaStream_t s);
 void launch_wave_simple(const SceneView& sc, const WaveArgs& a, cudaStream_t s);
 void launch_wave_bidirectional(const SceneView& sc, const WaveArgs& a, cudaStream_t s);
 void launch_trace(const SceneView& sc, const TraceArgs& a, int grid_blocks, cudaStream_t s);
@@ -64,6 +68,8 @@ void launch_develop(const SceneView& sc, const float* film, const float* develop
 void launch_camera_sample(const SceneView& sc, uint64_t seed, uint32_t tile, uint64_t sample, float* out /* 2 + 8 + 16 + 1 floats */, cudaStream_t s);
 
 size_t path_state_bytes();
+size_t pending_light_bytes();
+size_t bidir_state_bytes();
 size_t light_vertex_bytes();
 size_t cam_vertex_bytes();
 int bdpt_stage_rays();

@@ -17,7 +17,9 @@ struct PendingLight {          // tracer.rs:193-200 `DirectLight`, waiting for i
 };
 enum : uint32_t { PS_USE_ADDITIONAL = 1u, PS_SAMPLE_LIGHT = 2u, PS_HAS_MAIN = 4u, PS_PENDING_FOLD = 8u, PS_ALIVE = 16u };
 
-struct PathState {
+// What is stored per path slot in HBM: 256 B, copied to thread-local storage with 16-byte loads at
+// the start of a wavefront iteration and written back at its end.
+struct alignas(16) PathCore {
     Rng rng;
     float pos[2];              // film position in view coordinates (Tile::sample_point)
     uint32_t tile, flags;
@@ -28,12 +30,18 @@ struct PathState {
     float wl[MAX_SPECTRUM_SAMPLES];      // [0] = hero wavelength, then the additional ones (simple.rs:105-107)
     float bright[MAX_SPECTRUM_SAMPLES];  // Sample::brightness
     float refl[MAX_SPECTRUM_SAMPLES];    // the running reflectance of renderer/algorithm.rs:14-100
-    PendingLight pend[MAX_LIGHT_SAMPLES];
-    // bidirectional integrator only (bdpt.cuh)
+};
+// bidirectional integrator only (bdpt.cuh)
+struct alignas(16) BidirState {
     uint32_t phase, n_light, n_cam, n_cam_stored, lamp_bounces, conn_cam, conn_light, conn_next;
     float cam_o[3], cam_d[3];
     uint32_t cam_store_pending, pad2;
     Rng rng_saved;
+};
+// What the stage functions see: the thread's copy of the core plus where the colder records live.
+struct PathState : PathCore {
+    PendingLight* pend;        // MAX_LIGHT_SAMPLES records per path (HBM)
+    BidirState* bd;
 };
 
 struct ShadeOut {

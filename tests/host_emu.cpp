@@ -98,6 +98,10 @@ int emu_render(void* h, uint64_t seed, uint32_t spp_override, uint32_t offset, u
         std::vector<Ray> rays(1 + BDPT_STAGE);
         std::vector<Hit> hits(rays.size());
         auto ps = std::make_unique<PathState>();
+        std::vector<PendingLight> pend(MAX_LIGHT_SAMPLES);
+        BidirState bd{};
+        ps->pend = pend.data();
+        ps->bd = &bd;
         std::vector<LightVertex> lv(sc.renderer.light_bounces + 1);
         std::vector<CamVertex> cv(sc.renderer.bounces > 0 ? sc.renderer.bounces : 1);
         BidirCtx cx{lv.data(), cv.data()};
