@@ -663,50 +663,65 @@ PYR_HD Prim fetch_prim(const Prim* p) {
     return *p;
 #endif
 }
-// Traversal stack in thread-local storage (host emulation, fallback)
+// Traversal stack in thread-local storage (host emulation, fallback).  An entry is the child code and
+// the entry distance of its box, so that a subtree made irrelevant by a closer hit is dropped at pop
+// time without fetching its node.
 struct LocalStack {
-    int slots[BVH_STACK];
-    PYR_HD void put(int i, int v) { slots[i] = v; }
-    PYR_HD int get(int i) const { return slots[i]; }
+    int codes[BVH_STACK];
+    float dists[BVH_STACK];
+    PYR_HD void put(int i, int code, float dist) { codes[i] = code; dists[i] = dist; }
+    PYR_HD int code(int i) const { return codes[i]; }
+    PYR_HD float dist(int i) const { return dists[i]; }
 };
 
-template <bool STATS, class Stack>
-PYR_HD void trace_ray(const SceneView& sc, const Ray& ray, Hit& hit, TraceStats* stats, Stack& stack) {
-    const v3 o = ld3(ray.o), d = ld3(ray.d);
-    const uint32_t mode = ray.mode;
-    float closest = PYR_INF;
-    // visibility rays: nothing at or beyond `bound` can occlude
-    float bound = PYR_INF;
-    if (mode == 1) bound = ray.limit > 0.0f ? sqrtf(ray.limit) : 0.0f;
-    else if (mode == 2) bound = ray.limit;
-    hit.t = PYR_INF; hit.u = 0; hit.v = 0; hit.rank = 0xFFFFFFFFu; hit.kind = KIND_MISS; hit.nodes = 0; hit.leaves = 0; hit.pad = 0;
-    uint32_t vn = 0, vl = 0, de_evals = 0, de_iters = 0;
+// World::intersect for one ray as an explicit state machine: begin() tests the planes and the root
+// box, every step() processes one interior node or one leaf.  The kernels interleave the steps of 32
+// rays per warp and refill finished lanes; trace_ray() below simply runs it to completion.
+template <bool STATS>
+struct Traversal {
+    v3 o, d, inv;
+    uint32_t mode;
+    float limit, bound, closest;
+    float t, u, v;
+    uint32_t rank, kind;
+    int sp, cur;
+    bool done;
+    uint32_t vn, vl, de_evals, de_iters;
 
-    for (uint32_t i = 0; i < sc.n_planes; ++i) {
-        float t; v3 p;
-        if (plane_test(sc.planes[i], o, d, t, p) && t > DIST_EPSILON && t < closest) {
-            if (mode != 0) {  // visibility rays only report occluders
-                if (occludes(mode, t, ray.limit)) { hit.t = t; hit.rank = i; hit.kind = KIND_PLANE; return; }
-                continue;
+    template <class Stack>
+    PYR_HD void begin(const SceneView& sc, const Ray& ray, Stack& stack) {
+        (void)stack;
+        o = ld3(ray.o); d = ld3(ray.d);
+        mode = ray.mode; limit = ray.limit;
+        closest = PYR_INF;
+        // visibility rays: nothing at or beyond `bound` can occlude
+        bound = PYR_INF;
+        if (mode == 1) bound = limit > 0.0f ? sqrtf(limit) : 0.0f;
+        else if (mode == 2) bound = limit;
+        t = PYR_INF; u = 0; v = 0; rank = 0xFFFFFFFFu; kind = KIND_MISS;
+        vn = 0; vl = 0; de_evals = 0; de_iters = 0;
+        sp = 0; cur = 0; done = true;
+        for (uint32_t i = 0; i < sc.n_planes; ++i) {
+            float pt; v3 p;
+            if (plane_test(sc.planes[i], o, d, pt, p) && pt > DIST_EPSILON && pt < closest) {
+                if (mode != 0) {  // visibility rays only report occluders
+                    if (occludes(mode, pt, limit)) { t = pt; rank = i; kind = KIND_PLANE; return; }
+                    continue;
+                }
+                closest = pt; t = pt; rank = i; kind = KIND_PLANE;
             }
-            closest = t; hit.t = t; hit.rank = i; hit.kind = KIND_PLANE;
         }
-    }
-    if (sc.n_prims == 0) return;
-    const v3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-
-    int sp = 0;
-    int cur;  // child code to process: >= 0 interior node, < 0 leaf
-    {
+        if (sc.n_prims == 0) return;
+        inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
         float dr;
         if (STATS) ++vn;
-        if (!slab_test(ld3(sc.root_lo), ld3(sc.root_hi), o, inv, dr) || dr > closest) {
-            if (STATS && stats) { stats->nodes += vn; }
-            return;
-        }
+        if (!slab_test(ld3(sc.root_lo), ld3(sc.root_hi), o, inv, dr) || dr > closest) return;
         cur = sc.root;
+        done = false;
     }
-    for (;;) {
+
+    template <class Stack>
+    PYR_HD void step(const SceneView& sc, Stack& stack) {
         if (cur >= 0) {
             const Node nd = fetch_node(sc.nodes + cur);
             float d0, d1;
@@ -717,39 +732,51 @@ PYR_HD void trace_ray(const SceneView& sc, const Ray& ray, Hit& hit, TraceStats*
             h1 = h1 && !(d1 > closest) && !(mode != 0 && d1 > bound);
             int c0 = (int)f_bits(nd.n3.x), c1 = (int)f_bits(nd.n3.y);
             if (h0 && h1) {
-                if (d1 < d0) { int t = c0; c0 = c1; c1 = t; }
-                stack.put(sp++, c1);
+                if (d1 < d0) { int tc = c0; c0 = c1; c1 = tc; float td = d0; d0 = d1; d1 = td; }
+                stack.put(sp++, c1, d1);
                 cur = c0;
-                continue;
-            } else if (h0) { cur = c0; continue; }
-            else if (h1) { cur = c1; continue; }
+                return;
+            }
+            if (h0) { cur = c0; return; }
+            if (h1) { cur = c1; return; }
         } else {
-            const uint32_t rank = (uint32_t)~cur;
-            const Prim pr = fetch_prim(sc.prims + rank);
-            const uint32_t kind = prim_kind(pr);
+            const uint32_t r = (uint32_t)~cur;
+            const Prim pr = fetch_prim(sc.prims + r);
+            const uint32_t k = prim_kind(pr);
             if (STATS) ++vl;
-            float t = 0, u = 0, v = 0;
+            float ht = 0, hu = 0, hv = 0;
             bool ok;
-            if (kind == KIND_TRIANGLE) ok = triangle_test(prim_v1(pr), prim_e1(pr), prim_e2(pr), o, d, t, u, v);
-            else if (kind == KIND_SPHERE) { v3 p; ok = sphere_test(prim_v1(pr), pr.a.w, o, d, t, p); }
-            else ok = march_test(sc.marched[f_bits(pr.a.x)], o, d, t, de_evals, de_iters);
-            if (ok && t > DIST_EPSILON) {
+            if (k == KIND_TRIANGLE) ok = triangle_test(prim_v1(pr), prim_e1(pr), prim_e2(pr), o, d, ht, hu, hv);
+            else if (k == KIND_SPHERE) { v3 p; ok = sphere_test(prim_v1(pr), pr.a.w, o, d, ht, p); }
+            else ok = march_test(sc.marched[f_bits(pr.a.x)], o, d, ht, de_evals, de_iters);
+            if (ok && ht > DIST_EPSILON) {
                 if (mode != 0) {
-                    if (occludes(mode, t, ray.limit)) { hit.t = t; hit.u = u; hit.v = v; hit.rank = rank; hit.kind = kind; break; }
-                } else if (t < closest || (t == closest && hit.kind != KIND_PLANE && rank < hit.rank)) {
-                    closest = t; hit.t = t; hit.u = u; hit.v = v; hit.rank = rank; hit.kind = kind;
+                    if (occludes(mode, ht, limit)) { t = ht; u = hu; v = hv; rank = r; kind = k; done = true; return; }
+                } else if (ht < closest || (ht == closest && kind != KIND_PLANE && r < rank)) {
+                    closest = ht; t = ht; u = hu; v = hv; rank = r; kind = k;
                 }
             }
         }
-        // pop: skip subtrees that the shrinking `closest` has made irrelevant is done at push time only
-        // (a stale entry costs one node fetch; its children are culled by the test above)
-        if (sp == 0) break;
-        cur = stack.get(--sp);
+        // pop, dropping entries whose box now starts beyond the closest hit
+        for (;;) {
+            if (sp == 0) { done = true; return; }
+            --sp;
+            if (!(stack.dist(sp) > closest)) { cur = stack.code(sp); return; }
+        }
     }
-    if (STATS) {
-        hit.nodes = vn; hit.leaves = vl;
-        if (stats) { stats->nodes += vn; stats->leaves += vl; stats->de_evals += de_evals; stats->de_iters += de_iters; }
+
+    PYR_HD void finish(Hit& hit, TraceStats* stats) const {
+        hit.t = t; hit.u = u; hit.v = v; hit.rank = rank; hit.kind = kind; hit.nodes = vn; hit.leaves = vl; hit.pad = 0;
+        if (STATS && stats) { stats->nodes += vn; stats->leaves += vl; stats->de_evals += de_evals; stats->de_iters += de_iters; }
     }
+};
+
+template <bool STATS, class Stack>
+PYR_HD void trace_ray(const SceneView& sc, const Ray& ray, Hit& hit, TraceStats* stats, Stack& stack) {
+    Traversal<STATS> tr;
+    tr.begin(sc, ray, stack);
+    while (!tr.done) tr.step(sc, stack);
+    tr.finish(hit, stats);
 }
 
 template <bool STATS>

@@ -11,6 +11,8 @@
 //   k_develop       stage 6 tail: spectral film -> CIE XYZ -> sRGB
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "kernels.hpp"
 #include "shading.cuh"
 #include "bdpt.cuh"
@@ -146,85 +148,77 @@ __global__ void __launch_bounds__(WAVE_THREADS) k_wave_simple(const SceneView sc
 // ------------------------------------------------------------------------------------------
 // Traversal stack: the first SHARED_STACK entries live in shared memory ([entry][thread], no bank
 // conflicts), deeper entries (rare) in local memory.
-constexpr int SHARED_STACK = 24;
+constexpr int SHARED_STACK = 20;
 struct SharedStack {
-    int* base;  // &smem[threadIdx.x]
-    int deep[BVH_STACK - SHARED_STACK];
-    __device__ __forceinline__ void put(int i, int v) { if (i < SHARED_STACK) base[i * TRACE_THREADS] = v; else deep[i - SHARED_STACK] = v; }
-    __device__ __forceinline__ int get(int i) const { return i < SHARED_STACK ? base[i * TRACE_THREADS] : deep[i - SHARED_STACK]; }
+    int* codes;     // &smem_codes[threadIdx.x]
+    float* dists;   // &smem_dists[threadIdx.x]
+    int deep_codes[BVH_STACK - SHARED_STACK];
+    float deep_dists[BVH_STACK - SHARED_STACK];
+    __device__ __forceinline__ void put(int i, int code, float dist) {
+        if (i < SHARED_STACK) { codes[i * TRACE_THREADS] = code; dists[i * TRACE_THREADS] = dist; }
+        else { deep_codes[i - SHARED_STACK] = code; deep_dists[i - SHARED_STACK] = dist; }
+    }
+    __device__ __forceinline__ int code(int i) const { return i < SHARED_STACK ? codes[i * TRACE_THREADS] : deep_codes[i - SHARED_STACK]; }
+    __device__ __forceinline__ float dist(int i) const { return i < SHARED_STACK ? dists[i * TRACE_THREADS] : deep_dists[i - SHARED_STACK]; }
 };
 
-template <bool STATS>
-__global__ void __launch_bounds__(TRACE_THREADS) k_trace(const SceneView sc, const TraceArgs a) {
-    __shared__ int smem_stack[SHARED_STACK * TRACE_THREADS];
+// Persistent warps with lane-level refill: a warp reserves 32 ray indices with one atomicAdd and hands
+// them to its lanes as they finish, so that lanes whose rays end early (misses, occluded visibility
+// rays) do not idle until the longest ray of a packet is done.  Ray index space: [0, n_main) path rays,
+// then n_shadow visibility rays stored from `shadow_offset`.
+template <bool STATS, class Emit>
+__device__ __forceinline__ void trace_persistent(const SceneView& sc, const Ray* rays, uint32_t n_main, uint32_t n_shadow, uint32_t shadow_offset,
+                                                 uint32_t* cursor, DeviceCounters* counters, bool closest_only, uint32_t refill_min, uint32_t steps,
+                                                 Emit& emit) {
+    __shared__ int smem_codes[SHARED_STACK * TRACE_THREADS];
+    __shared__ float smem_dists[SHARED_STACK * TRACE_THREADS];
     SharedStack stack;
-    stack.base = smem_stack + threadIdx.x;
-    const uint32_t n_main = a.count[0], n_shadow = a.count[1];
-    const uint32_t main_packets = (n_main + 31u) >> 5, packets = main_packets + ((n_shadow + 31u) >> 5);
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&a.counters->rays, (unsigned long long)n_main + n_shadow);
+    stack.codes = smem_codes + threadIdx.x;
+    stack.dists = smem_dists + threadIdx.x;
+    const uint32_t total = n_main + n_shadow;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counters->rays, (unsigned long long)total);
     unsigned long long nodes = 0, leaves = 0, evals = 0, iters = 0;
+    Traversal<STATS> tr;
+    tr.done = true;
+    bool has_ray = false;
+    uint32_t ray_at = 0;
+    uint32_t pool_base = 0, pool_left = 0;  // warp-uniform: reserved, not yet assigned ray indices
+    bool exhausted = false;                 // warp-uniform
     for (;;) {
-        uint32_t packet = 0;
-        if (lane_id() == 0) packet = atomicAdd(a.cursor, 1u);
-        packet = __shfl_sync(FULL, packet, 0);
-        if (packet >= packets) break;
-        const bool is_main = packet < main_packets;
-        const uint32_t local = (is_main ? packet : packet - main_packets) * 32u + lane_id();
-        if (local < (is_main ? n_main : n_shadow)) {
-            const uint32_t i = is_main ? local : a.shadow_offset + local;
-            const Ray r = load_ray(a.rays + i);
-            Hit h;
-            TraceStats st;
-            st.nodes = 0; st.leaves = 0; st.de_evals = 0; st.de_iters = 0;
-            trace_ray<STATS>(sc, r, h, STATS ? &st : nullptr, stack);
-            float4* dst = reinterpret_cast<float4*>(a.hits + i);
-            dst[0] = make_float4(h.t, h.u, h.v, __uint_as_float(h.rank));
-            dst[1] = make_float4(__uint_as_float(h.kind), 0.0f, 0.0f, 0.0f);
-            if (STATS) { nodes += st.nodes; leaves += st.leaves; evals += st.de_evals; iters += st.de_iters; }
+        const unsigned idle = __ballot_sync(FULL, !has_ray);
+        if ((uint32_t)__popc(idle) >= refill_min || (idle == FULL)) {
+            if (pool_left == 0 && !exhausted) {
+                uint32_t base = 0;
+                if (lane_id() == 0) base = atomicAdd(cursor, 32u);
+                base = __shfl_sync(FULL, base, 0);
+                if (base >= total) exhausted = true;
+                else { pool_base = base; pool_left = min(32u, total - base); }
+            }
+            if (pool_left) {
+                const uint32_t my = __popc(idle & ((1u << lane_id()) - 1u));
+                const uint32_t taken = min((uint32_t)__popc(idle), pool_left);
+                if (!has_ray && my < taken) {
+                    const uint32_t idx = pool_base + my;
+                    ray_at = idx < n_main ? idx : shadow_offset + (idx - n_main);
+                    Ray r = load_ray(rays + ray_at);
+                    if (closest_only) { r.mode = 0; r.limit = 0.0f; }
+                    tr.begin(sc, r, stack);
+                    has_ray = true;
+                }
+                pool_base += taken;
+                pool_left -= taken;
+            } else if (idle == FULL && exhausted) {
+                break;
+            } else if (exhausted) {
+                refill_min = 33;  // nothing left to hand out: stop checking until the warp drains
+            }
         }
-    }
-    if (STATS) {
-        for (int d = 16; d; d >>= 1) {
-            nodes += __shfl_down_sync(FULL, nodes, d); leaves += __shfl_down_sync(FULL, leaves, d);
-            evals += __shfl_down_sync(FULL, evals, d); iters += __shfl_down_sync(FULL, iters, d);
-        }
-        if (lane_id() == 0) {
-            atomicAdd(&a.counters->nodes_visited, nodes); atomicAdd(&a.counters->leaves_tested, leaves);
-            atomicAdd(&a.counters->de_evals, evals); atomicAdd(&a.counters->de_iterations, iters);
-        }
-    }
-}
-
-// pyr_trace seam: pyr_ray (32 B) in, pyr_hit (20 B) out; always closest-hit mode
-struct AbiHit { uint32_t prim_id, kind; float t, u, v; };
-template <bool STATS>
-__global__ void __launch_bounds__(TRACE_THREADS) k_trace_batch(const SceneView sc, const Ray* rays, uint32_t n, AbiHit* hits, uint32_t* cursor,
-                                                               DeviceCounters* counters) {
-    __shared__ int smem_stack[SHARED_STACK * TRACE_THREADS];
-    SharedStack stack;
-    stack.base = smem_stack + threadIdx.x;
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counters->rays, (unsigned long long)n);
-    unsigned long long nodes = 0, leaves = 0, evals = 0, iters = 0;
-    for (;;) {
-        uint32_t base = 0;
-        if (lane_id() == 0) base = atomicAdd(cursor, 32u);
-        base = __shfl_sync(FULL, base, 0);
-        if (base >= n) break;
-        const uint32_t i = base + lane_id();
-        if (i < n) {
-            Ray r = load_ray(rays + i);
-            r.mode = 0; r.limit = 0.0f;
-            Hit h;
-            TraceStats st;
-            st.nodes = 0; st.leaves = 0; st.de_evals = 0; st.de_iters = 0;
-            trace_ray<STATS>(sc, r, h, STATS ? &st : nullptr, stack);
-            AbiHit o;
-            o.kind = h.kind; o.t = h.t; o.u = h.u; o.v = h.v;
-            if (h.kind == KIND_MISS) o.prim_id = 0xFFFFFFFFu;
-            else if (h.kind == KIND_PLANE) o.prim_id = h.rank;
-            else o.prim_id = prim_object(sc.prims[h.rank]);
-            hits[i] = o;
-            if (STATS) { nodes += st.nodes; leaves += st.leaves; evals += st.de_evals; iters += st.de_iters; }
+        for (uint32_t k = 0; k < steps; ++k)
+            if (has_ray && !tr.done) tr.step(sc, stack);
+        if (has_ray && tr.done) {
+            emit(ray_at, tr);
+            if (STATS) { nodes += tr.vn; leaves += tr.vl; evals += tr.de_evals; iters += tr.de_iters; }
+            has_ray = false;
         }
     }
     if (STATS) {
@@ -237,6 +231,44 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace_batch(const SceneView s
             atomicAdd(&counters->de_evals, evals); atomicAdd(&counters->de_iterations, iters);
         }
     }
+}
+
+struct EmitHit {
+    Hit* hits;
+    template <class T>
+    __device__ __forceinline__ void operator()(uint32_t at, const T& tr) const {
+        float4* dst = reinterpret_cast<float4*>(hits + at);
+        dst[0] = make_float4(tr.t, tr.u, tr.v, __uint_as_float(tr.rank));
+        dst[1] = make_float4(__uint_as_float(tr.kind), 0.0f, 0.0f, 0.0f);
+    }
+};
+
+template <bool STATS>
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace(const SceneView sc, const TraceArgs a) {
+    EmitHit emit{a.hits};
+    trace_persistent<STATS>(sc, a.rays, a.count[0], a.count[1], a.shadow_offset, a.cursor, a.counters, false, a.refill_min, a.steps, emit);
+}
+
+// pyr_trace seam: pyr_ray (32 B) in, pyr_hit (20 B) out; always closest-hit mode
+struct AbiHit { uint32_t prim_id, kind; float t, u, v; };
+struct EmitAbiHit {
+    AbiHit* hits;
+    const Prim* prims;
+    template <class T>
+    __device__ __forceinline__ void operator()(uint32_t at, const T& tr) const {
+        AbiHit o;
+        o.kind = tr.kind; o.t = tr.t; o.u = tr.u; o.v = tr.v;
+        if (tr.kind == KIND_MISS) o.prim_id = 0xFFFFFFFFu;
+        else if (tr.kind == KIND_PLANE) o.prim_id = tr.rank;
+        else o.prim_id = prim_object(prims[tr.rank]);
+        hits[at] = o;
+    }
+};
+template <bool STATS>
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace_batch(const SceneView sc, const Ray* rays, uint32_t n, AbiHit* hits, uint32_t* cursor,
+                                                               DeviceCounters* counters, uint32_t refill_min, uint32_t steps) {
+    EmitAbiHit emit{hits, sc.prims};
+    trace_persistent<STATS>(sc, rays, n, 0u, 0u, cursor, counters, true, refill_min, steps, emit);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -304,14 +336,30 @@ void launch_pool_reset(PathCore* paths, uint32_t pool, cudaStream_t s) {
 void launch_wave_simple(const SceneView& sc, const WaveArgs& a, cudaStream_t s) {
     k_wave_simple<<<(a.pool + WAVE_THREADS - 1) / WAVE_THREADS, WAVE_THREADS, 0, s>>>(sc, a);
 }
-void launch_trace(const SceneView& sc, const TraceArgs& a, int grid_blocks, cudaStream_t s) {
+TraceTuning trace_tuning() {
+    static TraceTuning t = [] {
+        TraceTuning v{8u, 4u};
+        if (const char* e = getenv("PYR_TRACE_REFILL")) v.refill_min = (uint32_t)atoi(e);
+        if (const char* e = getenv("PYR_TRACE_STEPS")) v.steps = (uint32_t)atoi(e);
+        if (v.refill_min < 1) v.refill_min = 1;
+        if (v.refill_min > 32) v.refill_min = 32;
+        if (v.steps < 1) v.steps = 1;
+        return v;
+    }();
+    return t;
+}
+void launch_trace(const SceneView& sc, const TraceArgs& a_in, int grid_blocks, cudaStream_t s) {
+    TraceArgs a = a_in;
+    const TraceTuning t = trace_tuning();
+    a.refill_min = t.refill_min; a.steps = t.steps;
     if (a.stats) k_trace<true><<<grid_blocks, TRACE_THREADS, 0, s>>>(sc, a);
     else k_trace<false><<<grid_blocks, TRACE_THREADS, 0, s>>>(sc, a);
 }
 void launch_trace_batch(const SceneView& sc, const void* rays32, size_t n, void* hits20, uint32_t* cursor, DeviceCounters* counters, int stats,
                         int grid_blocks, cudaStream_t s) {
-    if (stats) k_trace_batch<true><<<grid_blocks, TRACE_THREADS, 0, s>>>(sc, (const Ray*)rays32, (uint32_t)n, (AbiHit*)hits20, cursor, counters);
-    else k_trace_batch<false><<<grid_blocks, TRACE_THREADS, 0, s>>>(sc, (const Ray*)rays32, (uint32_t)n, (AbiHit*)hits20, cursor, counters);
+    const TraceTuning t = trace_tuning();
+    if (stats) k_trace_batch<true><<<grid_blocks, TRACE_THREADS, 0, s>>>(sc, (const Ray*)rays32, (uint32_t)n, (AbiHit*)hits20, cursor, counters, t.refill_min, t.steps);
+    else k_trace_batch<false><<<grid_blocks, TRACE_THREADS, 0, s>>>(sc, (const Ray*)rays32, (uint32_t)n, (AbiHit*)hits20, cursor, counters, t.refill_min, t.steps);
 }
 void launch_film_expose(const SceneView& sc, float* film, const float* positions, const float* samples, size_t n, cudaStream_t s) {
     if (n) k_film_expose<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(sc, film, positions, samples, n);

@@ -51,7 +51,10 @@ struct TraceArgs {
     uint32_t* cursor;        // dynamic work cursor in 32-ray packets (zero on entry)
     DeviceCounters* counters;
     int stats;
+    uint32_t refill_min, steps;  // lane-refill threshold and traversal steps between refill checks (tuning)
 };
+struct TraceTuning { uint32_t refill_min, steps; };
+TraceTuning trace_tuning();
 
 // the wavefront
 void launch_pool_reset(PathCore* paths, uint32_t pool, cudaStream_t s);
