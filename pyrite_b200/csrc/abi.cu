@@ -64,7 +64,7 @@ struct pyr_ctx {
     DeviceBuffer nodes, prims, tri_shade, tri_frames, planes, marched, materials, components, programs, code, spectra, spectrum_data,
         textures, texels, lamps, tiles, burns, xyz, d65;
     DeviceBuffer film, develop_params, counters, scalars, tile_first;
-    DeviceBuffer paths, pend, bidir, rays[2], hits, light_vertices, cam_vertices;
+    DeviceBuffer paths, pend, bidir, rays[2], hits, light_vertices, cam_vertices, bin_count, bin_list;
     uint32_t shadow_per_path = 1;
     DeviceBuffer scratch_a, scratch_b;
     uint32_t pool = 0;
@@ -126,6 +126,8 @@ void ensure_pool(pyr_ctx* ctx, uint32_t pool) {
     const size_t ray_cap = (size_t)pool * (1 + ctx->shadow_per_path);
     ctx->paths.ensure((size_t)pool * path_state_bytes());
     ctx->pend.ensure((size_t)pool * MAX_LIGHT_SAMPLES * pending_light_bytes());
+    ctx->bin_count.ensure(NUM_BINS * sizeof(uint32_t));
+    ctx->bin_list.ensure((size_t)NUM_BINS * pool * sizeof(uint32_t));
     if (bidir) ctx->bidir.ensure((size_t)pool * bidir_state_bytes());
     ctx->rays[0].ensure(ray_cap * sizeof(Ray));
     ctx->rays[1].ensure(ray_cap * sizeof(Ray));
@@ -206,7 +208,7 @@ void pyr_shutdown(pyr_ctx* ctx) {
     DeviceBuffer* all[] = {&ctx->nodes, &ctx->prims, &ctx->tri_shade, &ctx->tri_frames, &ctx->planes, &ctx->marched, &ctx->materials,
                            &ctx->components, &ctx->programs, &ctx->code, &ctx->spectra, &ctx->spectrum_data, &ctx->textures, &ctx->texels,
                            &ctx->lamps, &ctx->tiles, &ctx->burns, &ctx->xyz, &ctx->d65, &ctx->film, &ctx->develop_params, &ctx->counters,
-                           &ctx->scalars, &ctx->tile_first, &ctx->paths, &ctx->pend, &ctx->bidir, &ctx->rays[0], &ctx->rays[1], &ctx->hits, &ctx->light_vertices, &ctx->cam_vertices,
+                           &ctx->scalars, &ctx->tile_first, &ctx->paths, &ctx->pend, &ctx->bidir, &ctx->bin_count, &ctx->bin_list, &ctx->rays[0], &ctx->rays[1], &ctx->hits, &ctx->light_vertices, &ctx->cam_vertices,
                            &ctx->scratch_a, &ctx->scratch_b};
     for (DeviceBuffer* b : all) b->release();
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -417,6 +419,9 @@ pyr_status pyr_render(pyr_ctx* ctx, const pyr_render_params* params, pyr_progres
                 a.cam_stride = std::max<uint32_t>(R.bounces, 1);
                 a.ray_capacity = (uint32_t)(ctx->rays[0].bytes / sizeof(Ray));
                 if (timing) CU(cudaEventRecord(ctx->timing_events[3 * b], s));
+                a.bin_count = ctx->bin_count.as<uint32_t>();
+                a.bin_list = ctx->bin_list.as<uint32_t>();
+                launch_bin(a, ctx->bin_count.as<uint32_t>(), ctx->bin_list.as<uint32_t>(), R.algorithm == 1, s);
                 if (R.algorithm == 0) launch_wave_simple(ctx->view, a, s); else launch_wave_bidirectional(ctx->view, a, s);
                 if (timing) CU(cudaEventRecord(ctx->timing_events[3 * b + 1], s));
                 TraceArgs t{};
@@ -431,7 +436,7 @@ pyr_status pyr_render(pyr_ctx* ctx, const pyr_render_params* params, pyr_progres
                 if (timing) CU(cudaEventRecord(ctx->timing_events[3 * b + 2], s));
                 cur = nxt;
                 ++iterations;
-                launches += 2;
+                launches += 3;
             }
             CU(cudaGetLastError());
             CU(cudaMemcpyAsync(&ctx->pinned[0], ctx->count(cur), 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));

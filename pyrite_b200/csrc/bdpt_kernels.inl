@@ -2,9 +2,10 @@
 namespace {
 
 __global__ void __launch_bounds__(WAVE_THREADS) k_wave_bidirectional(const SceneView sc, const WaveArgs a) {
-    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = slot < a.pool;
-    if (slot == 0) *a.trace_cursor = 0;
+    const uint32_t g_thread = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g_thread == 0) *a.trace_cursor = 0;
+    bool valid;
+    const uint32_t slot = binned_slot(a, g_thread, valid);
     const uint32_t s = valid ? slot : 0;
     PathState ps;
     static_cast<PathCore&>(ps) = a.paths[s];
@@ -27,6 +28,7 @@ __global__ void __launch_bounds__(WAVE_THREADS) k_wave_bidirectional(const Scene
                             a.hits_in + a.shadow_offset + ps.shadow_base, out, add, pc);
         alive = out.alive != 0;
         if (alive) ps.flags |= PS_ALIVE; else ps.flags = 0;
+        if (alive && bd.phase >= PH_CONNECT) ps.n_pending = out.n_shadow;  // k_bin counts the unblocked ones
     }
     unsigned long long g = 0;
     if (claim_sample(a.next_sample, a.total_samples, valid && !alive, g)) {

@@ -101,10 +101,74 @@ __global__ void k_pool_reset(PathCore* paths, uint32_t pool) {
 }
 
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(WAVE_THREADS) k_wave_simple(const SceneView sc, const WaveArgs a) {
+// Shading-state key of a path slot: threads of a warp that share it take the same way through the
+// shade stage (regenerate / miss / surface hit, and the number of unblocked light samples to fold).
+__device__ __forceinline__ uint32_t hit_class(const Hit* hits, uint32_t at) {
+    const uint32_t kind = __ldg(&hits[at].kind);
+    return kind == KIND_MISS ? 1u : (kind == KIND_PLANE ? 2u : (kind == KIND_RAY_MARCHED ? 4u : 3u));
+}
+__device__ __forceinline__ uint32_t unblocked_count(const Hit* hits, uint32_t at, uint32_t n) {
+    uint32_t c = 0;
+    for (uint32_t j = 0; j < n; ++j) c += __ldg(&hits[at + j].kind) == KIND_MISS ? 1u : 0u;
+    return c;
+}
+__global__ void __launch_bounds__(256) k_bin(const PathCore* paths, const BidirState* bidir, uint32_t pool, const Hit* hits, uint32_t shadow_offset,
+                                             uint32_t* bin_count, uint32_t* bin_list) {
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = slot < a.pool;
-    if (slot == 0) *a.trace_cursor = 0;
+    uint32_t key = 0xFFFFFFFFu;
+    if (slot < pool) {
+        const uint4 h0 = reinterpret_cast<const uint4*>(paths + slot)[1];  // pos[2], tile, flags
+        const uint4 h1 = reinterpret_cast<const uint4*>(paths + slot)[2];  // bounce, light_events, n_pending, ray_base
+        const uint4 h2 = reinterpret_cast<const uint4*>(paths + slot)[3];  // pending_brdf, shadow_base
+        const uint32_t flags = h0.w, n_pending = h1.z, ray_base = h1.w, shadow_base = h2.y;
+        if (!(flags & PS_ALIVE)) key = 0;
+        else {
+            const uint32_t phase = bidir ? bidir[slot].phase : PH_CAMERA;
+            if (phase == PH_CAMERA) {
+                const uint32_t hc = (flags & PS_HAS_MAIN) ? hit_class(hits, ray_base) : 0u;
+                const uint32_t lit = (flags & PS_PENDING_FOLD) ? min(unblocked_count(hits, shadow_offset + shadow_base, n_pending), 4u) : 0u;
+                key = 1u + hc * 5u + lit;                                        // 1 .. 25
+            } else if (phase == PH_LAMP) {
+                key = 26u + hit_class(hits, ray_base);                          // 27 .. 30
+            } else {
+                const uint32_t lit = min(unblocked_count(hits, shadow_offset + shadow_base, n_pending), 14u) >> 1;
+                key = (phase == PH_CONNECT ? 32u : 40u) + lit;                 // 32 .. 47
+            }
+        }
+    }
+    const unsigned peers = __match_any_sync(FULL, key);
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if ((int)lane_id() == leader && key != 0xFFFFFFFFu) base = atomicAdd(&bin_count[key], (uint32_t)__popc(peers));
+    base = __shfl_sync(FULL, base, leader);
+    if (key != 0xFFFFFFFFu) bin_list[(size_t)key * pool + base + __popc(peers & ((1u << lane_id()) - 1u))] = slot;
+}
+
+// thread -> slot through the bins: the concatenation of all bins is a permutation of [0, pool)
+__device__ __forceinline__ uint32_t binned_slot(const WaveArgs& a, uint32_t g, bool& valid) {
+    __shared__ uint32_t s_first[NUM_BINS + 1];
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0;
+        for (int b = 0; b < NUM_BINS; ++b) { s_first[b] = acc; acc += a.bin_count[b]; }
+        s_first[NUM_BINS] = acc;
+    }
+    __syncthreads();
+    valid = g < s_first[NUM_BINS];
+    if (!valid) return 0;
+    int lo = 0, hi = NUM_BINS;  // s_first[lo] <= g < s_first[hi]
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (s_first[mid] <= g) lo = mid; else hi = mid;
+    }
+    return a.bin_list[(size_t)lo * a.pool + (g - s_first[lo])];
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(WAVE_THREADS) k_wave_simple(const SceneView sc, const WaveArgs a) {
+    const uint32_t g_thread = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g_thread == 0) *a.trace_cursor = 0;
+    bool valid;
+    const uint32_t slot = binned_slot(a, g_thread, valid);
     PathState ps;
     static_cast<PathCore&>(ps) = a.paths[valid ? slot : 0];
     ps.pend = a.pend + (size_t)(valid ? slot : 0) * MAX_LIGHT_SAMPLES;
@@ -332,6 +396,10 @@ __global__ void k_camera_sample(const SceneView sc, uint64_t seed, uint32_t tile
 
 void launch_pool_reset(PathCore* paths, uint32_t pool, cudaStream_t s) {
     if (pool) k_pool_reset<<<(pool + 255) / 256, 256, 0, s>>>(paths, pool);
+}
+void launch_bin(const WaveArgs& a, uint32_t* bin_count, uint32_t* bin_list, int bidirectional, cudaStream_t s) {
+    cudaMemsetAsync(bin_count, 0, NUM_BINS * sizeof(uint32_t), s);
+    k_bin<<<(a.pool + 255) / 256, 256, 0, s>>>(a.paths, bidirectional ? a.bidir : nullptr, a.pool, a.hits_in, a.shadow_offset, bin_count, bin_list);
 }
 void launch_wave_simple(const SceneView& sc, const WaveArgs& a, cudaStream_t s) {
     k_wave_simple<<<(a.pool + WAVE_THREADS - 1) / WAVE_THREADS, WAVE_THREADS, 0, s>>>(sc, a);

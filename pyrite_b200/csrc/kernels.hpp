@@ -41,7 +41,12 @@ struct WaveArgs {
     CamVertex* cam_vertices;      // bidirectional: pool * cam_stride stored camera-subpath vertices
     uint32_t light_stride, cam_stride;
     uint32_t ray_capacity;
+    // slots grouped by shading state (k_bin): bucket b holds bin_count[b] slot ids at bin_list[b * pool ..]
+    const uint32_t* bin_count;
+    const uint32_t* bin_list;
 };
+constexpr int NUM_BINS = 64;
+void launch_bin(const WaveArgs& a, uint32_t* bin_count, uint32_t* bin_list, int bidirectional, cudaStream_t s);
 
 struct TraceArgs {
     const Ray* rays;
