@@ -64,7 +64,7 @@ struct pyr_ctx {
     DeviceBuffer nodes, prims, tri_shade, tri_frames, planes, marched, materials, components, programs, code, spectra, spectrum_data,
         textures, texels, lamps, tiles, burns, xyz, d65;
     DeviceBuffer film, develop_params, counters, scalars, tile_first;
-    DeviceBuffer paths, pend, bidir, rays[2], hits, light_vertices, cam_vertices, bin_count, bin_list;
+    DeviceBuffer paths, pend, bidir, rays[2], hits, shadow_kinds, light_vertices, cam_vertices, bin_count, bin_list;
     uint32_t shadow_per_path = 1;
     DeviceBuffer scratch_a, scratch_b;
     uint32_t pool = 0;
@@ -131,7 +131,8 @@ void ensure_pool(pyr_ctx* ctx, uint32_t pool) {
     if (bidir) ctx->bidir.ensure((size_t)pool * bidir_state_bytes());
     ctx->rays[0].ensure(ray_cap * sizeof(Ray));
     ctx->rays[1].ensure(ray_cap * sizeof(Ray));
-    ctx->hits.ensure(ray_cap * sizeof(Hit));
+    ctx->hits.ensure((size_t)pool * sizeof(Hit));
+    ctx->shadow_kinds.ensure((size_t)pool * ctx->shadow_per_path * sizeof(uint32_t));
     if (bidir) {
         ctx->light_vertices.ensure((size_t)pool * (R.light_bounces + 1) * light_vertex_bytes());
         ctx->cam_vertices.ensure((size_t)pool * std::max<uint32_t>(R.bounces, 1) * cam_vertex_bytes());
@@ -208,7 +209,7 @@ void pyr_shutdown(pyr_ctx* ctx) {
     DeviceBuffer* all[] = {&ctx->nodes, &ctx->prims, &ctx->tri_shade, &ctx->tri_frames, &ctx->planes, &ctx->marched, &ctx->materials,
                            &ctx->components, &ctx->programs, &ctx->code, &ctx->spectra, &ctx->spectrum_data, &ctx->textures, &ctx->texels,
                            &ctx->lamps, &ctx->tiles, &ctx->burns, &ctx->xyz, &ctx->d65, &ctx->film, &ctx->develop_params, &ctx->counters,
-                           &ctx->scalars, &ctx->tile_first, &ctx->paths, &ctx->pend, &ctx->bidir, &ctx->bin_count, &ctx->bin_list, &ctx->rays[0], &ctx->rays[1], &ctx->hits, &ctx->light_vertices, &ctx->cam_vertices,
+                           &ctx->scalars, &ctx->tile_first, &ctx->paths, &ctx->pend, &ctx->bidir, &ctx->bin_count, &ctx->bin_list, &ctx->rays[0], &ctx->rays[1], &ctx->hits, &ctx->shadow_kinds, &ctx->light_vertices, &ctx->cam_vertices,
                            &ctx->scratch_a, &ctx->scratch_b};
     for (DeviceBuffer* b : all) b->release();
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -401,6 +402,7 @@ pyr_status pyr_render(pyr_ctx* ctx, const pyr_render_params* params, pyr_progres
                 a.pool = pool;
                 a.rays_in = ctx->rays[cur].as<Ray>();
                 a.hits_in = ctx->hits.as<Hit>();
+                a.shadow_kinds_in = ctx->shadow_kinds.as<uint32_t>();
                 a.rays_out = ctx->rays[nxt].as<Ray>();
                 a.count_out = ctx->count(nxt);
                 a.shadow_offset = pool;
@@ -427,6 +429,7 @@ pyr_status pyr_render(pyr_ctx* ctx, const pyr_render_params* params, pyr_progres
                 TraceArgs t{};
                 t.rays = ctx->rays[nxt].as<Ray>();
                 t.hits = ctx->hits.as<Hit>();
+                t.shadow_kinds = ctx->shadow_kinds.as<uint32_t>();
                 t.count = ctx->count(nxt);
                 t.shadow_offset = pool;
                 t.cursor = ctx->cursor();

@@ -66,7 +66,7 @@ PYR_HD float vertex_brdf(const LightVertex& v) {  // BounceType::brdf: lambertia
 }
 
 // `contribute` (renderer/algorithm.rs:14-100) of a lamp-subpath bounce on a detached sample state
-PYR_HD void contribute_vertex(const SceneView& sc, const LightVertex& v, const float* wl, uint32_t n, float* bright, float* refl, f4* R) {
+PYR_HD void contribute_vertex(const SceneView& sc, const LightVertex& v, const float* wl, uint32_t n, float* bright, float* refl, RegFile R) {
     VmInputs in;
     in.wavelength = 0.0f; in.incident = ld3(v.incident); in.normal = ld3(v.normal); in.tex[0] = v.tex[0]; in.tex[1] = v.tex[1];
     float c[MAX_SPECTRUM_SAMPLES];
@@ -81,7 +81,7 @@ PYR_HD void contribute_vertex(const SceneView& sc, const LightVertex& v, const f
 }
 // the fold over lamp_path[first..] shared by connect_paths (:373-389) and light tracing (:276-292)
 PYR_HD void fold_lamp_tail(const SceneView& sc, const LightVertex* lv, uint32_t first, uint32_t n_light, const float* wl, bool& use_additional,
-                           float* bright, float* refl, float brdf_in, f4* R) {
+                           float* bright, float* refl, float brdf_in, RegFile R) {
     const uint32_t S = sc.renderer.spectrum_samples;
     for (uint32_t k = first; k < n_light; ++k) {
         const LightVertex v = lv[k];
@@ -238,7 +238,7 @@ PYR_HD void end_camera_path(const SceneView& sc, PathState& ps, const BidirCtx& 
 // -------------------------------------------------------------------------------- generation
 // The start of one `render_tile` iteration (bidirectional.rs:105-176).
 PYR_HD void generate_bidirectional(const SceneView& sc, uint64_t seed, uint32_t tile, uint64_t sample, PathState& ps, const BidirCtx& cx, BidirOut& out) {
-    f4 R[VM_REGS];
+    PYR_REGFILE(R);
     const TileRec t = sc.tiles[tile];
     Rng rng = keyed_rng(seed, t.index, sample);
     float ox = t.size[0] * rng.gen_f32();
@@ -324,7 +324,7 @@ PYR_HD void generate_bidirectional(const SceneView& sc, uint64_t seed, uint32_t 
 // One iteration of `trace(&mut lamp_path, .., light_bounces, 0)` (tracer.rs:221-343 with light_samples = 0:
 // sample_light stays true, trace_direct still draws its lamp pick for the first two diffuse events).
 PYR_HD bool lamp_step(const SceneView& sc, PathState& ps, const BidirCtx& cx, const Ray& ray, const Hit& h, BidirOut& out, PathCounters& pc) {
-    f4 R[VM_REGS];
+    PYR_REGFILE(R);
     const v3 o = ld3(ray.o), d = ld3(ray.d);
     const float wavelength = ps.wl[0];
     LightVertex nv;
@@ -378,7 +378,7 @@ PYR_HD bool lamp_step(const SceneView& sc, PathState& ps, const BidirCtx& cx, co
 
 template <class Add>
 PYR_HD void shade_bidirectional(const SceneView& sc, PathState& ps, const BidirCtx& cx, const Ray* main_ray, const Hit* main_hit,
-                                const Ray* shadow_rays, const Hit* shadow_hits, BidirOut& out, Add& add, PathCounters& pc) {
+                                const Ray* shadow_rays, const uint32_t* shadow_kinds, BidirOut& out, Add& add, PathCounters& pc) {
     out.alive = 0; out.has_main = 0; out.n_shadow = 0;
     const uint32_t S = sc.renderer.spectrum_samples;
     if (ps.bd->phase == PH_LAMP) {
@@ -390,17 +390,18 @@ PYR_HD void shade_bidirectional(const SceneView& sc, PathState& ps, const BidirC
     }
     if (ps.bd->phase == PH_CAMERA) {
         ShadeOut so;
+        so.stage_base = sc.vm_regs * 128u;
         CameraHooks hooks{cx};
-        const bool more = camera_step(sc, ps, main_ray, main_hit, shadow_rays, shadow_hits, so, pc, hooks);
+        const bool more = camera_step(sc, ps, main_ray, main_hit, shadow_rays, shadow_kinds, so, pc, hooks);
         if (more) {
             out.alive = 1; out.has_main = so.has_main; out.main = so.main; out.n_shadow = so.n_shadow;
-            for (uint32_t j = 0; j < so.n_shadow; ++j) out.shadow[j] = so.shadow[j];
+            for (uint32_t j = 0; j < so.n_shadow; ++j) out.shadow[j] = so.get_shadow(j);
             return;
         }
         end_camera_path(sc, ps, cx, out, add);
         return;
     }
-    f4 R[VM_REGS];
+    PYR_REGFILE(R);
     uint32_t lamp_index[BDPT_STAGE];
     float bright[MAX_SPECTRUM_SAMPLES], refl[MAX_SPECTRUM_SAMPLES];
     if (ps.bd->phase == PH_CONNECT) {  // evaluate the connections whose visibility rays were just traced
@@ -410,7 +411,7 @@ PYR_HD void shade_bidirectional(const SceneView& sc, PathState& ps, const BidirC
         const v3 from = ld3(c.position), cn = ld3(c.normal);
         const float weight = 1.0f / (float)(ps.bd->n_cam * ps.bd->n_light);  // bidirectional.rs:217-218
         for (uint32_t j = 0; j < n; ++j) {
-            if (shadow_hits[j].kind != KIND_MISS) continue;
+            if (shadow_kinds[j] != KIND_MISS) continue;
             const LightVertex v = cx.lv[lamp_index[j]];
             v3 direction = ld3(v.position) - from;
             float sq_distance = length2(direction);
@@ -445,7 +446,7 @@ PYR_HD void shade_bidirectional(const SceneView& sc, PathState& ps, const BidirC
         const uint32_t n = stage_visibility(sc, ps, cx, replay, ps.bd->conn_light, nullptr, lamp_index, lens, next);
         const float weight = 1.0f / (float)ps.bd->n_light;
         for (uint32_t j = 0; j < n; ++j) {
-            if (shadow_hits[j].kind != KIND_MISS) continue;
+            if (shadow_kinds[j] != KIND_MISS) continue;
             const LightVertex v = cx.lv[lamp_index[j]];
             const v3 target = ld3(v.position);
             v3 local_target = transform_point(sc.camera.inv, target);

@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(WAVE_THREADS) k_wave_bidirectional(const Scene
     bool alive = valid && (ps.flags & PS_ALIVE);
     if (alive) {
         shade_bidirectional(sc, ps, cx, a.rays_in + ps.ray_base, a.hits_in + ps.ray_base, a.rays_in + a.shadow_offset + ps.shadow_base,
-                            a.hits_in + a.shadow_offset + ps.shadow_base, out, add, pc);
+                            a.shadow_kinds_in + ps.shadow_base, out, add, pc);
         alive = out.alive != 0;
         if (alive) ps.flags |= PS_ALIVE; else ps.flags = 0;
         if (alive && bd.phase >= PH_CONNECT) ps.n_pending = out.n_shadow;  // k_bin counts the unblocked ones
@@ -53,7 +53,8 @@ __global__ void __launch_bounds__(WAVE_THREADS) k_wave_bidirectional(const Scene
 }  // namespace
 
 void launch_wave_bidirectional(const SceneView& sc, const WaveArgs& a, cudaStream_t s) {
-    k_wave_bidirectional<<<(a.pool + WAVE_THREADS - 1) / WAVE_THREADS, WAVE_THREADS, 0, s>>>(sc, a);
+    cudaFuncSetAttribute(k_wave_bidirectional, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wave_smem(sc));
+    k_wave_bidirectional<<<(a.pool + WAVE_THREADS - 1) / WAVE_THREADS, WAVE_THREADS, wave_smem(sc), s>>>(sc, a);
 }
 size_t cam_vertex_bytes() { return sizeof(CamVertex); }
 int bdpt_stage_rays() { return BDPT_STAGE; }

@@ -373,6 +373,25 @@ PYR_HD float burns_rgb_spectrum(const SceneView& sc, f4 rgb, float wavelength) {
     float rr = rgb.x * r, gg = rgb.y * g, bb = rgb.z * b;
     return (rr + gg) + bb;
 }
+// The VM register file.  In the kernels it lives in dynamic shared memory, [register][thread] (blocks of
+// PYR_BLOCK threads), so that its dynamically indexed accesses stay on chip instead of going through
+// thread-local memory; on the host it is a plain array.
+#if defined(__CUDA_ARCH__)
+constexpr int PYR_BLOCK = 128;
+extern __shared__ float4 pyr_dyn_smem[];  // [0, VM_REGS * PYR_BLOCK): VM registers; the wave kernels stage visibility rays after them
+struct RegFile {
+    f4* base;
+    __device__ __forceinline__ f4& operator[](uint32_t i) const { return base[i * PYR_BLOCK]; }
+};
+#define PYR_REGFILE(R) RegFile R{reinterpret_cast<f4*>(pyr_dyn_smem) + threadIdx.x}
+#else
+struct RegFile {
+    f4* base;
+    f4& operator[](uint32_t i) const { return base[i]; }
+};
+#define PYR_REGFILE(R) f4 R##_storage[VM_REGS]; RegFile R{R##_storage}
+#endif
+
 // One instruction as eight 32-bit words (two 16-byte loads on the device).
 struct InstrWords { uint32_t head, regs, deps, resource, v[4]; };
 PYR_HD InstrWords fetch_instr(const Instr* p) {
@@ -388,7 +407,7 @@ PYR_HD InstrWords fetch_instr(const Instr* p) {
     return w;
 }
 // Runs `count` instructions starting at `code` into R (program/execution_context.rs:69-283).
-PYR_HD_NOINLINE void vm_execute(const SceneView& sc, const Instr* code, uint32_t count, const VmInputs& in, f4* R) {
+PYR_HD_NOINLINE void vm_execute(const SceneView& sc, const Instr* code, uint32_t count, const VmInputs& in, RegFile R) {
     for (uint32_t pc = 0; pc < count; ++pc) {
         const InstrWords I = fetch_instr(code + pc);
         const uint32_t op = I.head & 0xffu, vtype = (I.head >> 8) & 0xffu;
@@ -451,18 +470,18 @@ PYR_HD_NOINLINE void vm_execute(const SceneView& sc, const Instr* code, uint32_t
 // ExecutionContext::run for T = f32 (execution_context.rs:29-56).  `rerun`: the previous call on
 // the same R was the same program with the same inputs except the wavelength, so only the
 // wavelength-dependent instructions run again (MemoizedContext, execution_context.rs:310-342).
-PYR_HD float run_program(const SceneView& sc, const ProgramRec& p, const VmInputs& in, f4* R, bool rerun) {
+PYR_HD float run_program(const SceneView& sc, const ProgramRec& p, const VmInputs& in, RegFile R, bool rerun) {
     if (p.is_constant) return p.value;
     if (rerun) vm_execute(sc, sc.code + p.wl_offset, p.wl_count, in, R);
     else vm_execute(sc, sc.code + p.code_offset, p.n_instr, in, R);
     return R[p.out_reg & (VM_REGS - 1)].x;
 }
-PYR_HD float run_number(const SceneView& sc, int32_t program, const VmInputs& in, f4* R, bool rerun = false) {
+PYR_HD float run_number(const SceneView& sc, int32_t program, const VmInputs& in, RegFile R, bool rerun = false) {
     const ProgramRec p = sc.programs[program];
     return run_program(sc, p, in, R, rerun);
 }
 // ... and T = Vector (the compiler already appended the output conversion, compiler.rs:532-567)
-PYR_HD f4 run_vector(const SceneView& sc, int32_t program, const VmInputs& in, f4* R) {
+PYR_HD f4 run_vector(const SceneView& sc, int32_t program, const VmInputs& in, RegFile R) {
     const ProgramRec p = sc.programs[program];
     if (p.is_constant) return mk4(p.value, p.value, p.value, p.value);
     vm_execute(sc, sc.code + p.code_offset, p.n_instr, in, R);

@@ -183,7 +183,8 @@ struct SceneView {
     const float* burns;           // r, g, b interleaved
     const float* xyz;             // x, y, z interleaved
     const float* d65;
-    uint32_t n_nodes, n_prims, n_planes, n_marched, n_lamps, n_tiles, n_color_textures, pad0;
+    uint32_t n_nodes, n_prims, n_planes, n_marched, n_lamps, n_tiles, n_color_textures;
+    uint32_t vm_regs;             // registers the largest program uses (>= 1): sizes the on-chip register file
     int32_t root;                 // child code of the root: >= 0 interior node, < 0 leaf ~rank; only valid when n_prims > 0
     int32_t sky_program, filter_program, white_program;
     float root_lo[3], root_hi[3];

@@ -24,6 +24,11 @@ namespace {
 constexpr int WAVE_THREADS = 128;
 constexpr int TRACE_THREADS = 128;
 constexpr unsigned FULL = 0xffffffffu;
+// dynamic shared memory, sized by what the scene needs: VM registers (+ visibility-ray staging in the wave kernels)
+inline size_t vm_smem(const SceneView& sc) { return (size_t)sc.vm_regs * WAVE_THREADS * sizeof(float4); }
+inline size_t wave_smem(const SceneView& sc) {
+    return vm_smem(sc) + (size_t)2 * (sc.renderer.light_samples ? sc.renderer.light_samples : 1) * WAVE_THREADS * sizeof(float4);
+}
 
 struct FilmAdd {
     float* film;
@@ -107,12 +112,12 @@ __device__ __forceinline__ uint32_t hit_class(const Hit* hits, uint32_t at) {
     const uint32_t kind = __ldg(&hits[at].kind);
     return kind == KIND_MISS ? 1u : (kind == KIND_PLANE ? 2u : (kind == KIND_RAY_MARCHED ? 4u : 3u));
 }
-__device__ __forceinline__ uint32_t unblocked_count(const Hit* hits, uint32_t at, uint32_t n) {
+__device__ __forceinline__ uint32_t unblocked_count(const uint32_t* kinds, uint32_t at, uint32_t n) {
     uint32_t c = 0;
-    for (uint32_t j = 0; j < n; ++j) c += __ldg(&hits[at + j].kind) == KIND_MISS ? 1u : 0u;
+    for (uint32_t j = 0; j < n; ++j) c += __ldg(&kinds[at + j]) == KIND_MISS ? 1u : 0u;
     return c;
 }
-__global__ void __launch_bounds__(256) k_bin(const PathCore* paths, const BidirState* bidir, uint32_t pool, const Hit* hits, uint32_t shadow_offset,
+__global__ void __launch_bounds__(256) k_bin(const PathCore* paths, const BidirState* bidir, uint32_t pool, const Hit* hits, const uint32_t* shadow_kinds,
                                              uint32_t* bin_count, uint32_t* bin_list) {
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t key = 0xFFFFFFFFu;
@@ -126,12 +131,12 @@ __global__ void __launch_bounds__(256) k_bin(const PathCore* paths, const BidirS
             const uint32_t phase = bidir ? bidir[slot].phase : PH_CAMERA;
             if (phase == PH_CAMERA) {
                 const uint32_t hc = (flags & PS_HAS_MAIN) ? hit_class(hits, ray_base) : 0u;
-                const uint32_t lit = (flags & PS_PENDING_FOLD) ? min(unblocked_count(hits, shadow_offset + shadow_base, n_pending), 4u) : 0u;
+                const uint32_t lit = (flags & PS_PENDING_FOLD) ? min(unblocked_count(shadow_kinds, shadow_base, n_pending), 4u) : 0u;
                 key = 1u + hc * 5u + lit;                                        // 1 .. 25
             } else if (phase == PH_LAMP) {
                 key = 26u + hit_class(hits, ray_base);                          // 27 .. 30
             } else {
-                const uint32_t lit = min(unblocked_count(hits, shadow_offset + shadow_base, n_pending), 14u) >> 1;
+                const uint32_t lit = min(unblocked_count(shadow_kinds, shadow_base, n_pending), 14u) >> 1;
                 key = (phase == PH_CONNECT ? 32u : 40u) + lit;                 // 32 .. 47
             }
         }
@@ -177,13 +182,14 @@ __global__ void __launch_bounds__(WAVE_THREADS) k_wave_simple(const SceneView sc
     FilmAdd add{a.film};
     ShadeOut out;
     out.alive = 0; out.has_main = 0; out.n_shadow = 0;
+    out.stage_base = sc.vm_regs * WAVE_THREADS;
     PathCounters pc;
     pc.de_evals = 0; pc.de_iters = 0;
 
     bool alive = valid && (ps.flags & PS_ALIVE);
     if (alive) {
         shade_simple(sc, ps, a.rays_in + ps.ray_base, a.hits_in + ps.ray_base, a.rays_in + a.shadow_offset + ps.shadow_base,
-                     a.hits_in + a.shadow_offset + ps.shadow_base, out, add, pc);
+                     a.shadow_kinds_in + ps.shadow_base, out, add, pc);
         alive = out.alive != 0;
         if (!alive) ps.flags = 0;
     }
@@ -203,7 +209,7 @@ __global__ void __launch_bounds__(WAVE_THREADS) k_wave_simple(const SceneView sc
     if (n_main) { ps.ray_base = main_at; store_ray(a.rays_out + main_at, out.main); }
     if (n_shadow) {
         ps.shadow_base = shadow_at;
-        for (uint32_t j = 0; j < n_shadow; ++j) store_ray(a.rays_out + a.shadow_offset + shadow_at + j, out.shadow[j]);
+        for (uint32_t j = 0; j < n_shadow; ++j) store_ray(a.rays_out + a.shadow_offset + shadow_at + j, out.get_shadow(j));
     }
     if (valid && (alive || (flags_in & PS_ALIVE))) a.paths[slot] = static_cast<const PathCore&>(ps);
     if (pc.de_evals) { atomicAdd(&a.counters->de_evals, (unsigned long long)pc.de_evals); atomicAdd(&a.counters->de_iterations, (unsigned long long)pc.de_iters); }
@@ -299,8 +305,11 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sc, const Ray*
 
 struct EmitHit {
     Hit* hits;
+    uint32_t* shadow_kinds;
+    uint32_t shadow_offset;
     template <class T>
     __device__ __forceinline__ void operator()(uint32_t at, const T& tr) const {
+        if (at >= shadow_offset) { shadow_kinds[at - shadow_offset] = tr.kind; return; }  // visibility rays only report blocked / unblocked
         float4* dst = reinterpret_cast<float4*>(hits + at);
         dst[0] = make_float4(tr.t, tr.u, tr.v, __uint_as_float(tr.rank));
         dst[1] = make_float4(__uint_as_float(tr.kind), 0.0f, 0.0f, 0.0f);
@@ -309,7 +318,7 @@ struct EmitHit {
 
 template <bool STATS>
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace(const SceneView sc, const TraceArgs a) {
-    EmitHit emit{a.hits};
+    EmitHit emit{a.hits, a.shadow_kinds, a.shadow_offset};
     trace_persistent<STATS>(sc, a.rays, a.count[0], a.count[1], a.shadow_offset, a.cursor, a.counters, false, a.refill_min, a.steps, emit);
 }
 
@@ -399,10 +408,11 @@ void launch_pool_reset(PathCore* paths, uint32_t pool, cudaStream_t s) {
 }
 void launch_bin(const WaveArgs& a, uint32_t* bin_count, uint32_t* bin_list, int bidirectional, cudaStream_t s) {
     cudaMemsetAsync(bin_count, 0, NUM_BINS * sizeof(uint32_t), s);
-    k_bin<<<(a.pool + 255) / 256, 256, 0, s>>>(a.paths, bidirectional ? a.bidir : nullptr, a.pool, a.hits_in, a.shadow_offset, bin_count, bin_list);
+    k_bin<<<(a.pool + 255) / 256, 256, 0, s>>>(a.paths, bidirectional ? a.bidir : nullptr, a.pool, a.hits_in, a.shadow_kinds_in, bin_count, bin_list);
 }
 void launch_wave_simple(const SceneView& sc, const WaveArgs& a, cudaStream_t s) {
-    k_wave_simple<<<(a.pool + WAVE_THREADS - 1) / WAVE_THREADS, WAVE_THREADS, 0, s>>>(sc, a);
+    cudaFuncSetAttribute(k_wave_simple, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wave_smem(sc));
+    k_wave_simple<<<(a.pool + WAVE_THREADS - 1) / WAVE_THREADS, WAVE_THREADS, wave_smem(sc), s>>>(sc, a);
 }
 TraceTuning trace_tuning() {
     static TraceTuning t = [] {
@@ -432,10 +442,10 @@ void launch_trace_batch(const SceneView& sc, const void* rays32, size_t n, void*
 void launch_film_expose(const SceneView& sc, float* film, const float* positions, const float* samples, size_t n, cudaStream_t s) {
     if (n) k_film_expose<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(sc, film, positions, samples, n);
 }
-void launch_white_scan(const SceneView& sc, float* develop_params, cudaStream_t s) { k_white_scan<<<1, 1, 0, s>>>(sc, develop_params); }
+void launch_white_scan(const SceneView& sc, float* develop_params, cudaStream_t s) { k_white_scan<<<1, 1, vm_smem(sc), s>>>(sc, develop_params); }
 void launch_develop(const SceneView& sc, const float* film, const float* develop_params, float step_size, float* xyz, uint8_t* srgb, cudaStream_t s) {
     const uint64_t pixels = (uint64_t)sc.film.width * sc.film.height;
-    k_develop<<<(unsigned)((pixels + 127) / 128), 128, 0, s>>>(sc, film, develop_params, step_size, xyz, srgb);
+    k_develop<<<(unsigned)((pixels + 127) / 128), 128, vm_smem(sc), s>>>(sc, film, develop_params, step_size, xyz, srgb);
 }
 void launch_camera_sample(const SceneView& sc, uint64_t seed, uint32_t tile, uint64_t sample, float* out, cudaStream_t s) {
     k_camera_sample<<<1, 1, 0, s>>>(sc, seed, tile, sample, out);

@@ -26,6 +26,7 @@ struct WaveArgs {
     uint32_t pool;
     const Ray* rays_in;        // rays traced in the previous iteration (read by the shade stage)
     const Hit* hits_in;
+    const uint32_t* shadow_kinds_in;  // hit kind per visibility ray of the previous pass (KIND_MISS = unblocked)
     Ray* rays_out;             // rays emitted by this iteration: path rays in [0, pool), visibility rays from `shadow_offset`
     uint32_t* count_out;       // [0] path rays, [1] visibility rays emitted (device counters, pre-zeroed)
     uint32_t shadow_offset;    // first index of the visibility-ray region in rays / hits
@@ -50,7 +51,8 @@ void launch_bin(const WaveArgs& a, uint32_t* bin_count, uint32_t* bin_list, int 
 
 struct TraceArgs {
     const Ray* rays;
-    Hit* hits;
+    Hit* hits;               // closest-hit records of the path rays
+    uint32_t* shadow_kinds;  // hit kind per visibility ray
     const uint32_t* count;   // device-resident ray counts: [0] path rays, [1] visibility rays
     uint32_t shadow_offset;
     uint32_t* cursor;        // dynamic work cursor in 32-ray packets (zero on entry)

@@ -875,6 +875,10 @@ BakedScene build_scene(const Document& input) {
     sv.n_marched = (uint32_t)out.marched.size();
     sv.n_lamps = (uint32_t)out.lamps.size();
     sv.n_tiles = (uint32_t)out.tiles.size();
+    sv.vm_regs = 1;
+    for (const ProgramRec& pr : out.programs)
+        if (!pr.is_constant)
+            for (uint32_t i = 0; i < pr.n_instr; ++i) sv.vm_regs = std::max<uint32_t>(sv.vm_regs, (uint32_t)out.code[pr.code_offset + i].out + 1);
     (void)float_bits;
     return out;
 }

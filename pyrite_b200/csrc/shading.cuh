@@ -44,10 +44,32 @@ struct PathState : PathCore {
     BidirState* bd;
 };
 
+// What one shade step asks to be traced next.  The visibility rays are staged on chip (dynamic shared
+// memory behind the VM registers, two 16-byte halves per ray, [ray][half][thread]) in the kernels.
 struct ShadeOut {
     uint32_t alive, has_main, n_shadow, pad;
     Ray main;
-    Ray shadow[MAX_LIGHT_SAMPLES];
+#if defined(__CUDA_ARCH__)
+    uint32_t stage_base;  // first float4 of the staging area = vm_regs * PYR_BLOCK
+    __device__ __forceinline__ void put_shadow(uint32_t j, const Ray& r) {
+        float4* s = pyr_dyn_smem + stage_base + (2 * j) * PYR_BLOCK + threadIdx.x;
+        s[0] = make_float4(r.o[0], r.o[1], r.o[2], __uint_as_float(r.mode));
+        s[PYR_BLOCK] = make_float4(r.d[0], r.d[1], r.d[2], r.limit);
+    }
+    __device__ __forceinline__ Ray get_shadow(uint32_t j) const {
+        const float4* s = pyr_dyn_smem + stage_base + (2 * j) * PYR_BLOCK + threadIdx.x;
+        const float4 a = s[0], b = s[PYR_BLOCK];
+        Ray r;
+        r.o[0] = a.x; r.o[1] = a.y; r.o[2] = a.z; r.mode = __float_as_uint(a.w);
+        r.d[0] = b.x; r.d[1] = b.y; r.d[2] = b.z; r.limit = b.w;
+        return r;
+    }
+#else
+    uint32_t stage_base;
+    Ray shadow_[MAX_LIGHT_SAMPLES];
+    void put_shadow(uint32_t j, const Ray& r) { shadow_[j] = r; }
+    Ray get_shadow(uint32_t j) const { return shadow_[j]; }
+#endif
 };
 
 // ---------------------------------------------------------------- film (film.rs)
@@ -225,7 +247,7 @@ PYR_HD void hit_surface(const SceneView& sc, v3 o, v3 d, const Hit& h, Surface& 
     }
 }
 // Material::apply_normal_map (materials/mod.rs:68-81)
-PYR_HD v3 apply_normal_map(const SceneView& sc, const Surface& s, v3 incident, f4* R) {
+PYR_HD v3 apply_normal_map(const SceneView& sc, const Surface& s, v3 incident, RegFile R) {
     int32_t prog = sc.materials[s.material].normal_map_program;
     if (prog < 0) return s.normal;
     VmInputs in;
@@ -234,7 +256,7 @@ PYR_HD v3 apply_normal_map(const SceneView& sc, const Surface& s, v3 incident, f
     return normalize(qrotate(s.frame, mk3(v.x, v.y, v.z)));
 }
 // MaterialComponent::get_probability (materials/mod.rs:237-249); `used` = ProbabilityInput::wavelength_used
-PYR_HD float component_probability(const SceneView& sc, const ComponentRec& c, const VmInputs& in, f4* R, bool& used) {
+PYR_HD float component_probability(const SceneView& sc, const ComponentRec& c, const VmInputs& in, RegFile R, bool& used) {
     used = false;
     if (c.probability_program >= 0) {
         used = program_reads_wavelength(sc, c.probability_program);
@@ -397,7 +419,7 @@ PYR_HD LampSample lamp_sample(const SceneView& sc, const LampRec& lamp, Rng& rng
 // ---------------------------------------------------------------- the contribute fold (renderer/algorithm.rs:14-100)
 // values[k] = color(wl[k]) for k < n: the program record is fetched once and the memoised re-run
 // is used for k > 0
-PYR_HD void eval_spectral(const SceneView& sc, int32_t color, const VmInputs& base, const float* wl, uint32_t n, float* values, f4* R) {
+PYR_HD void eval_spectral(const SceneView& sc, int32_t color, const VmInputs& base, const float* wl, uint32_t n, float* values, RegFile R) {
     const ProgramRec p = sc.programs[color];
     if (p.is_constant) { for (uint32_t k = 0; k < n; ++k) values[k] = p.value; return; }
     VmInputs in = base;
@@ -408,7 +430,7 @@ PYR_HD void eval_spectral(const SceneView& sc, int32_t color, const VmInputs& ba
 }
 // brightness[k] += color(wl[k]) * probability * reflectance[k] for k < n
 PYR_HD void add_emission(const SceneView& sc, PathState& ps, uint32_t n, int32_t color, v3 incident, v3 normal, const float* tex,
-                         float probability, f4* R) {
+                         float probability, RegFile R) {
     VmInputs in;
     in.wavelength = 0.0f; in.incident = incident; in.normal = normal; in.tex[0] = tex[0]; in.tex[1] = tex[1];
     float c[MAX_SPECTRUM_SAMPLES];
@@ -416,7 +438,7 @@ PYR_HD void add_emission(const SceneView& sc, PathState& ps, uint32_t n, int32_t
     for (uint32_t k = 0; k < n; ++k) ps.bright[k] += c[k] * probability * ps.refl[k];
 }
 PYR_HD void mul_reflectance(const SceneView& sc, PathState& ps, uint32_t n, int32_t color, v3 incident, v3 normal, const float* tex,
-                            float probability, f4* R) {
+                            float probability, RegFile R) {
     VmInputs in;
     in.wavelength = 0.0f; in.incident = incident; in.normal = normal; in.tex[0] = tex[0]; in.tex[1] = tex[1];
     float c[MAX_SPECTRUM_SAMPLES];
@@ -430,7 +452,7 @@ struct PathCounters { uint32_t de_evals, de_iters; };
 // their visibility rays; the `DirectLight` records wait in `ps.pend` until the rays are traced.
 // Draw order is the reference's, except that the emissive-component pick of a shape lamp happens
 // before (and regardless of) the visibility result (the oracle has the same switch).
-PYR_HD void next_event(const SceneView& sc, PathState& ps, float wavelength, v3 ray_in, v3 position, v3 normal, ShadeOut& out, f4* R) {
+PYR_HD void next_event(const SceneView& sc, PathState& ps, float wavelength, v3 ray_in, v3 position, v3 normal, ShadeOut& out, RegFile R) {
     const uint32_t samples = sc.renderer.light_samples;
     if (sc.n_lamps == 0) return;  // unreachable: pyr_render refuses such scenes (the reference would panic here)
     const uint32_t lamp_index = (uint32_t)ps.rng.gen_range_usize(sc.n_lamps);  // World::pick_lamp (world.rs:301-305)
@@ -467,7 +489,7 @@ PYR_HD void next_event(const SceneView& sc, PathState& ps, float wavelength, v3 
         ps.pend[j] = pl;
         // blocked <=> a hit with t > eps and t^2 < sq_distance - eps (tracer.rs:381-389); lamps without a
         // distance (directional) are blocked by any hit
-        out.shadow[j] = make_ray(position, ls.direction, 1, ls.has_sq ? ls.sq_distance - DIST_EPSILON : PYR_INF);
+        out.put_shadow(j, make_ray(position, ls.direction, 1, ls.has_sq ? ls.sq_distance - DIST_EPSILON : PYR_INF));
     }
 }
 
@@ -493,7 +515,7 @@ PYR_HD void expose_path(const SceneView& sc, const PathState& ps, Add& add) {
 // bounce's direct light (its visibility rays are now traced), then process the closest hit of the
 // path ray exactly as one iteration of `trace`'s loop (tracer.rs:221-343) followed by
 // `contribute` for that bounce (algorithm.rs:14-100).  `main_ray` / `main_hit`: the path ray of the
-// finished trace pass (valid if PS_HAS_MAIN); `shadow_rays` / `shadow_hits`: its `n_pending`
+// finished trace pass (valid if PS_HAS_MAIN); `shadow_rays` / `shadow_kinds`: its `n_pending`
 // visibility rays.
 //
 // `hooks` lets the bidirectional integrator observe the camera subpath it shares with this one
@@ -506,8 +528,8 @@ struct NoHooks {
 };
 template <class Hooks>
 PYR_HD bool camera_step(const SceneView& sc, PathState& ps, const Ray* main_ray, const Hit* main_hit, const Ray* shadow_rays,
-                        const Hit* shadow_hits, ShadeOut& out, PathCounters& pc, Hooks& hooks) {
-    f4 R[VM_REGS];
+                        const uint32_t* shadow_kinds, ShadeOut& out, PathCounters& pc, Hooks& hooks) {
+    PYR_REGFILE(R);
     const uint32_t S = sc.renderer.spectrum_samples;
     out.alive = 0; out.has_main = 0; out.n_shadow = 0;
 
@@ -519,15 +541,16 @@ PYR_HD bool camera_step(const SceneView& sc, PathState& ps, const Ray* main_ray,
         uint32_t cached_n = 0;
         float c[MAX_SPECTRUM_SAMPLES];
         for (uint32_t j = 0; j < ps.n_pending; ++j) {
-            if (shadow_hits[j].kind != KIND_MISS) continue;  // blocked
+            if (shadow_kinds[j] != KIND_MISS) continue;  // blocked
             const PendingLight pl = ps.pend[j];
             const uint32_t m = pl.dispersed ? 1u : n;
             if (pl.color_program != cached_program || m > cached_n) {
-                VmInputs in;
-                in.wavelength = 0.0f; in.incident = ld3(shadow_rays[j].d); in.normal = ld3(pl.normal); in.tex[0] = pl.tex[0]; in.tex[1] = pl.tex[1];
-                eval_spectral(sc, pl.color_program, in, ps.wl, m, c, R);
                 const ProgramRec p = sc.programs[pl.color_program];
                 const bool wavelength_only = p.is_constant || !(p.reads & (IN_NORMAL | IN_INCIDENT | IN_TEXTURE));
+                VmInputs in;
+                in.wavelength = 0.0f; in.normal = ld3(pl.normal); in.tex[0] = pl.tex[0]; in.tex[1] = pl.tex[1];
+                in.incident = wavelength_only ? mk3(0, 0, 0) : ld3(shadow_rays[j].d);  // the ray is only fetched when the colour looks at it
+                eval_spectral(sc, pl.color_program, in, ps.wl, m, c, R);
                 cached_program = wavelength_only ? pl.color_program : -1;
                 cached_n = m;
             }
@@ -603,9 +626,9 @@ PYR_HD bool camera_step(const SceneView& sc, PathState& ps, const Ray* main_ray,
 // The camera-to-light integrator (renderer/simple.rs:78-140): when the path ends, expose it.
 template <class Add>
 PYR_HD void shade_simple(const SceneView& sc, PathState& ps, const Ray* main_ray, const Hit* main_hit, const Ray* shadow_rays,
-                         const Hit* shadow_hits, ShadeOut& out, Add& add, PathCounters& pc) {
+                         const uint32_t* shadow_kinds, ShadeOut& out, Add& add, PathCounters& pc) {
     NoHooks hooks;
-    if (!camera_step(sc, ps, main_ray, main_hit, shadow_rays, shadow_hits, out, pc, hooks)) expose_path(sc, ps, add);
+    if (!camera_step(sc, ps, main_ray, main_hit, shadow_rays, shadow_kinds, out, pc, hooks)) expose_path(sc, ps, add);
 }
 
 
@@ -615,7 +638,7 @@ struct DevelopParams { float white_max, d65_max, step_size; uint32_t pad; };
 PYR_HD float d65_get(const SceneView& sc, float w) { return array_get(sc.d65, sc.d65_t.n, 1, sc.d65_t.lo, sc.d65_t.hi, w); }
 // the white-balance scan of main.rs:206-214
 PYR_HD void white_scan(const SceneView& sc, float& white_max, float& d65_max) {
-    f4 R[VM_REGS];
+    PYR_REGFILE(R);
     white_max = 0.0f; d65_max = 0.0f;
     if (sc.white_program < 0) return;
     float wavelength = sc.renderer.span_lo;
@@ -629,7 +652,7 @@ PYR_HD void white_scan(const SceneView& sc, float& white_max, float& d65_max) {
     }
 }
 // the spectrum_get closure of main.rs:224-238
-PYR_HD float develop_adjust(const SceneView& sc, const DevelopParams& dp, float intensity, float wavelength, f4* R) {
+PYR_HD float develop_adjust(const SceneView& sc, const DevelopParams& dp, float intensity, float wavelength, RegFile R) {
     VmInputs in;
     in.wavelength = wavelength; in.normal = mk3(0, 0, 0); in.incident = mk3(0, 0, 0); in.tex[0] = 0; in.tex[1] = 0;
     float filtered = sc.filter_program >= 0 ? intensity * run_number(sc, sc.filter_program, in, R) : intensity;
@@ -654,7 +677,7 @@ PYR_HD float film_spectrum_get(const SceneView& sc, const float* film, uint64_t 
 }
 // spectrum_to_xyz / spectrum_to_tristimulus (main.rs:352-418), x 3.444 (main.rs:322)
 PYR_HD void pixel_to_xyz(const SceneView& sc, const DevelopParams& dp, const float* film, uint64_t pixel, float* out) {
-    f4 R[VM_REGS];
+    PYR_REGFILE(R);
     float lo = sc.film.wavelength_start, hi = sc.film.wavelength_start + sc.film.wavelength_width;
     float sum[3] = {0, 0, 0};
     float weight = 0.0f;

@@ -97,6 +97,7 @@ int emu_render(void* h, uint64_t seed, uint32_t spp_override, uint32_t offset, u
         if (stride == 0) stride = 1;
         std::vector<Ray> rays(1 + BDPT_STAGE);
         std::vector<Hit> hits(rays.size());
+        std::vector<uint32_t> kinds(rays.size());
         auto ps = std::make_unique<PathState>();
         std::vector<PendingLight> pend(MAX_LIGHT_SAMPLES);
         BidirState bd{};
@@ -109,6 +110,7 @@ int emu_render(void* h, uint64_t seed, uint32_t spp_override, uint32_t offset, u
             const uint64_t iterations = (uint64_t)sc.tiles[t].width * sc.tiles[t].height * spp;
             for (uint64_t i = offset; i < iterations; i += stride) {
                 ShadeOut out;
+                out.stage_base = 0;
                 PathCounters pc{0, 0};
                 if (sc.renderer.algorithm == 0) {
                     generate_simple(sc, seed, t, i, *ps, out.main);
@@ -116,17 +118,17 @@ int emu_render(void* h, uint64_t seed, uint32_t spp_override, uint32_t offset, u
                     while (out.alive) {
                         uint32_t n = 0;
                         if (out.has_main) rays[n++] = out.main; else n = 1;
-                        for (uint32_t j = 0; j < out.n_shadow; ++j) rays[n++] = out.shadow[j];
-                        for (uint32_t j = out.has_main ? 0 : 1; j < n; ++j) { trace_ray<false>(sc, rays[j], hits[j], nullptr); ++e->rays; }
-                        shade_simple(sc, *ps, rays.data(), hits.data(), rays.data() + 1, hits.data() + 1, out, add, pc);
+                        for (uint32_t j = 0; j < out.n_shadow; ++j) rays[n++] = out.get_shadow(j);
+                        for (uint32_t j = out.has_main ? 0 : 1; j < n; ++j) { trace_ray<false>(sc, rays[j], hits[j], nullptr); kinds[j] = hits[j].kind; ++e->rays; }
+                        shade_simple(sc, *ps, rays.data(), hits.data(), rays.data() + 1, kinds.data() + 1, out, add, pc);
                     }
                 } else {
                     BidirOut bo;
                     generate_bidirectional(sc, seed, t, i, *ps, cx, bo);
                     while (bo.alive) {
                         if (bo.has_main) { rays[0] = bo.main; trace_ray<false>(sc, rays[0], hits[0], nullptr); ++e->rays; }
-                        for (uint32_t j = 0; j < bo.n_shadow; ++j) { rays[1 + j] = bo.shadow[j]; trace_ray<false>(sc, rays[1 + j], hits[1 + j], nullptr); ++e->rays; }
-                        shade_bidirectional(sc, *ps, cx, rays.data(), hits.data(), rays.data() + 1, hits.data() + 1, bo, add, pc);
+                        for (uint32_t j = 0; j < bo.n_shadow; ++j) { rays[1 + j] = bo.shadow[j]; trace_ray<false>(sc, rays[1 + j], hits[1 + j], nullptr); kinds[1 + j] = hits[1 + j].kind; ++e->rays; }
+                        shade_bidirectional(sc, *ps, cx, rays.data(), hits.data(), rays.data() + 1, kinds.data() + 1, bo, add, pc);
                     }
                 }
             }
@@ -171,7 +173,7 @@ void emu_run_program(void* h, int32_t index, const float* inputs, float* out4) {
     in.normal = mk3(inputs[1], inputs[2], inputs[3]);
     in.incident = mk3(inputs[4], inputs[5], inputs[6]);
     in.tex[0] = inputs[7]; in.tex[1] = inputs[8];
-    f4 R[VM_REGS];
+    PYR_REGFILE(R);
     f4 v = run_vector(e->view, index, in, R);
     const ProgramRec p = e->view.programs[index];
     if (p.is_constant) { out4[0] = p.value; out4[1] = out4[2] = out4[3] = p.value; return; }
