@@ -739,49 +739,60 @@ struct Traversal {
         done = false;
     }
 
+    // pop, dropping entries whose box now starts beyond the closest hit
     template <class Stack>
-    PYR_HD void step(const SceneView& sc, Stack& stack) {
-        if (cur >= 0) {
-            const Node nd = fetch_node(sc.nodes + cur);
-            float d0, d1;
-            bool h0 = slab_test(mk3(nd.n0.x, nd.n0.y, nd.n0.z), mk3(nd.n0.w, nd.n1.x, nd.n1.y), o, inv, d0);
-            bool h1 = slab_test(mk3(nd.n1.z, nd.n1.w, nd.n2.x), mk3(nd.n2.y, nd.n2.z, nd.n2.w), o, inv, d1);
-            if (STATS) vn += 2;
-            h0 = h0 && !(d0 > closest) && !(mode != 0 && d0 > bound);
-            h1 = h1 && !(d1 > closest) && !(mode != 0 && d1 > bound);
-            int c0 = (int)f_bits(nd.n3.x), c1 = (int)f_bits(nd.n3.y);
-            if (h0 && h1) {
-                if (d1 < d0) { int tc = c0; c0 = c1; c1 = tc; float td = d0; d0 = d1; d1 = td; }
-                stack.put(sp++, c1, d1);
-                cur = c0;
-                return;
-            }
-            if (h0) { cur = c0; return; }
-            if (h1) { cur = c1; return; }
-        } else {
-            const uint32_t r = (uint32_t)~cur;
-            const Prim pr = fetch_prim(sc.prims + r);
-            const uint32_t k = prim_kind(pr);
-            if (STATS) ++vl;
-            float ht = 0, hu = 0, hv = 0;
-            bool ok;
-            if (k == KIND_TRIANGLE) ok = triangle_test(prim_v1(pr), prim_e1(pr), prim_e2(pr), o, d, ht, hu, hv);
-            else if (k == KIND_SPHERE) { v3 p; ok = sphere_test(prim_v1(pr), pr.a.w, o, d, ht, p); }
-            else ok = march_test(sc.marched[f_bits(pr.a.x)], o, d, ht, de_evals, de_iters);
-            if (ok && ht > DIST_EPSILON) {
-                if (mode != 0) {
-                    if (occludes(mode, ht, limit)) { t = ht; u = hu; v = hv; rank = r; kind = k; done = true; return; }
-                } else if (ht < closest || (ht == closest && kind != KIND_PLANE && r < rank)) {
-                    closest = ht; t = ht; u = hu; v = hv; rank = r; kind = k;
-                }
-            }
-        }
-        // pop, dropping entries whose box now starts beyond the closest hit
+    PYR_HD void pop(Stack& stack) {
         for (;;) {
             if (sp == 0) { done = true; return; }
             --sp;
             if (!(stack.dist(sp) > closest)) { cur = stack.code(sp); return; }
         }
+    }
+    // one interior node (cur >= 0): both children's boxes, nearest first
+    template <class Stack>
+    PYR_HD void node_step(const SceneView& sc, Stack& stack) {
+        const Node nd = fetch_node(sc.nodes + cur);
+        float d0, d1;
+        bool h0 = slab_test(mk3(nd.n0.x, nd.n0.y, nd.n0.z), mk3(nd.n0.w, nd.n1.x, nd.n1.y), o, inv, d0);
+        bool h1 = slab_test(mk3(nd.n1.z, nd.n1.w, nd.n2.x), mk3(nd.n2.y, nd.n2.z, nd.n2.w), o, inv, d1);
+        if (STATS) vn += 2;
+        h0 = h0 && !(d0 > closest) && !(mode != 0 && d0 > bound);
+        h1 = h1 && !(d1 > closest) && !(mode != 0 && d1 > bound);
+        int c0 = (int)f_bits(nd.n3.x), c1 = (int)f_bits(nd.n3.y);
+        if (h0 && h1) {
+            if (d1 < d0) { int tc = c0; c0 = c1; c1 = tc; float td = d0; d0 = d1; d1 = td; }
+            stack.put(sp++, c1, d1);
+            cur = c0;
+            return;
+        }
+        if (h0) { cur = c0; return; }
+        if (h1) { cur = c1; return; }
+        pop(stack);
+    }
+    // one leaf (cur < 0): the primitive test of Shape::ray_intersect and World::intersect's acceptance rule
+    template <class Stack>
+    PYR_HD void leaf_step(const SceneView& sc, Stack& stack) {
+        const uint32_t r = (uint32_t)~cur;
+        const Prim pr = fetch_prim(sc.prims + r);
+        const uint32_t k = prim_kind(pr);
+        if (STATS) ++vl;
+        float ht = 0, hu = 0, hv = 0;
+        bool ok;
+        if (k == KIND_TRIANGLE) ok = triangle_test(prim_v1(pr), prim_e1(pr), prim_e2(pr), o, d, ht, hu, hv);
+        else if (k == KIND_SPHERE) { v3 p; ok = sphere_test(prim_v1(pr), pr.a.w, o, d, ht, p); }
+        else ok = march_test(sc.marched[f_bits(pr.a.x)], o, d, ht, de_evals, de_iters);
+        if (ok && ht > DIST_EPSILON) {
+            if (mode != 0) {
+                if (occludes(mode, ht, limit)) { t = ht; u = hu; v = hv; rank = r; kind = k; done = true; return; }
+            } else if (ht < closest || (ht == closest && kind != KIND_PLANE && r < rank)) {
+                closest = ht; t = ht; u = hu; v = hv; rank = r; kind = k;
+            }
+        }
+        pop(stack);
+    }
+    template <class Stack>
+    PYR_HD void step(const SceneView& sc, Stack& stack) {
+        if (cur >= 0) node_step(sc, stack); else leaf_step(sc, stack);
     }
 
     PYR_HD void finish(Hit& hit, TraceStats* stats) const {

@@ -22,6 +22,9 @@ namespace pyr {
 namespace {
 
 constexpr int WAVE_THREADS = 128;
+#ifndef WAVE_MIN_BLOCKS
+#define WAVE_MIN_BLOCKS 3
+#endif
 constexpr int TRACE_THREADS = 128;
 constexpr unsigned FULL = 0xffffffffu;
 // dynamic shared memory, sized by what the scene needs: VM registers (+ visibility-ray staging in the wave kernels)
@@ -169,7 +172,7 @@ __device__ __forceinline__ uint32_t binned_slot(const WaveArgs& a, uint32_t g, b
 }
 
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(WAVE_THREADS) k_wave_simple(const SceneView sc, const WaveArgs a) {
+__global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS) k_wave_simple(const SceneView sc, const WaveArgs a) {
     const uint32_t g_thread = blockIdx.x * blockDim.x + threadIdx.x;
     if (g_thread == 0) *a.trace_cursor = 0;
     bool valid;
@@ -283,8 +286,11 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sc, const Ray*
                 refill_min = 33;  // nothing left to hand out: stop checking until the warp drains
             }
         }
+        // interior nodes first, `steps` of them; then the lanes that stand at a leaf test it together (lanes
+        // that reach a leaf early wait, which costs less than running the leaf code for one lane at a time)
         for (uint32_t k = 0; k < steps; ++k)
-            if (has_ray && !tr.done) tr.step(sc, stack);
+            if (has_ray && !tr.done && tr.cur >= 0) tr.node_step(sc, stack);
+        if (has_ray && !tr.done && tr.cur < 0) tr.leaf_step(sc, stack);
         if (has_ray && tr.done) {
             emit(ray_at, tr);
             if (STATS) { nodes += tr.vn; leaves += tr.vl; evals += tr.de_evals; iters += tr.de_iters; }

@@ -12,6 +12,10 @@ kw = dict(spp=256) if scene == "dragon" else {}
 ir = project.serialize_project(scenes.SCENES[scene](**kw))
 with api.Renderer(0) as r:
     r.load(ir)
+    import os
+    if not os.environ.get('PYR_NO_WARMUP'):
+        r.render(seed=0, spp=1)
+        r.counters(reset=True)
     secs = r.render(seed=1, spp=spp, timing=True)
     c = r.counters()
     print(f"{scene}: {spp} spp in {secs * 1e3:.1f} ms, {c['rays'] / secs / 1e6:.0f} Mrays/s, trace {c['trace_seconds'] * 1e3:.1f} ms shade {c['shade_seconds'] * 1e3:.1f} ms, "
