@@ -745,7 +745,8 @@ struct Traversal {
         for (;;) {
             if (sp == 0) { done = true; return; }
             --sp;
-            if (!(stack.dist(sp) > closest)) { cur = stack.code(sp); return; }
+            const float entry_dist = stack.dist(sp);
+            if (!(entry_dist > closest)) { cur = stack.code(sp); return; }
         }
     }
     // one interior node (cur >= 0): both children's boxes, nearest first
@@ -758,16 +759,16 @@ struct Traversal {
         if (STATS) vn += 2;
         h0 = h0 && !(d0 > closest) && !(mode != 0 && d0 > bound);
         h1 = h1 && !(d1 > closest) && !(mode != 0 && d1 > bound);
-        int c0 = (int)f_bits(nd.n3.x), c1 = (int)f_bits(nd.n3.y);
-        if (h0 && h1) {
-            if (d1 < d0) { int tc = c0; c0 = c1; c1 = tc; float td = d0; d0 = d1; d1 = td; }
-            stack.put(sp++, c1, d1);
-            cur = c0;
-            return;
-        }
-        if (h0) { cur = c0; return; }
-        if (h1) { cur = c1; return; }
-        pop(stack);
+        const int c0 = (int)f_bits(nd.n3.x), c1 = (int)f_bits(nd.n3.y);
+        // branch-free choice of the child to descend into (the nearer hit one) and the one to defer
+        const bool both = h0 && h1;
+        const bool take1 = h1 && (!h0 || d1 < d0);
+        const int near_code = take1 ? c1 : c0, far_code = take1 ? c0 : c1;
+        const float far_dist = take1 ? d0 : d1;
+        if (both) stack.put(sp, far_code, far_dist);
+        sp += both ? 1 : 0;
+        if (h0 || h1) cur = near_code;
+        else pop(stack);
     }
     // one leaf (cur < 0): the primitive test of Shape::ray_intersect and World::intersect's acceptance rule
     template <class Stack>

@@ -223,16 +223,15 @@ __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS) k_wave_simple(c
 // conflicts), deeper entries (rare) in local memory.
 constexpr int SHARED_STACK = 20;
 struct SharedStack {
-    int* codes;     // &smem_codes[threadIdx.x]
-    float* dists;   // &smem_dists[threadIdx.x]
-    int deep_codes[BVH_STACK - SHARED_STACK];
-    float deep_dists[BVH_STACK - SHARED_STACK];
+    int2* entries;  // &smem[threadIdx.x]: (child code, entry distance bits), one 8-byte access per push / pop
+    int2 deep[BVH_STACK - SHARED_STACK];
     __device__ __forceinline__ void put(int i, int code, float dist) {
-        if (i < SHARED_STACK) { codes[i * TRACE_THREADS] = code; dists[i * TRACE_THREADS] = dist; }
-        else { deep_codes[i - SHARED_STACK] = code; deep_dists[i - SHARED_STACK] = dist; }
+        const int2 e = make_int2(code, __float_as_int(dist));
+        if (i < SHARED_STACK) entries[i * TRACE_THREADS] = e; else deep[i - SHARED_STACK] = e;
     }
-    __device__ __forceinline__ int code(int i) const { return i < SHARED_STACK ? codes[i * TRACE_THREADS] : deep_codes[i - SHARED_STACK]; }
-    __device__ __forceinline__ float dist(int i) const { return i < SHARED_STACK ? dists[i * TRACE_THREADS] : deep_dists[i - SHARED_STACK]; }
+    __device__ __forceinline__ int2 at(int i) const { return i < SHARED_STACK ? entries[i * TRACE_THREADS] : deep[i - SHARED_STACK]; }
+    __device__ __forceinline__ int code(int i) const { return at(i).x; }
+    __device__ __forceinline__ float dist(int i) const { return __int_as_float(at(i).y); }
 };
 
 // Persistent warps with lane-level refill: a warp reserves 32 ray indices with one atomicAdd and hands
@@ -243,11 +242,9 @@ template <bool STATS, class Emit>
 __device__ __forceinline__ void trace_persistent(const SceneView& sc, const Ray* rays, uint32_t n_main, uint32_t n_shadow, uint32_t shadow_offset,
                                                  uint32_t* cursor, DeviceCounters* counters, bool closest_only, uint32_t refill_min, uint32_t steps,
                                                  Emit& emit) {
-    __shared__ int smem_codes[SHARED_STACK * TRACE_THREADS];
-    __shared__ float smem_dists[SHARED_STACK * TRACE_THREADS];
+    __shared__ int2 smem_stack[SHARED_STACK * TRACE_THREADS];
     SharedStack stack;
-    stack.codes = smem_codes + threadIdx.x;
-    stack.dists = smem_dists + threadIdx.x;
+    stack.entries = smem_stack + threadIdx.x;
     const uint32_t total = n_main + n_shadow;
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counters->rays, (unsigned long long)total);
     unsigned long long nodes = 0, leaves = 0, evals = 0, iters = 0;
