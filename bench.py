@@ -278,7 +278,7 @@ def run_product(args):
                        "step": f"{spp_step} spp per GPU per step ({256 // max(spp_step, 1)} steps = the 256-spp config on 1 GPU)",
                        "parallelism": f"sample-pass sharding over {world} GPU(s), one NCCL film reduce at the end",
                        "l2": "working set (film 1.06 GB + path pool + 150 MB BVH) exceeds the 126 MB L2; no flush needed",
-                       "pool_paths": args.pool or (1 << 20)},
+                       "pool_paths": args.pool or (1 << 21)},
             "clocks": clocks,
             "e2e": {"value": e2e_mrays, "unit": "Mrays/s", "h2d_bytes_per_step": 32, "d2h_bytes_per_step": pixels * 15,
                     "what": "pyr_render step + pyr_film_develop + XYZ f32 and sRGB u8 image download to host, wall clock"},
@@ -299,7 +299,7 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
-    ap.add_argument("--spp-per-step", type=int, default=4)
+    ap.add_argument("--spp-per-step", type=int, default=8)
     ap.add_argument("--pool", type=int, default=0, help="paths in flight (0 = library default)")
     ap.add_argument("--cpu-fraction", type=int, default=16, help="the CPU legs render 1/N of one sample pass per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -144,12 +144,12 @@ void ensure_pool(pyr_ctx* ctx, uint32_t pool) {
 // vertex storage stays within ~6 GB
 uint32_t default_pool(const pyr_ctx* ctx) {
     const RendererRec& R = ctx->view.renderer;
-    if (R.algorithm != 1) return 1u << 20;
+    if (R.algorithm != 1) return 1u << 21;
     const size_t per_path = path_state_bytes() + MAX_LIGHT_SAMPLES * pending_light_bytes() + bidir_state_bytes() + (size_t)(R.light_bounces + 1) * light_vertex_bytes() +
                             (size_t)std::max<uint32_t>(R.bounces, 1) * cam_vertex_bytes() + (size_t)(1 + bdpt_stage_rays()) * (2 * sizeof(Ray) + sizeof(Hit));
     size_t pool = (size_t)6 << 30;
     pool /= per_path;
-    return (uint32_t)std::min<size_t>(std::max<size_t>(pool, 4096), (size_t)1 << 20);
+    return (uint32_t)std::min<size_t>(std::max<size_t>(pool, 4096), (size_t)1 << 21);
 }
 
 }  // namespace

@@ -4,8 +4,9 @@ namespace {
 __global__ void __launch_bounds__(WAVE_THREADS) k_wave_bidirectional(const SceneView sc, const WaveArgs a) {
     const uint32_t g_thread = blockIdx.x * blockDim.x + threadIdx.x;
     if (g_thread == 0) *a.trace_cursor = 0;
-    bool valid;
-    const uint32_t slot = binned_slot(a, g_thread, valid);
+    bool valid, dead;
+    const uint32_t slot = binned_slot(a, g_thread, valid, dead);
+    if (__all_sync(FULL, !valid || dead) && *a.next_sample >= a.total_samples) return;
     const uint32_t s = valid ? slot : 0;
     PathState ps;
     static_cast<PathCore&>(ps) = a.paths[s];

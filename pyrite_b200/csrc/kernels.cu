@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(256) k_bin(const PathCore* paths, const BidirS
 }
 
 // thread -> slot through the bins: the concatenation of all bins is a permutation of [0, pool)
-__device__ __forceinline__ uint32_t binned_slot(const WaveArgs& a, uint32_t g, bool& valid) {
+__device__ __forceinline__ uint32_t binned_slot(const WaveArgs& a, uint32_t g, bool& valid, bool& dead) {
     __shared__ uint32_t s_first[NUM_BINS + 1];
     if (threadIdx.x == 0) {
         uint32_t acc = 0;
@@ -162,12 +162,14 @@ __device__ __forceinline__ uint32_t binned_slot(const WaveArgs& a, uint32_t g, b
     }
     __syncthreads();
     valid = g < s_first[NUM_BINS];
+    dead = false;
     if (!valid) return 0;
     int lo = 0, hi = NUM_BINS;  // s_first[lo] <= g < s_first[hi]
     while (hi - lo > 1) {
         int mid = (lo + hi) >> 1;
         if (s_first[mid] <= g) lo = mid; else hi = mid;
     }
+    dead = lo == 0;  // bin 0: slots without a live path
     return a.bin_list[(size_t)lo * a.pool + (g - s_first[lo])];
 }
 
@@ -175,10 +177,13 @@ __device__ __forceinline__ uint32_t binned_slot(const WaveArgs& a, uint32_t g, b
 __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS) k_wave_simple(const SceneView sc, const WaveArgs a) {
     const uint32_t g_thread = blockIdx.x * blockDim.x + threadIdx.x;
     if (g_thread == 0) *a.trace_cursor = 0;
-    bool valid;
-    const uint32_t slot = binned_slot(a, g_thread, valid);
+    bool valid, dead;
+    const uint32_t slot = binned_slot(a, g_thread, valid, dead);
+    // a whole warp of dead slots with no samples left to start has nothing to do (long-tailed scenes)
+    if (__all_sync(FULL, !valid || dead) && *a.next_sample >= a.total_samples) return;
     PathState ps;
-    static_cast<PathCore&>(ps) = a.paths[valid ? slot : 0];
+    if (valid && !dead) static_cast<PathCore&>(ps) = a.paths[slot];
+    else ps.flags = 0;
     ps.pend = a.pend + (size_t)(valid ? slot : 0) * MAX_LIGHT_SAMPLES;
     ps.bd = nullptr;
     const uint32_t flags_in = ps.flags;

@@ -9,14 +9,23 @@ from pyrite_b200 import api, project, scenes
 spp = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 scene = sys.argv[2] if len(sys.argv) > 2 else "dragon"
 kw = dict(spp=256) if scene == "dragon" else {}
+if scene == "fractals":
+    kw = dict(width=1920, height=1080)
+if scene == "bdpt_cornell_dragon":
+    kw = dict(width=1920, height=1080)
+if scene == "cornell_bd":
+    scene, kw = "cornell", dict(width=1024, height=1024, integrator="bidirectional")
+if scene == "diamonds":
+    kw = dict(width=1920, height=1080)
 ir = project.serialize_project(scenes.SCENES[scene](**kw))
 with api.Renderer(0) as r:
     r.load(ir)
     import os
     if not os.environ.get('PYR_NO_WARMUP'):
-        r.render(seed=0, spp=1)
+        r.render(seed=0, spp=1, pool_paths=int(os.environ.get('PYR_POOL', '0')))
         r.counters(reset=True)
-    secs = r.render(seed=1, spp=spp, timing=True)
+    pool = int(os.environ.get('PYR_POOL', '0'))
+    secs = r.render(seed=1, spp=spp, timing=True, pool_paths=pool)
     c = r.counters()
     print(f"{scene}: {spp} spp in {secs * 1e3:.1f} ms, {c['rays'] / secs / 1e6:.0f} Mrays/s, trace {c['trace_seconds'] * 1e3:.1f} ms shade {c['shade_seconds'] * 1e3:.1f} ms, "
           f"{c['wavefront_iterations']} iterations")
