@@ -26,7 +26,9 @@ constexpr int BDPT_STAGE = 16;  // visibility rays staged per path per iteration
 enum : uint32_t { PH_LAMP = 0, PH_CAMERA = 1, PH_CONNECT = 2, PH_SPLAT = 3 };
 enum : uint32_t { VT_DIFFUSE = 0, VT_SPECULAR = 1, VT_EMISSION = 2 };
 
-// One stored vertex of the lamp subpath (tracer.rs:157-167 `Bounce`; lamp paths carry no direct light). 80 B.
+// One stored vertex of the lamp subpath (tracer.rs:157-167 `Bounce`; lamp paths carry no direct light), plus
+// its colour program evaluated at the path's wavelengths: connect_paths and light tracing re-fold the tail of
+// the lamp path for every connection (bidirectional.rs:373-389, 276-292), always with the same colours. 144 B.
 struct alignas(16) LightVertex {
     float position[3];
     uint32_t type;
@@ -38,6 +40,7 @@ struct alignas(16) LightVertex {
     uint32_t dispersed;
     float tex[2];
     uint32_t pad[2];
+    float color[MAX_SPECTRUM_SAMPLES];  // color(wl[k]), filled by finish_lamp_path
 };
 // A diffuse camera-subpath vertex with the sample state right after its `contribute`. 160 B.
 struct alignas(16) CamVertex {
@@ -66,28 +69,24 @@ PYR_HD float vertex_brdf(const LightVertex& v) {  // BounceType::brdf: lambertia
 }
 
 // `contribute` (renderer/algorithm.rs:14-100) of a lamp-subpath bounce on a detached sample state
-PYR_HD void contribute_vertex(const SceneView& sc, const LightVertex& v, const float* wl, uint32_t n, float* bright, float* refl, RegFile R) {
-    VmInputs in;
-    in.wavelength = 0.0f; in.incident = ld3(v.incident); in.normal = ld3(v.normal); in.tex[0] = v.tex[0]; in.tex[1] = v.tex[1];
-    float c[MAX_SPECTRUM_SAMPLES];
-    eval_spectral(sc, v.color_program, in, wl, n, c, R);
+PYR_HD void contribute_vertex(const LightVertex& v, uint32_t n, float* bright, float* refl) {
     if (v.type == VT_EMISSION) {
-        for (uint32_t k = 0; k < n; ++k) bright[k] += c[k] * v.probability * refl[k];
+        for (uint32_t k = 0; k < n; ++k) bright[k] += v.color[k] * v.probability * refl[k];
     } else {
-        for (uint32_t k = 0; k < n; ++k) refl[k] *= c[k] * v.probability;
+        for (uint32_t k = 0; k < n; ++k) refl[k] *= v.color[k] * v.probability;
         const float brdf = vertex_brdf(v);
         for (uint32_t k = 0; k < n; ++k) refl[k] *= brdf;
     }
 }
 // the fold over lamp_path[first..] shared by connect_paths (:373-389) and light tracing (:276-292)
-PYR_HD void fold_lamp_tail(const SceneView& sc, const LightVertex* lv, uint32_t first, uint32_t n_light, const float* wl, bool& use_additional,
-                           float* bright, float* refl, float brdf_in, RegFile R) {
+PYR_HD void fold_lamp_tail(const SceneView& sc, const LightVertex* lv, uint32_t first, uint32_t n_light, bool& use_additional,
+                           float* bright, float* refl, float brdf_in) {
     const uint32_t S = sc.renderer.spectrum_samples;
     for (uint32_t k = first; k < n_light; ++k) {
         const LightVertex v = lv[k];
         use_additional = !v.dispersed && use_additional;
         const uint32_t n = use_additional ? S : 1u;
-        contribute_vertex(sc, v, wl, n, bright, refl, R);
+        contribute_vertex(v, n, bright, refl);
         if (k == first) for (uint32_t j = 0; j < n; ++j) refl[j] *= brdf_in;
     }
 }
@@ -135,7 +134,7 @@ PYR_HD void begin_camera(PathState& ps, BidirOut& out) {
 
 // The end of the lamp subpath: utils::pairs fix-up (skips the last pair, utils.rs:5-13), drop a trailing
 // emission vertex, reverse (bidirectional.rs:187-202).
-PYR_HD void finish_lamp_path(PathState& ps, LightVertex* lv) {
+PYR_HD void finish_lamp_path(const SceneView& sc, PathState& ps, LightVertex* lv) {
     uint32_t n = ps.bd->n_light;
     if (n >= 2)
         for (uint32_t pos = 0; pos + 2 < n; ++pos) {
@@ -147,6 +146,16 @@ PYR_HD void finish_lamp_path(PathState& ps, LightVertex* lv) {
     if (n > 1 && lv[n - 1].type == VT_EMISSION) n -= 1;
     for (uint32_t i = 0; i < n / 2; ++i) { LightVertex t = lv[i]; lv[i] = lv[n - 1 - i]; lv[n - 1 - i] = t; }
     ps.bd->n_light = n;
+    // evaluate every vertex' colour once at the path's wavelengths (with the incident vectors as fixed up above)
+    PYR_REGFILE(R);
+    for (uint32_t i = 0; i < n; ++i) {
+        LightVertex& v = lv[i];
+        VmInputs in;
+        in.wavelength = 0.0f; in.incident = ld3(v.incident); in.normal = ld3(v.normal); in.tex[0] = v.tex[0]; in.tex[1] = v.tex[1];
+        float c[MAX_SPECTRUM_SAMPLES];
+        eval_spectral(sc, v.color_program, in, ps.wl, sc.renderer.spectrum_samples, c, R);
+        for (uint32_t k = 0; k < sc.renderer.spectrum_samples; ++k) v.color[k] = c[k];
+    }
 }
 
 // Stage the visibility rays of connect_paths for camera vertex `conn_cam`, lamp vertices from `conn_light`.
@@ -310,7 +319,7 @@ PYR_HD void generate_bidirectional(const SceneView& sc, uint64_t seed, uint32_t 
     cx.lv[0] = first;
     ps.bd->n_light = 1;
     if (sc.renderer.light_bounces == 0) {
-        finish_lamp_path(ps, cx.lv);
+        finish_lamp_path(sc, ps, cx.lv);
         begin_camera(ps, out);
         return;
     }
@@ -383,7 +392,7 @@ PYR_HD void shade_bidirectional(const SceneView& sc, PathState& ps, const BidirC
     const uint32_t S = sc.renderer.spectrum_samples;
     if (ps.bd->phase == PH_LAMP) {
         if (lamp_step(sc, ps, cx, *main_ray, *main_hit, out, pc)) return;
-        finish_lamp_path(ps, cx.lv);
+        finish_lamp_path(sc, ps, cx.lv);
         ps.light_events = 0;
         begin_camera(ps, out);
         return;
@@ -401,7 +410,6 @@ PYR_HD void shade_bidirectional(const SceneView& sc, PathState& ps, const BidirC
         end_camera_path(sc, ps, cx, out, add);
         return;
     }
-    PYR_REGFILE(R);
     uint32_t lamp_index[BDPT_STAGE];
     float bright[MAX_SPECTRUM_SAMPLES], refl[MAX_SPECTRUM_SAMPLES];
     if (ps.bd->phase == PH_CONNECT) {  // evaluate the connections whose visibility rays were just traced
@@ -424,7 +432,7 @@ PYR_HD void shade_bidirectional(const SceneView& sc, PathState& ps, const BidirC
             float brdf_in = vertex_brdf(v) / vertex_brdf(v);
             for (uint32_t k = 0; k < S; ++k) { bright[k] = c.bright[k]; refl[k] = c.refl[k] * scale; }
             bool use_additional = c.use_additional != 0;
-            fold_lamp_tail(sc, cx.lv, lamp_index[j], ps.bd->n_light, ps.wl, use_additional, bright, refl, brdf_in, R);
+            fold_lamp_tail(sc, cx.lv, lamp_index[j], ps.bd->n_light, use_additional, bright, refl, brdf_in);
             film_expose(sc.film, ps.pos[0], ps.pos[1], bright[0], ps.wl[0], weight, add);
             if (use_additional)
                 for (uint32_t k = 1; k < S; ++k) film_expose(sc.film, ps.pos[0], ps.pos[1], bright[k], ps.wl[k], weight, add);
@@ -464,7 +472,7 @@ PYR_HD void shade_bidirectional(const SceneView& sc, PathState& ps, const BidirC
             const float brdf_in = vertex_brdf(v) / vertex_brdf(v);
             for (uint32_t k = 0; k < S; ++k) { bright[k] = 0.0f; refl[k] = scale; }
             bool use_additional = true;
-            fold_lamp_tail(sc, cx.lv, lamp_index[j], ps.bd->n_light, ps.wl, use_additional, bright, refl, brdf_in, R);
+            fold_lamp_tail(sc, cx.lv, lamp_index[j], ps.bd->n_light, use_additional, bright, refl, brdf_in);
             film_expose(sc.film, px, py, bright[0], ps.wl[0], weight, add);
             if (use_additional)
                 for (uint32_t k = 1; k < S; ++k) film_expose(sc.film, px, py, bright[k], ps.wl[k], weight, add);
