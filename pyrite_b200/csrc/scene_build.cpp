@@ -455,18 +455,20 @@ struct TreeBuilder {
     std::vector<uint32_t> order;  // item index per rank
     struct Interior { Box box[2]; int32_t child[2]; };
     std::vector<Interior> interiors;
+    int max_depth = 0;
 
     // Builds the subtree over `ids`, emitting leaves in the reference's flattened pre-order, and
     // returns its child code.  The reference's `first` child (visited first) is the subtree of the
     // SECOND item group: the Join pops it from the node stack first (bvh.rs:39-50).
     int32_t run(std::vector<uint32_t> root_ids, Hull2 root_hull) {
-        struct Frame { std::vector<uint32_t> ids; Hull2 hull; int32_t parent; int slot; };
+        struct Frame { std::vector<uint32_t> ids; Hull2 hull; int32_t parent; int slot; int depth; };
         std::vector<Frame> stack;
-        stack.push_back(Frame{std::move(root_ids), root_hull, -1, 0});
+        stack.push_back(Frame{std::move(root_ids), root_hull, -1, 0, 0});
         int32_t root_code = 0;
         while (!stack.empty()) {
             Frame f = std::move(stack.back());
             stack.pop_back();
+            if (f.depth > max_depth) max_depth = f.depth;
             int32_t code;
             if (f.ids.size() == 1) {
                 code = ~(int32_t)order.size();
@@ -482,8 +484,8 @@ struct TreeBuilder {
                 in.child[0] = in.child[1] = 0;
                 interiors.push_back(in);
                 // depth-first: the B group (child 0) completely before the A group (child 1)
-                stack.push_back(Frame{std::move(group_a), hull_a, code, 1});
-                stack.push_back(Frame{std::move(group_b), hull_b, code, 0});
+                stack.push_back(Frame{std::move(group_a), hull_a, code, 1, f.depth + 1});
+                stack.push_back(Frame{std::move(group_b), hull_b, code, 0, f.depth + 1});
             }
             if (f.parent < 0) root_code = code; else interiors[f.parent].child[f.slot] = code;
         }
@@ -802,6 +804,9 @@ BakedScene build_scene(const Document& input) {
         Hull2 hull = Hull2::around(items[0].box);
         for (const auto& it : items) hull = hull.plus(it.box);
         sv.root = tb.run(std::move(all), hull);
+        // the traversal defers at most one child per level
+        if (tb.max_depth >= BVH_STACK) throw BuildError("the BVH is deeper than the traversal stack (" + std::to_string(tb.max_depth) + " levels)");
+        out.bvh_depth = (uint32_t)tb.max_depth;
         sv.root_lo[0] = hull.all.lo.x; sv.root_lo[1] = hull.all.lo.y; sv.root_lo[2] = hull.all.lo.z;
         sv.root_hi[0] = hull.all.hi.x; sv.root_hi[1] = hull.all.hi.y; sv.root_hi[2] = hull.all.hi.z;
     }

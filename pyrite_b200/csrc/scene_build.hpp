@@ -33,6 +33,7 @@ struct BakedScene {
     std::vector<float> burns, xyz, d65;
     std::vector<uint32_t> rank_of_object;  // object id -> rank
     uint32_t n_objects = 0;
+    uint32_t bvh_depth = 0;
     // header part of SceneView (pointers are filled in after upload)
     SceneView view{};
 };

@@ -70,9 +70,9 @@ class Emu:
         if self.L.emu_load(buf, len(ir), C.byref(self.h)) != 0:
             raise EmuError(self.L.emu_last_error().decode())
         self.shape = tuple(shape)
-        info = np.zeros(8, np.uint32)
+        info = np.zeros(9, np.uint32)
         self.L.emu_info(self.h, _ptr(info))
-        self.info = dict(zip(("n_objects", "n_planes", "n_lamps", "n_nodes", "n_materials", "n_programs", "n_instr", "n_tiles"), map(int, info)))
+        self.info = dict(zip(("n_objects", "n_planes", "n_lamps", "n_nodes", "n_materials", "n_programs", "n_instr", "n_tiles", "bvh_depth"), map(int, info)))
 
     def __del__(self):
         try:

@@ -60,6 +60,7 @@ void emu_info(void* h, uint32_t* out) {
     out[0] = e->scene.n_objects; out[1] = e->view.n_planes; out[2] = e->view.n_lamps; out[3] = e->view.n_nodes;
     out[4] = (uint32_t)e->scene.materials.size(); out[5] = (uint32_t)e->scene.programs.size(); out[6] = (uint32_t)e->scene.code.size();
     out[7] = e->view.n_tiles;
+    out[8] = e->scene.bvh_depth;
 }
 void emu_leaf_order(void* h, uint32_t* object_ids) {
     Emu* e = (Emu*)h;
