@@ -300,3 +300,72 @@ def test_two_gpu_sharded_render_equals_single(tmp_path, gpu_renderer_factory):
     assert np.array_equal(whole[..., 1], reduced[..., 1])
     assert np.allclose(whole[..., 0], reduced[..., 0], rtol=1e-4, atol=1e-5)
     assert np.allclose(r.develop()[0], np.load(tmp_path / "xyz.npy"), rtol=1e-4, atol=1e-6)
+
+
+def test_c1_full_config_film(gpu_renderer_factory):
+    """BASELINE config C1: pyrite/test/cornell (box.obj, camera-to-light), 512x512 at 64 spp, S=10 - the whole
+    configuration on identical per-path streams, GPU vs the oracle on the host cores."""
+    from oracle_lib import Oracle
+
+    ir = scene_ir("cornell", width=512, height=512, spp=64)
+    r = gpu_renderer_factory("cornell", width=512, height=512, spp=64)
+    o = Oracle(ir)
+    secs_gpu = r.render(seed=64)
+    secs_cpu = o.render(seed=64)
+    fg, fo = r.film(), o.film()
+    assert np.array_equal(fg[..., 1], fo[..., 1])
+    xg, sg = r.develop()
+    xo, so = o.develop()
+    dmean, rmse, off = luminance_stats(xo, xg)
+    print(f"C1 512x512x64spp: GPU {secs_gpu:.3f} s, oracle ({o.threads} threads) {secs_cpu:.1f} s; mean-Y rel err {dmean:.2e}, RMSE/mean {rmse:.2e}, "
+          f"sRGB bytes differing by more than 1: {np.mean(np.abs(sg.astype(int) - so.astype(int)) > 1):.2e}")
+    assert dmean <= 1e-3 and rmse <= 1e-2
+    assert np.mean(np.abs(sg.astype(int) - so.astype(int)) > 1) <= 1e-3
+    assert r.counters()["path_samples"] >= 512 * 512 * 64
+
+
+def test_independent_seed_noise_floor(gpu_renderer_factory, oracle_factory):
+    """Independent-seed mode: GPU with one seed vs the oracle with another must differ by no more than
+    1.5 x what two oracle runs differ by, and agree in mean luminance within 5e-3 (scaled by the noise of the mean)."""
+    r, o = gpu_renderer_factory("cornell"), oracle_factory("cornell")
+    spp = 64
+    r.render(seed=101, spp=spp)
+    xg, _ = r.develop()
+    o.render(seed=202, spp=spp)
+    xa, _ = o.develop()
+    o.render(seed=303, spp=spp)
+    xb, _ = o.develop()
+    _, floor, _ = luminance_stats(xa, xb)
+    dmean, rmse, _ = luminance_stats(xa, xg)
+    print(f"independent seeds: RMSE/mean gpu-vs-oracle {rmse:.3e}, oracle-vs-oracle {floor:.3e}, mean-Y rel err {dmean:.2e}")
+    assert rmse <= 1.5 * floor
+    assert dmean <= max(5e-3, 3.0 * floor / np.sqrt(xa.shape[0] * xa.shape[1]))
+
+
+def test_full_size_ray_batches_against_oracle():
+    """SURVEY.md §8d ray-batch parity at BASELINE size: the 871,200-triangle stand-in, 3 batches (camera, bounce, shadow
+    rays) of 2^22 rays each, ids bit-exact and distances within 1e-5 relative."""
+    from oracle_lib import Oracle
+
+    from pyrite_b200 import api, project, scenes
+
+    ir = project.serialize_project(scenes.dragon(width=480, height=270, spp=1))
+    o = Oracle(ir)
+    r = api.Renderer(0)
+    r.load(ir)
+    assert np.array_equal(r.bvh_leaf_order(), o.bvh_leaf_order())
+    total_ties = 0
+    for kind in (0, 1, 2):
+        rays = o.gen_rays(kind, 1 << 22, seed=40 + kind)
+        want, cw = o.trace(rays)
+        got = r.trace(rays)
+        same = (want["prim_id"] == got["prim_id"]) & (want["kind"] == got["kind"])
+        ties = int((~same).sum())
+        total_ties += ties
+        hit = (want["kind"] != 0) & same
+        rel = np.abs(want["t"][hit] - got["t"][hit]) / np.abs(want["t"][hit])
+        print(f"dragon 871,200 tris, batch {kind}: {len(rays)} rays, {ties} id mismatches, max rel t err {rel.max() if rel.size else 0:.1e}, "
+              f"reference-order nodes/ray {cw['nodes'] / len(rays):.1f}, leaves/ray {cw['leaves'] / len(rays):.1f}")
+        assert rel.size == 0 or rel.max() <= 1e-5
+    assert total_ties == 0
+    r.close()
