@@ -696,11 +696,14 @@ struct LocalStack {
 // World::intersect for one ray as an explicit state machine: begin() tests the planes and the root
 // box, every step() processes one interior node or one leaf.  The kernels interleave the steps of 32
 // rays per warp and refill finished lanes; trace_ray() below simply runs it to completion.
+constexpr float CULL_SLACK = 1.000002f;  // ~16 ulps
+
 template <bool STATS>
 struct Traversal {
     v3 o, d, inv;
     uint32_t mode;
     float limit, bound, closest;
+    float cull;  // closest widened by a few ulps: boxes are only skipped beyond it (see node_step)
     float t, u, v;
     uint32_t rank, kind;
     int sp, cur;
@@ -712,7 +715,7 @@ struct Traversal {
         (void)stack;
         o = ld3(ray.o); d = ld3(ray.d);
         mode = ray.mode; limit = ray.limit;
-        closest = PYR_INF;
+        closest = PYR_INF; cull = PYR_INF;
         // visibility rays: nothing at or beyond `bound` can occlude
         bound = PYR_INF;
         if (mode == 1) bound = limit > 0.0f ? sqrtf(limit) : 0.0f;
@@ -727,14 +730,14 @@ struct Traversal {
                     if (occludes(mode, pt, limit)) { t = pt; rank = i; kind = KIND_PLANE; return; }
                     continue;
                 }
-                closest = pt; t = pt; rank = i; kind = KIND_PLANE;
+                closest = pt; cull = pt * CULL_SLACK; t = pt; rank = i; kind = KIND_PLANE;
             }
         }
         if (sc.n_prims == 0) return;
         inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
         float dr;
         if (STATS) ++vn;
-        if (!slab_test(ld3(sc.root_lo), ld3(sc.root_hi), o, inv, dr) || dr > closest) return;
+        if (!slab_test(ld3(sc.root_lo), ld3(sc.root_hi), o, inv, dr) || dr > cull) return;
         cur = sc.root;
         done = false;
     }
@@ -746,7 +749,7 @@ struct Traversal {
             if (sp == 0) { done = true; return; }
             --sp;
             const float entry_dist = stack.dist(sp);
-            if (!(entry_dist > closest)) { cur = stack.code(sp); return; }
+            if (!(entry_dist > cull)) { cur = stack.code(sp); return; }
         }
     }
     // one interior node (cur >= 0): both children's boxes, nearest first
@@ -757,8 +760,11 @@ struct Traversal {
         bool h0 = slab_test(mk3(nd.n0.x, nd.n0.y, nd.n0.z), mk3(nd.n0.w, nd.n1.x, nd.n1.y), o, inv, d0);
         bool h1 = slab_test(mk3(nd.n1.z, nd.n1.w, nd.n2.x), mk3(nd.n2.y, nd.n2.z, nd.n2.w), o, inv, d1);
         if (STATS) vn += 2;
-        h0 = h0 && !(d0 > closest) && !(mode != 0 && d0 > bound);
-        h1 = h1 && !(d1 > closest) && !(mode != 0 && d1 > bound);
+        // A box is skipped only when it starts beyond the closest hit by more than rounding: a leaf that ties with the
+        // current hit (a ray through a shared edge) can have a box entry a few ulps beyond its own hit distance, and the
+        // reference, walking in pre-order, would have tested it first (World::intersect's tie rule, world.rs:288-296).
+        h0 = h0 && !(d0 > cull) && !(mode != 0 && d0 > bound);
+        h1 = h1 && !(d1 > cull) && !(mode != 0 && d1 > bound);
         const int c0 = (int)f_bits(nd.n3.x), c1 = (int)f_bits(nd.n3.y);
         // branch-free choice of the child to descend into (the nearer hit one) and the one to defer
         const bool both = h0 && h1;
@@ -786,7 +792,7 @@ struct Traversal {
             if (mode != 0) {
                 if (occludes(mode, ht, limit)) { t = ht; u = hu; v = hv; rank = r; kind = k; done = true; return; }
             } else if (ht < closest || (ht == closest && kind != KIND_PLANE && r < rank)) {
-                closest = ht; t = ht; u = hu; v = hv; rank = r; kind = k;
+                closest = ht; cull = ht * CULL_SLACK; t = ht; u = hu; v = hv; rank = r; kind = k;
             }
         }
         pop(stack);
