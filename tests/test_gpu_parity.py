@@ -379,3 +379,23 @@ def test_full_size_ray_batches_against_oracle():
     print(f"edge-grazing ties over {3 << 22} rays: {total_ties}")
     assert total_ties <= 3
     r.close()
+
+
+def test_cli_renders_a_project_lua(tmp_path):
+    """`python -m pyrite_b200 project.lua`: load_project -> parse_project -> render -> develop -> render.png (main.rs:52-332)."""
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    from PIL import Image
+
+    root = Path(__file__).resolve().parent.parent
+    out = tmp_path / "render.png"
+    res = subprocess.run([sys.executable, "-m", "pyrite_b200", str(root / "tests" / "golden" / "scenes" / "orbs.lua"), "--seed", "1", "--out", str(out)],
+                         cwd=root, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr
+    assert "Project loading" in res.stdout and "Rendering" in res.stdout and "Total" in res.stdout
+    im = np.asarray(Image.open(out))
+    assert im.shape == (48, 96, 3) and im.mean() > 1.0
+    bad = subprocess.run([sys.executable, "-m", "pyrite_b200", str(tmp_path / "missing.lua")], cwd=root, capture_output=True, text=True, timeout=120)
+    assert bad.returncode == 1 and "error while loading project file" in bad.stderr
