@@ -30,7 +30,8 @@ constexpr unsigned FULL = 0xffffffffu;
 // dynamic shared memory, sized by what the scene needs: VM registers (+ visibility-ray staging in the wave kernels)
 inline size_t vm_smem(const SceneView& sc) { return (size_t)sc.vm_regs * WAVE_THREADS * sizeof(float4); }
 inline size_t wave_smem(const SceneView& sc) {
-    return vm_smem(sc) + (size_t)2 * (sc.renderer.light_samples ? sc.renderer.light_samples : 1) * WAVE_THREADS * sizeof(float4);
+    return vm_smem(sc) + (size_t)2 * (sc.renderer.light_samples ? sc.renderer.light_samples : 1) * WAVE_THREADS * sizeof(float4) +
+           (size_t)sc.renderer.spectrum_samples * WAVE_THREADS * sizeof(float);
 }
 
 struct FilmAdd {

@@ -419,31 +419,31 @@ PYR_HD LampSample lamp_sample(const SceneView& sc, const LampRec& lamp, Rng& rng
 // ---------------------------------------------------------------- the contribute fold (renderer/algorithm.rs:14-100)
 // values[k] = color(wl[k]) for k < n: the program record is fetched once and the memoised re-run
 // is used for k > 0
-PYR_HD void eval_spectral(const SceneView& sc, int32_t color, const VmInputs& base, const float* wl, uint32_t n, float* values, RegFile R) {
+template <class Sink>
+PYR_HD void eval_spectral_each(const SceneView& sc, int32_t color, const VmInputs& base, const float* wl, uint32_t n, RegFile R, Sink&& sink) {
     const ProgramRec p = sc.programs[color];
-    if (p.is_constant) { for (uint32_t k = 0; k < n; ++k) values[k] = p.value; return; }
+    if (p.is_constant) { for (uint32_t k = 0; k < n; ++k) sink(k, p.value); return; }
     VmInputs in = base;
     for (uint32_t k = 0; k < n; ++k) {
         in.wavelength = wl[k];
-        values[k] = run_program(sc, p, in, R, k > 0);
+        sink(k, run_program(sc, p, in, R, k > 0));
     }
+}
+PYR_HD void eval_spectral(const SceneView& sc, int32_t color, const VmInputs& base, const float* wl, uint32_t n, float* values, RegFile R) {
+    eval_spectral_each(sc, color, base, wl, n, R, [&](uint32_t k, float v) { values[k] = v; });
 }
 // brightness[k] += color(wl[k]) * probability * reflectance[k] for k < n
 PYR_HD void add_emission(const SceneView& sc, PathState& ps, uint32_t n, int32_t color, v3 incident, v3 normal, const float* tex,
                          float probability, RegFile R) {
     VmInputs in;
     in.wavelength = 0.0f; in.incident = incident; in.normal = normal; in.tex[0] = tex[0]; in.tex[1] = tex[1];
-    float c[MAX_SPECTRUM_SAMPLES];
-    eval_spectral(sc, color, in, ps.wl, n, c, R);
-    for (uint32_t k = 0; k < n; ++k) ps.bright[k] += c[k] * probability * ps.refl[k];
+    eval_spectral_each(sc, color, in, ps.wl, n, R, [&](uint32_t k, float c) { ps.bright[k] += c * probability * ps.refl[k]; });
 }
 PYR_HD void mul_reflectance(const SceneView& sc, PathState& ps, uint32_t n, int32_t color, v3 incident, v3 normal, const float* tex,
                             float probability, RegFile R) {
     VmInputs in;
     in.wavelength = 0.0f; in.incident = incident; in.normal = normal; in.tex[0] = tex[0]; in.tex[1] = tex[1];
-    float c[MAX_SPECTRUM_SAMPLES];
-    eval_spectral(sc, color, in, ps.wl, n, c, R);
-    for (uint32_t k = 0; k < n; ++k) ps.refl[k] *= c[k] * probability;
+    eval_spectral_each(sc, color, in, ps.wl, n, R, [&](uint32_t k, float c) { ps.refl[k] *= c * probability; });
 }
 
 struct PathCounters { uint32_t de_evals, de_iters; };
@@ -539,7 +539,14 @@ PYR_HD bool camera_step(const SceneView& sc, PathState& ps, const Ray* main_ray,
         // the wavelength, colour(wl[k]) is the same for all of them and is evaluated once.
         int32_t cached_program = -1;
         uint32_t cached_n = 0;
-        float c[MAX_SPECTRUM_SAMPLES];
+#if defined(__CUDA_ARCH__)
+        // [wavelength][thread] floats behind the staged visibility rays
+        float* const c_base = reinterpret_cast<float*>(pyr_dyn_smem + out.stage_base + 2 * max(sc.renderer.light_samples, 1u) * PYR_BLOCK) + threadIdx.x;
+#define PYR_C(k) c_base[(k) * PYR_BLOCK]
+#else
+        float c_local[MAX_SPECTRUM_SAMPLES];
+#define PYR_C(k) c_local[k]
+#endif
         for (uint32_t j = 0; j < ps.n_pending; ++j) {
             if (shadow_kinds[j] != KIND_MISS) continue;  // blocked
             const PendingLight pl = ps.pend[j];
@@ -550,12 +557,13 @@ PYR_HD bool camera_step(const SceneView& sc, PathState& ps, const Ray* main_ray,
                 VmInputs in;
                 in.wavelength = 0.0f; in.normal = ld3(pl.normal); in.tex[0] = pl.tex[0]; in.tex[1] = pl.tex[1];
                 in.incident = wavelength_only ? mk3(0, 0, 0) : ld3(shadow_rays[j].d);  // the ray is only fetched when the colour looks at it
-                eval_spectral(sc, pl.color_program, in, ps.wl, m, c, R);
+                eval_spectral_each(sc, pl.color_program, in, ps.wl, m, R, [&](uint32_t k, float v) { PYR_C(k) = v; });
                 cached_program = wavelength_only ? pl.color_program : -1;
                 cached_n = m;
             }
-            for (uint32_t k = 0; k < m; ++k) ps.bright[k] += c[k] * pl.probability * ps.refl[k];
+            for (uint32_t k = 0; k < m; ++k) ps.bright[k] += PYR_C(k) * pl.probability * ps.refl[k];
         }
+#undef PYR_C
         for (uint32_t k = 0; k < n; ++k) ps.refl[k] *= ps.pending_brdf;
         ps.flags &= ~PS_PENDING_FOLD;
         ps.n_pending = 0;
