@@ -30,7 +30,7 @@ import numpy as np  # noqa: E402
 
 SCENE = dict(width=1920, height=1080, spp=256, bounces=8, light_samples=4, spectrum_samples=10)
 WORKLOAD = "C2 dragon stand-in 871,200 tris + 3 planes + point light, 1920x1080, simple integrator S=10 B=8 L=4"
-NODE_BYTES, PRIM_BYTES, RAY_BYTES, HIT_BYTES = 64, 48, 32, 32
+NODE_BYTES, PRIM_BYTES, RAY_BYTES, HIT_BYTES = 128, 48, 32, 32  # Node4, Prim, Ray, Hit records (device_types.h)
 
 
 def build_project(args):
@@ -242,9 +242,10 @@ def run_product(args):
         r.counters(reset=True)
         r.render(seed=1000, spp=1, sample_offset=0, sample_stride=1, reset_film=False, pool_paths=args.pool, stats=True)
         cs = r.counters()
-        pairs_per_ray = cs["nodes_visited"] / 2.0 / max(cs["rays"], 1)
+        nodes_per_ray = cs["node_fetches"] / max(cs["rays"], 1)
+        boxes_per_ray = cs["nodes_visited"] / max(cs["rays"], 1)
         leaves_per_ray = cs["leaves_tested"] / max(cs["rays"], 1)
-        bytes_per_ray = RAY_BYTES + HIT_BYTES + pairs_per_ray * NODE_BYTES + leaves_per_ray * PRIM_BYTES
+        bytes_per_ray = RAY_BYTES + HIT_BYTES + nodes_per_ray * NODE_BYTES + leaves_per_ray * PRIM_BYTES
         trace_s, trace_n = c["trace_seconds"], max(c["trace_launches"], 1)
         rays_per_launch = c["rays"] / trace_n
         achieved = (c["rays"] * bytes_per_ray) / max(trace_s, 1e-12) / 1e9
@@ -257,7 +258,7 @@ def run_product(args):
             except Exception:
                 traffic = None
         roofline = {"bound": "hbm", "kernel": "k_trace", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "peak_source": peak_src, "bytes_per_ray": bytes_per_ray, "node_pairs_per_ray": pairs_per_ray,
+                    "traffic": traffic, "peak_source": peak_src, "bytes_per_ray": bytes_per_ray, "nodes_fetched_per_ray": nodes_per_ray, "boxes_tested_per_ray": boxes_per_ray,
                     "leaves_per_ray": leaves_per_ray, "rays_per_launch": rays_per_launch, "avg_launch_ms": 1e3 * trace_s / trace_n,
                     "trace_share_of_step": trace_s / max(c["trace_seconds"] + c["shade_seconds"], 1e-12),
                     "trace_mrays_per_s": c["rays"] / max(trace_s, 1e-12) / 1e6}

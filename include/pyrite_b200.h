@@ -93,6 +93,7 @@ typedef struct pyr_counters {
      * shade/regenerate kernel since the last reset */
     double trace_seconds, shade_seconds;
     uint64_t trace_launches, shade_launches;
+    uint64_t node_fetches; /* 128-byte BVH nodes fetched (stats mode); nodes_visited counts the boxes tested */
 } pyr_counters;
 
 /* renderer::Progress{progress: u8, message} (renderer/mod.rs:229-232); invoked on the calling

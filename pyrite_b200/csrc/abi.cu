@@ -253,7 +253,7 @@ pyr_status pyr_project_load(pyr_ctx* ctx, const void* ir_blob, size_t bytes) {
         upload(ctx->xyz, baked.xyz, s);
         upload(ctx->d65, baked.d65, s);
         SceneView v = baked.view;
-        v.nodes = ctx->nodes.as<Node>(); v.prims = ctx->prims.as<Prim>(); v.tri_shade = ctx->tri_shade.as<TriShade>();
+        v.nodes = ctx->nodes.as<Node4>(); v.prims = ctx->prims.as<Prim>(); v.tri_shade = ctx->tri_shade.as<TriShade>();
         v.tri_frames = ctx->tri_frames.as<TriFrames>(); v.planes = ctx->planes.as<PlaneRec>(); v.marched = ctx->marched.as<MarchedRec>();
         v.materials = ctx->materials.as<MaterialRec>(); v.components = ctx->components.as<ComponentRec>();
         v.programs = ctx->programs.as<ProgramRec>(); v.code = ctx->code.as<Instr>(); v.spectra = ctx->spectra.as<SpectrumRec>();
@@ -576,6 +576,7 @@ pyr_status pyr_counters_get(pyr_ctx* ctx, pyr_counters* out, int32_t reset) {
             out->leaves_tested = dc.leaves_tested;
             out->de_evals = dc.de_evals;
             out->de_iterations = dc.de_iterations;
+            out->node_fetches = dc.node_fetches;
         }
         if (reset) {
             CU(cudaMemsetAsync(ctx->counters.p, 0, sizeof(DeviceCounters), ctx->stream));

@@ -643,7 +643,7 @@ PYR_HD bool march_test(const MarchedRec& m, v3 o, v3 d, float& dist, uint32_t& e
 }
 
 // ---------------------------------------------------------------- World::intersect (world.rs:273-299)
-struct TraceStats { uint32_t nodes, leaves, de_evals, de_iters; };
+struct TraceStats { uint32_t nodes, leaves, de_evals, de_iters, fetches; };
 
 PYR_HD v3 prim_v1(const Prim& p) { return mk3(p.a.x, p.a.y, p.a.z); }
 PYR_HD v3 prim_e1(const Prim& p) { return mk3(p.a.w, p.b.x, p.b.y); }
@@ -660,12 +660,15 @@ PYR_HD bool occludes(uint32_t mode, float t, float limit) { return mode == 1 ? (
 // minimum (t, plane-before-leaf, rank) over the leaves whose boxes are hit - the reference's
 // answer whenever no leaf lies closer than its own box's entry distance by rounding.
 // 16-byte loads through the read-only path on the device
-PYR_HD Node fetch_node(const Node* p) {
+PYR_HD Node4 fetch_node(const Node4* p) {
 #if defined(__CUDA_ARCH__)
     const float4* q = reinterpret_cast<const float4*>(p);
-    const float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
-    Node n;
-    n.n0 = mk4(a.x, a.y, a.z, a.w); n.n1 = mk4(b.x, b.y, b.z, b.w); n.n2 = mk4(c.x, c.y, c.z, c.w); n.n3 = mk4(d.x, d.y, d.z, d.w);
+    const float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3), e = __ldg(q + 4), f = __ldg(q + 5);
+    const int4 ch = __ldg(reinterpret_cast<const int4*>(q + 6));
+    Node4 n;
+    n.lo_x = mk4(a.x, a.y, a.z, a.w); n.lo_y = mk4(b.x, b.y, b.z, b.w); n.lo_z = mk4(c.x, c.y, c.z, c.w);
+    n.hi_x = mk4(d.x, d.y, d.z, d.w); n.hi_y = mk4(e.x, e.y, e.z, e.w); n.hi_z = mk4(f.x, f.y, f.z, f.w);
+    n.child[0] = ch.x; n.child[1] = ch.y; n.child[2] = ch.z; n.child[3] = ch.w;
     return n;
 #else
     return *p;
@@ -706,9 +709,9 @@ struct Traversal {
     float cull;  // closest widened by a few ulps: boxes are only skipped beyond it (see node_step)
     float t, u, v;
     uint32_t rank, kind;
-    int sp, cur;
+    int sp, cur;       // cur: Node4 index (>= 0) or leaf code (< 0) to process next
     bool done;
-    uint32_t vn, vl, de_evals, de_iters;
+    uint32_t vn, vl, vf, de_evals, de_iters;  // boxes tested, leaves tested, nodes fetched (STATS)
 
     template <class Stack>
     PYR_HD void begin(const SceneView& sc, const Ray& ray, Stack& stack) {
@@ -721,7 +724,7 @@ struct Traversal {
         if (mode == 1) bound = limit > 0.0f ? sqrtf(limit) : 0.0f;
         else if (mode == 2) bound = limit;
         t = PYR_INF; u = 0; v = 0; rank = 0xFFFFFFFFu; kind = KIND_MISS;
-        vn = 0; vl = 0; de_evals = 0; de_iters = 0;
+        vn = 0; vl = 0; vf = 0; de_evals = 0; de_iters = 0;
         sp = 0; cur = 0; done = true;
         for (uint32_t i = 0; i < sc.n_planes; ++i) {
             float pt; v3 p;
@@ -742,6 +745,7 @@ struct Traversal {
         done = false;
     }
 
+    PYR_HD bool at_node() const { return cur >= 0; }
     // pop, dropping entries whose box now starts beyond the closest hit
     template <class Stack>
     PYR_HD void pop(Stack& stack) {
@@ -752,28 +756,39 @@ struct Traversal {
             if (!(entry_dist > cull)) { cur = stack.code(sp); return; }
         }
     }
-    // one interior node (cur >= 0): both children's boxes, nearest first
+    // one 4-wide node (cur >= 0): up to four boxes with the reference's slab arithmetic; descend into the
+    // nearest hit child and defer the others, farthest first, so that they pop nearest first
     template <class Stack>
     PYR_HD void node_step(const SceneView& sc, Stack& stack) {
-        const Node nd = fetch_node(sc.nodes + cur);
-        float d0, d1;
-        bool h0 = slab_test(mk3(nd.n0.x, nd.n0.y, nd.n0.z), mk3(nd.n0.w, nd.n1.x, nd.n1.y), o, inv, d0);
-        bool h1 = slab_test(mk3(nd.n1.z, nd.n1.w, nd.n2.x), mk3(nd.n2.y, nd.n2.z, nd.n2.w), o, inv, d1);
-        if (STATS) vn += 2;
-        // A box is skipped only when it starts beyond the closest hit by more than rounding: a leaf that ties with the
-        // current hit (a ray through a shared edge) can have a box entry a few ulps beyond its own hit distance, and the
-        // reference, walking in pre-order, would have tested it first (World::intersect's tie rule, world.rs:288-296).
-        h0 = h0 && !(d0 > cull) && !(mode != 0 && d0 > bound);
-        h1 = h1 && !(d1 > cull) && !(mode != 0 && d1 > bound);
-        const int c0 = (int)f_bits(nd.n3.x), c1 = (int)f_bits(nd.n3.y);
-        // branch-free choice of the child to descend into (the nearer hit one) and the one to defer
-        const bool both = h0 && h1;
-        const bool take1 = h1 && (!h0 || d1 < d0);
-        const int near_code = take1 ? c1 : c0, far_code = take1 ? c0 : c1;
-        const float far_dist = take1 ? d0 : d1;
-        if (both) stack.put(sp, far_code, far_dist);
-        sp += both ? 1 : 0;
-        if (h0 || h1) cur = near_code;
+        const Node4 nd = fetch_node(sc.nodes + cur);
+        const float lox[4] = {nd.lo_x.x, nd.lo_x.y, nd.lo_x.z, nd.lo_x.w}, loy[4] = {nd.lo_y.x, nd.lo_y.y, nd.lo_y.z, nd.lo_y.w};
+        const float loz[4] = {nd.lo_z.x, nd.lo_z.y, nd.lo_z.z, nd.lo_z.w}, hix[4] = {nd.hi_x.x, nd.hi_x.y, nd.hi_x.z, nd.hi_x.w};
+        const float hiy[4] = {nd.hi_y.x, nd.hi_y.y, nd.hi_y.z, nd.hi_y.w}, hiz[4] = {nd.hi_z.x, nd.hi_z.y, nd.hi_z.z, nd.hi_z.w};
+        float dist[4];
+        int code[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float dk;
+            bool h = slab_test(mk3(lox[k], loy[k], loz[k]), mk3(hix[k], hiy[k], hiz[k]), o, inv, dk);
+            code[k] = nd.child[k];
+            // A box is skipped only when it starts beyond the closest hit by more than rounding: a leaf that ties with the
+            // current hit (a ray through a shared edge) can have a box entry a few ulps beyond its own hit distance, and the
+            // reference, walking in pre-order, would have tested it first (World::intersect's tie rule, world.rs:288-296).
+            h = h && code[k] != NODE4_EMPTY && !(dk > cull) && !(mode != 0 && dk > bound);
+            if (STATS) vn += code[k] != NODE4_EMPTY ? 1u : 0u;
+            dist[k] = h ? dk : PYR_INF;
+            if (!h) code[k] = NODE4_EMPTY;
+        }
+        if (STATS) ++vf;
+        // sorting network on (dist, code), ascending; misses carry +inf and sink to the end
+#define PYR_CSWAP(a, b) { const bool sw = dist[b] < dist[a]; const float da = sw ? dist[b] : dist[a], db = sw ? dist[a] : dist[b]; \
+                          const int ca = sw ? code[b] : code[a], cb = sw ? code[a] : code[b]; dist[a] = da; dist[b] = db; code[a] = ca; code[b] = cb; }
+        PYR_CSWAP(0, 1) PYR_CSWAP(2, 3) PYR_CSWAP(0, 2) PYR_CSWAP(1, 3) PYR_CSWAP(1, 2)
+#undef PYR_CSWAP
+        if (code[3] != NODE4_EMPTY) stack.put(sp++, code[3], dist[3]);
+        if (code[2] != NODE4_EMPTY) stack.put(sp++, code[2], dist[2]);
+        if (code[1] != NODE4_EMPTY) stack.put(sp++, code[1], dist[1]);
+        if (code[0] != NODE4_EMPTY) cur = code[0];
         else pop(stack);
     }
     // one leaf (cur < 0): the primitive test of Shape::ray_intersect and World::intersect's acceptance rule
@@ -799,12 +814,12 @@ struct Traversal {
     }
     template <class Stack>
     PYR_HD void step(const SceneView& sc, Stack& stack) {
-        if (cur >= 0) node_step(sc, stack); else leaf_step(sc, stack);
+        if (at_node()) node_step(sc, stack); else leaf_step(sc, stack);
     }
 
     PYR_HD void finish(Hit& hit, TraceStats* stats) const {
         hit.t = t; hit.u = u; hit.v = v; hit.rank = rank; hit.kind = kind; hit.nodes = vn; hit.leaves = vl; hit.pad = 0;
-        if (STATS && stats) { stats->nodes += vn; stats->leaves += vl; stats->de_evals += de_evals; stats->de_iters += de_iters; }
+        if (STATS && stats) { stats->nodes += vn; stats->leaves += vl; stats->de_evals += de_evals; stats->de_iters += de_iters; stats->fetches += vf; }
     }
 };
 

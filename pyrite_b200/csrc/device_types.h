@@ -33,11 +33,19 @@ struct alignas(16) f4 { float x, y, z, w; };
 //   c.y = kind (uint bits), c.z = object id (insertion order, world.rs:75,182,229), c.w = material
 struct alignas(16) Prim { f4 a, b, c; };
 
-// Binary BVH node carrying BOTH children's boxes (the box values and the slab arithmetic are the
-// reference's, math.rs:184-207).  64 B = four 16-byte loads.
-//   n0 = (c0.min.xyz, c0.max.x)  n1 = (c0.max.y, c0.max.z, c1.min.x, c1.min.y)
-//   n2 = (c1.min.z, c1.max.xyz)  n3 = (child0, child1, -, -) as int bits; child < 0: leaf, rank = ~child
-struct alignas(16) Node { f4 n0, n1, n2, n3; };
+// 4-wide BVH node: the reference's binary tree (spatial/bvh.rs:13-155) with every second level folded away.
+// A node holds the boxes of up to four descendants of one binary node - its children, or its
+// grandchildren where a child is itself interior - with the reference's box VALUES, so every leaf is
+// still guarded by exactly its own box and its ancestors' boxes that remain.  Skipping the folded
+// ancestors' tests changes nothing: a child box lies inside its parent's and the slab test is monotone.
+// 128 B = eight 16-byte loads, boxes stored component-wise (lo_x[4], lo_y[4], ...).
+//   child[k] >= 0: Node4 index; < 0: leaf, rank = ~child; NODE4_EMPTY: no child in this slot
+struct alignas(16) Node4 {
+    f4 lo_x, lo_y, lo_z, hi_x, hi_y, hi_z;
+    int32_t child[4];
+    uint32_t pad[4];
+};
+constexpr int32_t NODE4_EMPTY = 0x7fffffff;
 
 // Per-triangle shading data in the same rank order.  64 B.
 struct alignas(16) TriShade { float n1[3], n2[3], n3[3]; float t1[2], t2[2], t3[2]; float area; };
@@ -164,7 +172,7 @@ struct TableRec { float lo, hi; uint32_t n, pad; };
 // The same struct points at host arrays when the stage functions are exercised by the CPU unit
 // tests (tests/host_emu.cpp).
 struct SceneView {
-    const Node* nodes;
+    const Node4* nodes;
     const Prim* prims;
     const TriShade* tri_shade;
     const TriFrames* tri_frames;

@@ -253,7 +253,7 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sc, const Ray*
     stack.entries = smem_stack + threadIdx.x;
     const uint32_t total = n_main + n_shadow;
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counters->rays, (unsigned long long)total);
-    unsigned long long nodes = 0, leaves = 0, evals = 0, iters = 0;
+    unsigned long long nodes = 0, leaves = 0, evals = 0, iters = 0, fetches = 0;
     Traversal<STATS> tr;
     tr.done = true;
     bool has_ray = false;
@@ -292,11 +292,11 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sc, const Ray*
         // interior nodes first, `steps` of them; then the lanes that stand at a leaf test it together (lanes
         // that reach a leaf early wait, which costs less than running the leaf code for one lane at a time)
         for (uint32_t k = 0; k < steps; ++k)
-            if (has_ray && !tr.done && tr.cur >= 0) tr.node_step(sc, stack);
-        if (has_ray && !tr.done && tr.cur < 0) tr.leaf_step(sc, stack);
+            if (has_ray && !tr.done && tr.at_node()) tr.node_step(sc, stack);
+        if (has_ray && !tr.done && !tr.at_node()) tr.leaf_step(sc, stack);
         if (has_ray && tr.done) {
             emit(ray_at, tr);
-            if (STATS) { nodes += tr.vn; leaves += tr.vl; evals += tr.de_evals; iters += tr.de_iters; }
+            if (STATS) { nodes += tr.vn; leaves += tr.vl; evals += tr.de_evals; iters += tr.de_iters; fetches += tr.vf; }
             has_ray = false;
         }
     }
@@ -304,10 +304,12 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sc, const Ray*
         for (int d = 16; d; d >>= 1) {
             nodes += __shfl_down_sync(FULL, nodes, d); leaves += __shfl_down_sync(FULL, leaves, d);
             evals += __shfl_down_sync(FULL, evals, d); iters += __shfl_down_sync(FULL, iters, d);
+            fetches += __shfl_down_sync(FULL, fetches, d);
         }
         if (lane_id() == 0) {
             atomicAdd(&counters->nodes_visited, nodes); atomicAdd(&counters->leaves_tested, leaves);
             atomicAdd(&counters->de_evals, evals); atomicAdd(&counters->de_iterations, iters);
+            atomicAdd(&counters->node_fetches, fetches);
         }
     }
 }
@@ -425,7 +427,7 @@ void launch_wave_simple(const SceneView& sc, const WaveArgs& a, cudaStream_t s) 
 }
 TraceTuning trace_tuning() {
     static TraceTuning t = [] {
-        TraceTuning v{8u, 4u};
+        TraceTuning v{8u, 2u};
         if (const char* e = getenv("PYR_TRACE_REFILL")) v.refill_min = (uint32_t)atoi(e);
         if (const char* e = getenv("PYR_TRACE_STEPS")) v.steps = (uint32_t)atoi(e);
         if (v.refill_min < 1) v.refill_min = 1;

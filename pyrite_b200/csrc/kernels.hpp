@@ -15,7 +15,7 @@ struct CamVertex;
 
 // Device-side work counters (one instance per context).
 struct DeviceCounters {
-    unsigned long long rays, path_samples, nodes_visited, leaves_tested, de_evals, de_iterations;
+    unsigned long long rays, path_samples, nodes_visited, leaves_tested, de_evals, de_iterations, node_fetches;
 };
 
 // Everything one wavefront iteration needs besides the scene.

@@ -849,15 +849,50 @@ BakedScene build_scene(const Document& input) {
         out.prims[rank] = p;
         out.tri_shade[rank] = ts;
     }
-    out.nodes.resize(tb.interiors.size());
-    for (size_t i = 0; i < tb.interiors.size(); ++i) {
-        const auto& in = tb.interiors[i];
-        Node n;
-        n.n0 = pack4(in.box[0].lo.x, in.box[0].lo.y, in.box[0].lo.z, in.box[0].hi.x);
-        n.n1 = pack4(in.box[0].hi.y, in.box[0].hi.z, in.box[1].lo.x, in.box[1].lo.y);
-        n.n2 = pack4(in.box[1].lo.z, in.box[1].hi.x, in.box[1].hi.y, in.box[1].hi.z);
-        n.n3 = pack4(bits_to_float((uint32_t)in.child[0]), bits_to_float((uint32_t)in.child[1]), 0.0f, 0.0f);
-        out.nodes[i] = n;
+    // fold the binary tree into 4-wide nodes: a Node4 per binary node that is the root or a grandchild-level entry
+    if (!tb.interiors.empty()) {
+        std::vector<int32_t> node4_of(tb.interiors.size(), -1);
+        std::vector<uint32_t> todo;  // binary interior indices that need a Node4
+        auto node4_for = [&](uint32_t binary) {
+            if (node4_of[binary] < 0) {
+                node4_of[binary] = (int32_t)out.nodes.size();
+                out.nodes.emplace_back();
+                todo.push_back(binary);
+            }
+            return node4_of[binary];
+        };
+        sv.root = node4_for((uint32_t)sv.root);  // the root is interior here (sv.root >= 0)
+        while (!todo.empty()) {
+            const uint32_t b = todo.back();
+            todo.pop_back();
+            struct Entry { int32_t code; Box box; };
+            Entry entries[4];
+            int n = 0;
+            for (int side = 0; side < 2; ++side) {
+                const int32_t c = tb.interiors[b].child[side];
+                if (c < 0) { entries[n++] = Entry{c, tb.interiors[b].box[side]}; continue; }
+                for (int g = 0; g < 2; ++g) {
+                    const int32_t gc = tb.interiors[c].child[g];
+                    entries[n++] = Entry{gc < 0 ? gc : node4_for((uint32_t)gc), tb.interiors[c].box[g]};
+                }
+            }
+            Node4 nd;
+            memset(&nd, 0, sizeof(nd));
+            const float inf = std::numeric_limits<float>::infinity();
+            float* comps[6] = {&nd.lo_x.x, &nd.lo_y.x, &nd.lo_z.x, &nd.hi_x.x, &nd.hi_y.x, &nd.hi_z.x};
+            for (int k = 0; k < 4; ++k) {
+                if (k < n) {
+                    const Box& bx = entries[k].box;
+                    const float v[6] = {bx.lo.x, bx.lo.y, bx.lo.z, bx.hi.x, bx.hi.y, bx.hi.z};
+                    for (int c = 0; c < 6; ++c) comps[c][k] = v[c];
+                    nd.child[k] = entries[k].code;
+                } else {
+                    for (int c = 0; c < 6; ++c) comps[c][k] = c < 3 ? inf : -inf;  // an empty slot can never be hit
+                    nd.child[k] = NODE4_EMPTY;
+                }
+            }
+            out.nodes[node4_of[b]] = nd;
+        }
     }
 
     // ---- lamps, in the order the reference collects them (world.rs:75-83, 250-262)

@@ -14,7 +14,7 @@
 namespace pyr {
 
 struct BakedScene {
-    std::vector<Node> nodes;
+    std::vector<Node4> nodes;
     std::vector<Prim> prims;            // leaf pre-order ("rank")
     std::vector<TriShade> tri_shade;    // by rank
     std::vector<TriFrames> tri_frames;  // by rank; empty unless some material has a normal map

@@ -71,12 +71,12 @@ struct AbiRay { float o[3], pad0, d[3], pad1; };
 struct AbiHit { uint32_t prim_id, kind; float t, u, v; };
 void emu_trace(void* h, const AbiRay* rays, size_t n, AbiHit* hits, uint64_t* stats3) {
     Emu* e = (Emu*)h;
-    TraceStats st{0, 0, 0, 0};
+    TraceStats st{0, 0, 0, 0, 0};
     uint64_t nodes = 0, leaves = 0;
     for (size_t i = 0; i < n; ++i) {
         Ray r = make_ray(mk3(rays[i].o[0], rays[i].o[1], rays[i].o[2]), mk3(rays[i].d[0], rays[i].d[1], rays[i].d[2]), 0, 0.0f);
         Hit hit;
-        st = TraceStats{0, 0, 0, 0};
+        st = TraceStats{0, 0, 0, 0, 0};
         trace_ray<true>(e->view, r, hit, &st);
         nodes += st.nodes; leaves += st.leaves;
         AbiHit o;

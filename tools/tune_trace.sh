@@ -1,1 +1,1 @@
-for r in 4 8 12; do for st in 2 3 4 6 8; do echo -n "refill=$r steps=$st: "; PYR_TRACE_REFILL=$r PYR_TRACE_STEPS=$st python tools/profile_step.py 8 | grep -o "trace [0-9.]* ms"; done; done
+for r in 6 8 12; do for st in 1 2 3 4; do echo -n "refill=$r steps=$st: "; PYR_TRACE_REFILL=$r PYR_TRACE_STEPS=$st python tools/profile_step.py 8 | grep -o "trace [0-9.]* ms"; done; done
