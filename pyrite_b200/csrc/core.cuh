@@ -712,6 +712,7 @@ struct Traversal {
     int sp, cur;       // cur: Node4 index (>= 0) or leaf code (< 0) to process next
     bool done;
     uint32_t vn, vl, vf, de_evals, de_iters;  // boxes tested, leaves tested, nodes fetched (STATS)
+    uint32_t march_mask;  // ray-marched shapes whose leaf was reached: sphere-traced after the walk (resolve_marched)
 
     template <class Stack>
     PYR_HD void begin(const SceneView& sc, const Ray& ray, Stack& stack) {
@@ -724,7 +725,7 @@ struct Traversal {
         if (mode == 1) bound = limit > 0.0f ? sqrtf(limit) : 0.0f;
         else if (mode == 2) bound = limit;
         t = PYR_INF; u = 0; v = 0; rank = 0xFFFFFFFFu; kind = KIND_MISS;
-        vn = 0; vl = 0; vf = 0; de_evals = 0; de_iters = 0;
+        vn = 0; vl = 0; vf = 0; de_evals = 0; de_iters = 0; march_mask = 0;
         sp = 0; cur = 0; done = true;
         for (uint32_t i = 0; i < sc.n_planes; ++i) {
             float pt; v3 p;
@@ -802,7 +803,13 @@ struct Traversal {
         bool ok;
         if (k == KIND_TRIANGLE) ok = triangle_test(prim_v1(pr), prim_e1(pr), prim_e2(pr), o, d, ht, hu, hv);
         else if (k == KIND_SPHERE) { v3 p; ok = sphere_test(prim_v1(pr), pr.a.w, o, d, ht, p); }
-        else ok = march_test(sc.marched[f_bits(pr.a.x)], o, d, ht, de_evals, de_iters);
+        else {
+            // Sphere tracing is hundreds of distance-estimator evaluations: it is not run here, one lane at a time,
+            // but after the walk (resolve_marched / k_march), where every lane marches.  The result is the same
+            // lexicographic minimum (t, rank); only the culling by `closest` is less tight meanwhile.
+            march_mask |= 1u << (f_bits(pr.a.x) & 31u);
+            ok = false;
+        }
         if (ok && ht > DIST_EPSILON) {
             if (mode != 0) {
                 if (occludes(mode, ht, limit)) { t = ht; u = hu; v = hv; rank = r; kind = k; done = true; return; }
@@ -817,6 +824,41 @@ struct Traversal {
         if (at_node()) node_step(sc, stack); else leaf_step(sc, stack);
     }
 
+    // Shape::RayMarched leaves reached by the walk (shapes/mod.rs:120-154), merged with World::intersect's rule
+    PYR_HD void resolve_marched(const SceneView& sc) {
+        uint32_t m = march_mask;
+        march_mask = 0;
+        while (m) {
+#if defined(__CUDA_ARCH__)
+            const int i = __ffs((int)m) - 1;
+#else
+            const int i = __builtin_ffs((int)m) - 1;
+#endif
+            m &= m - 1u;
+            const MarchedRec& mr = sc.marched[i];
+            float ht = 0.0f;
+            if (march_test(mr, o, d, ht, de_evals, de_iters) && ht > DIST_EPSILON) {
+                if (mode != 0) {
+                    if (occludes(mode, ht, limit)) { t = ht; u = 0; v = 0; rank = mr.rank; kind = KIND_RAY_MARCHED; return; }
+                } else if (ht < closest || (ht == closest && kind != KIND_PLANE && mr.rank < rank)) {
+                    closest = ht; cull = ht * CULL_SLACK; t = ht; u = 0; v = 0; rank = mr.rank; kind = KIND_RAY_MARCHED;
+                }
+            }
+        }
+    }
+    // resume from a stored result (k_march): the ray and what the walk found so far
+    PYR_HD void resume(const Ray& ray, float t_, float u_, float v_, uint32_t rank_, uint32_t kind_, uint32_t mask) {
+        o = ld3(ray.o); d = ld3(ray.d);
+        mode = ray.mode; limit = ray.limit;
+        t = t_; u = u_; v = v_; rank = rank_; kind = kind_;
+        closest = kind_ == KIND_MISS ? PYR_INF : t_;
+        cull = closest * CULL_SLACK;
+        bound = PYR_INF;
+        vn = 0; vl = 0; vf = 0; de_evals = 0; de_iters = 0;
+        sp = 0; cur = 0; done = true;
+        march_mask = mask;
+    }
+
     PYR_HD void finish(Hit& hit, TraceStats* stats) const {
         hit.t = t; hit.u = u; hit.v = v; hit.rank = rank; hit.kind = kind; hit.nodes = vn; hit.leaves = vl; hit.pad = 0;
         if (STATS && stats) { stats->nodes += vn; stats->leaves += vl; stats->de_evals += de_evals; stats->de_iters += de_iters; stats->fetches += vf; }
@@ -828,6 +870,7 @@ PYR_HD void trace_ray(const SceneView& sc, const Ray& ray, Hit& hit, TraceStats*
     Traversal<STATS> tr;
     tr.begin(sc, ray, stack);
     while (!tr.done) tr.step(sc, stack);
+    if (tr.march_mask && !(tr.mode != 0 && tr.kind != KIND_MISS)) tr.resolve_marched(sc);
     tr.finish(hit, stats);
 }
 

@@ -318,8 +318,12 @@ struct EmitHit {
     Hit* hits;
     uint32_t* shadow_kinds;
     uint32_t shadow_offset;
+    uint2* march_queue;
+    uint32_t* march_count;
     template <class T>
     __device__ __forceinline__ void operator()(uint32_t at, const T& tr) const {
+        // rays that reached ray-marched leaves (and are not decided yet) go on to the sphere-tracing kernel
+        if (tr.march_mask && !(tr.mode != 0 && tr.kind != KIND_MISS)) march_queue[atomicAdd(march_count, 1u)] = make_uint2(at, tr.march_mask);
         if (at >= shadow_offset) { shadow_kinds[at - shadow_offset] = tr.kind; return; }  // visibility rays only report blocked / unblocked
         float4* dst = reinterpret_cast<float4*>(hits + at);
         dst[0] = make_float4(tr.t, tr.u, tr.v, __uint_as_float(tr.rank));
@@ -329,8 +333,108 @@ struct EmitHit {
 
 template <bool STATS>
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace(const SceneView sc, const TraceArgs a) {
-    EmitHit emit{a.hits, a.shadow_kinds, a.shadow_offset};
+    EmitHit emit{a.hits, a.shadow_kinds, a.shadow_offset, a.march_queue, a.march_count};
     trace_persistent<STATS>(sc, a.rays, a.count[0], a.count[1], a.shadow_offset, a.cursor, a.counters, false, a.refill_min, a.steps, emit);
+}
+
+// Stage 3: sphere tracing (Shape::RayMarched, shapes/mod.rs:120-154 + shapes/distance_estimators.rs) for the rays
+// whose walk reached ray-marched leaves; every lane marches, merging into the stored result with World::intersect's rule.
+template <bool STATS>
+__global__ void __launch_bounds__(TRACE_THREADS) k_march(const SceneView sc, const TraceArgs a, uint32_t* cursor) {
+    // Persistent warps with lane-level refill, like the walk: march lengths range from a handful of steps to
+    // thousands (grazing rays creep at the 1e-4 minimum step), so a lane that finishes takes the next ray at once.
+    const uint32_t n = *a.march_count;
+    unsigned long long evals = 0, iters = 0;
+    Traversal<STATS> tr;        // the ray and the result so far (merging rule of World::intersect)
+    bool active = false, marching = false, decided = false;
+    uint32_t at = 0, shape = 0;
+    float total = 0.0f, hi = 0.0f;
+    v3 origin = mk3(0, 0, 0);
+    uint32_t pool_base = 0, pool_left = 0;
+    bool exhausted = false;
+    for (;;) {
+        const unsigned idle = __ballot_sync(FULL, !active);
+        if (idle) {
+            if (pool_left == 0 && !exhausted) {
+                uint32_t base = 0;
+                if (lane_id() == 0) base = atomicAdd(cursor, 32u);
+                base = __shfl_sync(FULL, base, 0);
+                if (base >= n) exhausted = true;
+                else { pool_base = base; pool_left = min(32u, n - base); }
+            }
+            if (pool_left) {
+                const uint32_t my = __popc(idle & ((1u << lane_id()) - 1u));
+                const uint32_t taken = min((uint32_t)__popc(idle), pool_left);
+                if (!active && my < taken) {
+                    const uint2 item = a.march_queue[pool_base + my];
+                    at = item.x;
+                    const Ray r = load_ray(a.rays + at);
+                    if (at >= a.shadow_offset) tr.resume(r, PYR_INF, 0.0f, 0.0f, 0xFFFFFFFFu, KIND_MISS, item.y);
+                    else {
+                        const float4* src = reinterpret_cast<const float4*>(a.hits + at);
+                        const float4 h0 = src[0], h1 = src[1];
+                        tr.resume(r, h0.x, h0.y, h0.z, __float_as_uint(h0.w), __float_as_uint(h1.x), item.y);
+                    }
+                    active = true; marching = false; decided = false;
+                }
+                pool_base += taken;
+                pool_left -= taken;
+            } else if (idle == FULL && exhausted) {
+                break;
+            }
+        }
+#pragma unroll 1
+        for (int k = 0; k < 8; ++k) {
+            if (!active) continue;
+            float hit_t = 0.0f;
+            bool have_hit = false;
+            if (!marching) {
+                if (decided || tr.march_mask == 0) {  // this ray is finished: store what changed
+                    if (at >= a.shadow_offset) { if (tr.kind != KIND_MISS) a.shadow_kinds[at - a.shadow_offset] = tr.kind; }
+                    else if (tr.kind == KIND_RAY_MARCHED) {
+                        float4* dst = reinterpret_cast<float4*>(a.hits + at);
+                        dst[0] = make_float4(tr.t, tr.u, tr.v, __uint_as_float(tr.rank));
+                        dst[1] = make_float4(__uint_as_float(tr.kind), 0.0f, 0.0f, 0.0f);
+                    }
+                    if (STATS) { evals += tr.de_evals; iters += tr.de_iters; }
+                    active = false;
+                    continue;
+                }
+                shape = (uint32_t)(__ffs((int)tr.march_mask) - 1);  // next candidate: Shape::RayMarched branch of ray_intersect
+                tr.march_mask &= tr.march_mask - 1u;
+                const MarchedRec& mr = sc.marched[shape];
+                float lo;
+                if (bounds_test(mr, tr.o, tr.d, lo, hi)) {
+                    origin = tr.o + (-bounds_center(mr));
+                    total = lo;
+                    marching = total < hi;
+                    if (!marching && total <= hi) { have_hit = true; hit_t = total; }
+                }
+            } else {
+                const MarchedRec& mr = sc.marched[shape];
+                const v3 p = origin + tr.d * total;
+                ++tr.de_evals;
+                const float distance = estimate_distance(mr, p, tr.de_iters);
+                total += distance;
+                if (distance < DIST_EPSILON || total > hi || !(total < hi)) {
+                    marching = false;
+                    if (total <= hi) { have_hit = true; hit_t = total; }
+                }
+            }
+            if (have_hit && hit_t > DIST_EPSILON) {
+                const uint32_t rank = sc.marched[shape].rank;
+                if (tr.mode != 0) {
+                    if (occludes(tr.mode, hit_t, tr.limit)) { tr.t = hit_t; tr.rank = rank; tr.kind = KIND_RAY_MARCHED; decided = true; }
+                } else if (hit_t < tr.closest || (hit_t == tr.closest && tr.kind != KIND_PLANE && rank < tr.rank)) {
+                    tr.closest = hit_t; tr.t = hit_t; tr.u = 0.0f; tr.v = 0.0f; tr.rank = rank; tr.kind = KIND_RAY_MARCHED;
+                }
+            }
+        }
+    }
+    if (STATS) {
+        for (int d = 16; d; d >>= 1) { evals += __shfl_down_sync(FULL, evals, d); iters += __shfl_down_sync(FULL, iters, d); }
+        if (lane_id() == 0) { atomicAdd(&a.counters->de_evals, evals); atomicAdd(&a.counters->de_iterations, iters); }
+    }
 }
 
 // pyr_trace seam: pyr_ray (32 B) in, pyr_hit (20 B) out; always closest-hit mode
@@ -338,8 +442,11 @@ struct AbiHit { uint32_t prim_id, kind; float t, u, v; };
 struct EmitAbiHit {
     AbiHit* hits;
     const Prim* prims;
+    const SceneView* scene;
     template <class T>
-    __device__ __forceinline__ void operator()(uint32_t at, const T& tr) const {
+    __device__ __forceinline__ void operator()(uint32_t at, const T& tr_in) const {
+        T tr = tr_in;
+        if (tr.march_mask) tr.resolve_marched(*scene);  // the parity seam resolves sphere tracing in place
         AbiHit o;
         o.kind = tr.kind; o.t = tr.t; o.u = tr.u; o.v = tr.v;
         if (tr.kind == KIND_MISS) o.prim_id = 0xFFFFFFFFu;
@@ -351,7 +458,7 @@ struct EmitAbiHit {
 template <bool STATS>
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace_batch(const SceneView sc, const Ray* rays, uint32_t n, AbiHit* hits, uint32_t* cursor,
                                                                DeviceCounters* counters, uint32_t refill_min, uint32_t steps) {
-    EmitAbiHit emit{hits, sc.prims};
+    EmitAbiHit emit{hits, sc.prims, &sc};
     trace_persistent<STATS>(sc, rays, n, 0u, 0u, cursor, counters, true, refill_min, steps, emit);
 }
 
@@ -443,6 +550,12 @@ void launch_trace(const SceneView& sc, const TraceArgs& a_in, int grid_blocks, c
     a.refill_min = t.refill_min; a.steps = t.steps;
     if (a.stats) k_trace<true><<<grid_blocks, TRACE_THREADS, 0, s>>>(sc, a);
     else k_trace<false><<<grid_blocks, TRACE_THREADS, 0, s>>>(sc, a);
+}
+void launch_march(const SceneView& sc, const TraceArgs& a_in, int grid_blocks, cudaStream_t s) {
+    TraceArgs a = a_in;
+    cudaMemsetAsync(a.cursor, 0, sizeof(uint32_t), s);  // the walk's cursor is free again
+    if (a.stats) k_march<true><<<grid_blocks, TRACE_THREADS, 0, s>>>(sc, a, a.cursor);
+    else k_march<false><<<grid_blocks, TRACE_THREADS, 0, s>>>(sc, a, a.cursor);
 }
 void launch_trace_batch(const SceneView& sc, const void* rays32, size_t n, void* hits20, uint32_t* cursor, DeviceCounters* counters, int stats,
                         int grid_blocks, cudaStream_t s) {

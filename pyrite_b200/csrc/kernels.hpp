@@ -59,6 +59,8 @@ struct TraceArgs {
     DeviceCounters* counters;
     int stats;
     uint32_t refill_min, steps;  // lane-refill threshold and traversal steps between refill checks (tuning)
+    uint2* march_queue;          // (ray index, candidate mask) of rays that reached ray-marched leaves
+    uint32_t* march_count;       // device counter (zeroed before the launch)
 };
 struct TraceTuning { uint32_t refill_min, steps; };
 TraceTuning trace_tuning();
@@ -68,6 +70,7 @@ void launch_pool_reset(PathCore* paths, uint32_t pool, cudaStream_t s);
 void launch_wave_simple(const SceneView& sc, const WaveArgs& a, cudaStream_t s);
 void launch_wave_bidirectional(const SceneView& sc, const WaveArgs& a, cudaStream_t s);
 void launch_trace(const SceneView& sc, const TraceArgs& a, int grid_blocks, cudaStream_t s);
+void launch_march(const SceneView& sc, const TraceArgs& a, int grid_blocks, cudaStream_t s);
 
 // ABI seams
 void launch_trace_batch(const SceneView& sc, const void* rays32, size_t n, void* hits20, uint32_t* cursor, DeviceCounters* counters, int stats,
