@@ -64,7 +64,7 @@ struct pyr_ctx {
     DeviceBuffer nodes, prims, tri_shade, tri_frames, planes, marched, materials, components, programs, code, spectra, spectrum_data,
         textures, texels, lamps, tiles, burns, xyz, d65;
     DeviceBuffer film, develop_params, counters, scalars, tile_first;
-    DeviceBuffer paths, pend, bidir, rays[2], hits, shadow_kinds, march_queue, light_vertices, cam_vertices, bin_count, bin_list;
+    DeviceBuffer paths, pend, bidir, rays[2], hits, shadow_kinds, march_queue[2], march_key, light_vertices, cam_vertices, bin_count, bin_list;
     uint32_t shadow_per_path = 1;
     DeviceBuffer scratch_a, scratch_b;
     uint32_t pool = 0;
@@ -74,10 +74,10 @@ struct pyr_ctx {
     unsigned long long* pinned = nullptr;  // [0] ray count, [1] next sample
 
     size_t film_floats() const { return (size_t)view.film.width * view.film.height * view.film.bins * 2; }
-    // scalars: [0..1] counts A {path rays, visibility rays}, [2..3] counts B, [4] trace cursor, [5] march count, [6..7] next_sample (u64)
+    // scalars: [0..1] counts A {path rays, visibility rays}, [2..3] counts B, [4] trace cursor, [6..7] next_sample (u64), [8..9] march counts, [10..11] march cursors
     uint32_t* count(int i) const { return scalars.as<uint32_t>() + 2 * i; }
     uint32_t* cursor() const { return scalars.as<uint32_t>() + 4; }
-    uint32_t* march_count() const { return scalars.as<uint32_t>() + 5; }
+    uint32_t* march_count() const { return scalars.as<uint32_t>() + 8; }
     unsigned long long* next_sample() const { return (unsigned long long*)(scalars.as<uint32_t>() + 6); }
 };
 
@@ -134,7 +134,12 @@ void ensure_pool(pyr_ctx* ctx, uint32_t pool) {
     ctx->rays[1].ensure(ray_cap * sizeof(Ray));
     ctx->hits.ensure((size_t)pool * sizeof(Hit));
     ctx->shadow_kinds.ensure((size_t)pool * ctx->shadow_per_path * sizeof(uint32_t));
-    if (ctx->view.n_marched) ctx->march_queue.ensure(ray_cap * sizeof(uint2));
+    if (ctx->view.n_marched) {
+        const size_t items = ray_cap * std::min<uint32_t>(ctx->view.n_marched, 4);
+        ctx->march_queue[0].ensure(items * sizeof(uint2));
+        ctx->march_queue[1].ensure(items * sizeof(uint2));
+        ctx->march_key.ensure((size_t)pool * sizeof(unsigned long long));
+    }
     if (bidir) {
         ctx->light_vertices.ensure((size_t)pool * (R.light_bounces + 1) * light_vertex_bytes());
         ctx->cam_vertices.ensure((size_t)pool * std::max<uint32_t>(R.bounces, 1) * cam_vertex_bytes());
@@ -211,7 +216,7 @@ void pyr_shutdown(pyr_ctx* ctx) {
     DeviceBuffer* all[] = {&ctx->nodes, &ctx->prims, &ctx->tri_shade, &ctx->tri_frames, &ctx->planes, &ctx->marched, &ctx->materials,
                            &ctx->components, &ctx->programs, &ctx->code, &ctx->spectra, &ctx->spectrum_data, &ctx->textures, &ctx->texels,
                            &ctx->lamps, &ctx->tiles, &ctx->burns, &ctx->xyz, &ctx->d65, &ctx->film, &ctx->develop_params, &ctx->counters,
-                           &ctx->scalars, &ctx->tile_first, &ctx->paths, &ctx->pend, &ctx->bidir, &ctx->bin_count, &ctx->bin_list, &ctx->rays[0], &ctx->rays[1], &ctx->hits, &ctx->shadow_kinds, &ctx->march_queue, &ctx->light_vertices, &ctx->cam_vertices,
+                           &ctx->scalars, &ctx->tile_first, &ctx->paths, &ctx->pend, &ctx->bidir, &ctx->bin_count, &ctx->bin_list, &ctx->rays[0], &ctx->rays[1], &ctx->hits, &ctx->shadow_kinds, &ctx->march_queue[0], &ctx->march_queue[1], &ctx->march_key, &ctx->light_vertices, &ctx->cam_vertices,
                            &ctx->scratch_a, &ctx->scratch_b};
     for (DeviceBuffer* b : all) b->release();
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -437,11 +442,14 @@ pyr_status pyr_render(pyr_ctx* ctx, const pyr_render_params* params, pyr_progres
                 t.cursor = ctx->cursor();
                 t.counters = ctx->counters.as<DeviceCounters>();
                 t.stats = stats;
-                t.march_queue = ctx->march_queue.as<uint2>();
+                t.march_queue[0] = ctx->march_queue[0].as<uint2>();
+                t.march_queue[1] = ctx->march_queue[1].as<uint2>();
                 t.march_count = ctx->march_count();
-                if (ctx->view.n_marched) CU(cudaMemsetAsync(ctx->march_count(), 0, sizeof(uint32_t), s));
+                t.march_capacity = (uint32_t)(ctx->march_queue[0].bytes / sizeof(uint2));
+                t.march_key = ctx->march_key.as<unsigned long long>();
+                if (ctx->view.n_marched) CU(cudaMemsetAsync(ctx->march_count(), 0, 4 * sizeof(uint32_t), s));
                 launch_trace(ctx->view, t, trace_blocks, s);
-                if (ctx->view.n_marched) { launch_march(ctx->view, t, trace_blocks, s); launches += 1; }
+                if (ctx->view.n_marched) { launch_march(ctx->view, t, trace_blocks, s); launches += 2; }
                 if (timing) CU(cudaEventRecord(ctx->timing_events[3 * b + 2], s));
                 cur = nxt;
                 ++iterations;

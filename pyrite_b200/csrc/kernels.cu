@@ -314,16 +314,44 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sc, const Ray*
     }
 }
 
+// (distance, tie rank) packed so that an unsigned 64-bit minimum is World::intersect's choice: smaller distance first
+// (positive floats order like their bit patterns), then planes before BVH leaves, then the earlier leaf (lower rank)
+__device__ __forceinline__ unsigned long long pack_hit(float t, uint32_t kind, uint32_t rank) {
+    if (kind == KIND_MISS) return ~0ull;
+    const uint32_t tie = kind == KIND_PLANE ? rank : (0x80000000u | rank);
+    return ((unsigned long long)__float_as_uint(t) << 32) | tie;
+}
+
 struct EmitHit {
     Hit* hits;
     uint32_t* shadow_kinds;
     uint32_t shadow_offset;
-    uint2* march_queue;
+    uint2* march_queue0;
+    uint2* march_queue1;
     uint32_t* march_count;
+    uint32_t march_capacity;
+    unsigned long long* march_key;
+    const MarchedRec* marched;
     template <class T>
     __device__ __forceinline__ void operator()(uint32_t at, const T& tr) const {
-        // rays that reached ray-marched leaves (and are not decided yet) go on to the sphere-tracing kernel
-        if (tr.march_mask && !(tr.mode != 0 && tr.kind != KIND_MISS)) march_queue[atomicAdd(march_count, 1u)] = make_uint2(at, tr.march_mask);
+        // rays that reached ray-marched leaves (and are not decided yet) go on to the sphere-tracing kernels
+        if (tr.march_mask && !(tr.mode != 0 && tr.kind != KIND_MISS)) {
+            uint32_t m = tr.march_mask;
+            while (m) {
+                const uint32_t shape = (uint32_t)(__ffs((int)m) - 1);
+                m &= m - 1u;
+                const uint32_t type = marched[shape].estimator ? 1u : 0u;
+                // one atomicAdd per queue for the lanes that are here together
+                const unsigned peers = __match_any_sync(__activemask(), type);
+                const int leader = __ffs((int)peers) - 1;
+                uint32_t base = 0;
+                if ((int)lane_id() == leader) base = atomicAdd(march_count + type, (uint32_t)__popc(peers));
+                base = __shfl_sync(peers, base, leader);
+                const uint32_t pos = base + __popc(peers & ((1u << lane_id()) - 1u));
+                if (pos < march_capacity) (type ? march_queue1 : march_queue0)[pos] = make_uint2(at, shape);
+            }
+            if (at < shadow_offset) march_key[at] = pack_hit(tr.t, tr.kind, tr.rank);
+        }
         if (at >= shadow_offset) { shadow_kinds[at - shadow_offset] = tr.kind; return; }  // visibility rays only report blocked / unblocked
         float4* dst = reinterpret_cast<float4*>(hits + at);
         dst[0] = make_float4(tr.t, tr.u, tr.v, __uint_as_float(tr.rank));
@@ -333,23 +361,31 @@ struct EmitHit {
 
 template <bool STATS>
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace(const SceneView sc, const TraceArgs a) {
-    EmitHit emit{a.hits, a.shadow_kinds, a.shadow_offset, a.march_queue, a.march_count};
+    EmitHit emit{a.hits, a.shadow_kinds, a.shadow_offset, a.march_queue[0], a.march_queue[1], a.march_count, a.march_capacity, a.march_key, sc.marched};
     trace_persistent<STATS>(sc, a.rays, a.count[0], a.count[1], a.shadow_offset, a.cursor, a.counters, false, a.refill_min, a.steps, emit);
 }
 
-// Stage 3: sphere tracing (Shape::RayMarched, shapes/mod.rs:120-154 + shapes/distance_estimators.rs) for the rays
-// whose walk reached ray-marched leaves; every lane marches, merging into the stored result with World::intersect's rule.
+// Stage 3: sphere tracing (Shape::RayMarched, shapes/mod.rs:120-154 + shapes/distance_estimators.rs:12-70) for the
+// (ray, shape) pairs whose leaf the walk reached.  Persistent warps with lane-level refill, one queue per estimator
+// type, and the march flattened down to the estimator's inner iteration: one loop trip is ONE iteration of
+// `Mandelbulb::get` / `QuaternionJulia::get` for every lane, whatever march step or ray the lane is at.  March
+// lengths (a handful to thousands of steps) and escape times (2 to `iterations` trips) vary per ray, so any coarser
+// unit leaves most lanes waiting.  Results merge per ray with a 64-bit atomicMin on (distance, tie rank).
 template <bool STATS>
-__global__ void __launch_bounds__(TRACE_THREADS) k_march(const SceneView sc, const TraceArgs a, uint32_t* cursor) {
-    // Persistent warps with lane-level refill, like the walk: march lengths range from a handful of steps to
-    // thousands (grazing rays creep at the 1e-4 minimum step), so a lane that finishes takes the next ray at once.
-    const uint32_t n = *a.march_count;
+__global__ void __launch_bounds__(TRACE_THREADS) k_march(const SceneView sc, const TraceArgs a, uint32_t* cursors) {
+    // every warp works on one estimator type at a time (half of them start with each) and moves to the other queue
+    // when its own is empty, so that both queues drain together and their long tails overlap
+    uint32_t TYPE = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) & 1u;
+    bool switched = false;
+    uint32_t n = min(a.march_count[TYPE], a.march_capacity);
+    const uint2* queue = a.march_queue[TYPE];
+    uint32_t* cursor = cursors + TYPE;
     unsigned long long evals = 0, iters = 0;
-    Traversal<STATS> tr;        // the ray and the result so far (merging rule of World::intersect)
-    bool active = false, marching = false, decided = false;
-    uint32_t at = 0, shape = 0;
-    float total = 0.0f, hi = 0.0f;
-    v3 origin = mk3(0, 0, 0);
+    bool active = false, in_de = false;
+    uint32_t at = 0, shape = 0, mode = 0, it = 0;
+    float limit = 0.0f, total = 0.0f, hi = 0.0f, r = 0.0f, dr = 1.0f;
+    v3 dir = mk3(0, 0, 0), origin = mk3(0, 0, 0), point = mk3(0, 0, 0);
+    f4 z = mk4(0, 0, 0, 0), dz = mk4(1, 0, 0, 0);
     uint32_t pool_base = 0, pool_left = 0;
     bool exhausted = false;
     for (;;) {
@@ -366,67 +402,93 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_march(const SceneView sc, con
                 const uint32_t my = __popc(idle & ((1u << lane_id()) - 1u));
                 const uint32_t taken = min((uint32_t)__popc(idle), pool_left);
                 if (!active && my < taken) {
-                    const uint2 item = a.march_queue[pool_base + my];
-                    at = item.x;
-                    const Ray r = load_ray(a.rays + at);
-                    if (at >= a.shadow_offset) tr.resume(r, PYR_INF, 0.0f, 0.0f, 0xFFFFFFFFu, KIND_MISS, item.y);
-                    else {
-                        const float4* src = reinterpret_cast<const float4*>(a.hits + at);
-                        const float4 h0 = src[0], h1 = src[1];
-                        tr.resume(r, h0.x, h0.y, h0.z, __float_as_uint(h0.w), __float_as_uint(h1.x), item.y);
+                    const uint2 item = queue[pool_base + my];
+                    at = item.x; shape = item.y;
+                    const Ray ray = load_ray(a.rays + at);
+                    const MarchedRec& mr = sc.marched[shape];
+                    const v3 o = ld3(ray.o);
+                    dir = ld3(ray.d); mode = ray.mode; limit = ray.limit;
+                    float lo;
+                    if (bounds_test(mr, o, dir, lo, hi)) {       // Shape::RayMarched branch of ray_intersect
+                        // nothing behind the walk's closest hit can win: the march only moves forward from `lo`
+                        const float best = at < a.shadow_offset ? __uint_as_float((uint32_t)(a.march_key[at] >> 32)) : PYR_INF;
+                        if (!(lo > best)) {                      // (`best` is NaN-patterned for a miss: the test passes)
+                            origin = o + (-bounds_center(mr));
+                            total = lo;
+                            if (total < hi) { active = true; in_de = false; }
+                            else if (total <= hi && total > DIST_EPSILON) {  // the loop body never runs
+                                if (mode == 0) atomicMin(a.march_key + at, pack_hit(total, KIND_RAY_MARCHED, mr.rank));
+                                else if (occludes(mode, total, limit)) a.shadow_kinds[at - a.shadow_offset] = KIND_RAY_MARCHED;
+                            }
+                        }
                     }
-                    active = true; marching = false; decided = false;
                 }
                 pool_base += taken;
                 pool_left -= taken;
             } else if (idle == FULL && exhausted) {
-                break;
+                if (switched) break;
+                switched = true;
+                TYPE ^= 1u;
+                n = min(a.march_count[TYPE], a.march_capacity);
+                queue = a.march_queue[TYPE];
+                cursor = cursors + TYPE;
+                exhausted = false;
+                continue;
             }
         }
 #pragma unroll 1
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < 16; ++k) {
             if (!active) continue;
-            float hit_t = 0.0f;
-            bool have_hit = false;
-            if (!marching) {
-                if (decided || tr.march_mask == 0) {  // this ray is finished: store what changed
-                    if (at >= a.shadow_offset) { if (tr.kind != KIND_MISS) a.shadow_kinds[at - a.shadow_offset] = tr.kind; }
-                    else if (tr.kind == KIND_RAY_MARCHED) {
-                        float4* dst = reinterpret_cast<float4*>(a.hits + at);
-                        dst[0] = make_float4(tr.t, tr.u, tr.v, __uint_as_float(tr.rank));
-                        dst[1] = make_float4(__uint_as_float(tr.kind), 0.0f, 0.0f, 0.0f);
-                    }
-                    if (STATS) { evals += tr.de_evals; iters += tr.de_iters; }
-                    active = false;
-                    continue;
+            const MarchedRec& mr = sc.marched[shape];
+            bool de_done = false;
+            if (!in_de) {  // start one distance estimate at the current march position
+                point = origin + dir * total;
+                if (STATS) ++evals;
+                it = 0; r = 0.0f; in_de = true;
+                if (TYPE == 0) { z = mk4(point.x, point.y, point.z, 0.0f); dr = 1.0f; }
+                else { z = mk4(point.x, point.y, point.z, mr.slice_plane); dz = mk4(1.0f, 0.0f, 0.0f, 0.0f); }
+            }
+            if (it >= mr.iterations) de_done = true;
+            else if (TYPE == 0) {  // one trip of Mandelbulb::get's loop (distance_estimators.rs:20-37)
+                const v3 zz = mk3(z.x, z.y, z.z);
+                r = length(zz);
+                if (r > mr.threshold) de_done = true;
+                else {
+                    if (STATS) ++iters;
+                    float theta = acosf(zz.z / r);
+                    float phi = atan2f(zz.y, zz.x);
+                    const float dc = mr.has_constant ? 0.0f : 1.0f;
+                    dr = powf(r, mr.power - 1.0f) * mr.power * dr + dc;
+                    const float zr = powf(r, mr.power);
+                    theta *= mr.power;
+                    phi *= mr.power;
+                    v3 nz = mk3(zr * sinf(theta) * cosf(phi), zr * sinf(phi) * sinf(theta), zr * cosf(theta));
+                    nz = nz + (mr.has_constant ? ld3(mr.mb_constant) : point);
+                    z = mk4(nz.x, nz.y, nz.z, 0.0f);
+                    ++it;
                 }
-                shape = (uint32_t)(__ffs((int)tr.march_mask) - 1);  // next candidate: Shape::RayMarched branch of ray_intersect
-                tr.march_mask &= tr.march_mask - 1u;
-                const MarchedRec& mr = sc.marched[shape];
-                float lo;
-                if (bounds_test(mr, tr.o, tr.d, lo, hi)) {
-                    origin = tr.o + (-bounds_center(mr));
-                    total = lo;
-                    marching = total < hi;
-                    if (!marching && total <= hi) { have_hit = true; hit_t = total; }
-                }
-            } else {
-                const MarchedRec& mr = sc.marched[shape];
-                const v3 p = origin + tr.d * total;
-                ++tr.de_evals;
-                const float distance = estimate_distance(mr, p, tr.de_iters);
-                total += distance;
-                if (distance < DIST_EPSILON || total > hi || !(total < hi)) {
-                    marching = false;
-                    if (total <= hi) { have_hit = true; hit_t = total; }
+            } else {               // one trip of QuaternionJulia::get's loop (distance_estimators.rs:57-66)
+                r = qlength(z);
+                if (r > mr.threshold) de_done = true;
+                else {
+                    if (STATS) ++iters;
+                    if (mr.variant == 0) { dz = scale4(qmul(dz, z), 2.0f); z = qmul(z, z); }
+                    else if (mr.variant == 1) { dz = scale4(qmul(qmul(dz, z), z), 3.0f); z = qmul(qmul(z, z), z); }
+                    else { dz = scale4(bicomplex_mul(bicomplex_mul(dz, z), z), 2.0f); z = bicomplex_mul(z, z); }
+                    z = add4(z, mr.constant);
+                    ++it;
                 }
             }
-            if (have_hit && hit_t > DIST_EPSILON) {
-                const uint32_t rank = sc.marched[shape].rank;
-                if (tr.mode != 0) {
-                    if (occludes(tr.mode, hit_t, tr.limit)) { tr.t = hit_t; tr.rank = rank; tr.kind = KIND_RAY_MARCHED; decided = true; }
-                } else if (hit_t < tr.closest || (hit_t == tr.closest && tr.kind != KIND_PLANE && rank < tr.rank)) {
-                    tr.closest = hit_t; tr.t = hit_t; tr.u = 0.0f; tr.v = 0.0f; tr.rank = rank; tr.kind = KIND_RAY_MARCHED;
+            if (!de_done) continue;
+            // the estimate is complete: one step of the march loop (shapes/mod.rs:127-135)
+            const float distance = TYPE == 0 ? 0.5f * logf(r) * r / dr : 0.5f * logf(r) * r / qlength(dz);
+            in_de = false;
+            total += distance;
+            if (distance < DIST_EPSILON || total > hi || !(total < hi)) {
+                active = false;
+                if (total <= hi && total > DIST_EPSILON) {
+                    if (mode == 0) atomicMin(a.march_key + at, pack_hit(total, KIND_RAY_MARCHED, mr.rank));
+                    else if (occludes(mode, total, limit)) a.shadow_kinds[at - a.shadow_offset] = KIND_RAY_MARCHED;
                 }
             }
         }
@@ -434,6 +496,23 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_march(const SceneView sc, con
     if (STATS) {
         for (int d = 16; d; d >>= 1) { evals += __shfl_down_sync(FULL, evals, d); iters += __shfl_down_sync(FULL, iters, d); }
         if (lane_id() == 0) { atomicAdd(&a.counters->de_evals, evals); atomicAdd(&a.counters->de_iterations, iters); }
+    }
+}
+
+// Write the merged result back into the hit record of every path ray a marched shape won.
+__global__ void __launch_bounds__(256) k_march_apply(const TraceArgs a, const MarchedRec* marched) {
+    for (int type = 0; type < 2; ++type) {
+        const uint32_t n = min(a.march_count[type], a.march_capacity);
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            const uint2 item = a.march_queue[type][i];
+            if (item.x >= a.shadow_offset) continue;
+            const unsigned long long key = a.march_key[item.x];
+            const uint32_t tie = (uint32_t)key;
+            if (key == ~0ull || !(tie & 0x80000000u) || (tie & 0x7fffffffu) != marched[item.y].rank) continue;  // this shape did not win
+            float4* dst = reinterpret_cast<float4*>(a.hits + item.x);
+            dst[0] = make_float4(__uint_as_float((uint32_t)(key >> 32)), 0.0f, 0.0f, __uint_as_float(tie & 0x7fffffffu));
+            dst[1] = make_float4(__uint_as_float((uint32_t)KIND_RAY_MARCHED), 0.0f, 0.0f, 0.0f);
+        }
     }
 }
 
@@ -553,9 +632,10 @@ void launch_trace(const SceneView& sc, const TraceArgs& a_in, int grid_blocks, c
 }
 void launch_march(const SceneView& sc, const TraceArgs& a_in, int grid_blocks, cudaStream_t s) {
     TraceArgs a = a_in;
-    cudaMemsetAsync(a.cursor, 0, sizeof(uint32_t), s);  // the walk's cursor is free again
-    if (a.stats) k_march<true><<<grid_blocks, TRACE_THREADS, 0, s>>>(sc, a, a.cursor);
-    else k_march<false><<<grid_blocks, TRACE_THREADS, 0, s>>>(sc, a, a.cursor);
+    uint32_t* cursors = a.march_count + 2;  // two work cursors behind the two queue counters (zeroed with them)
+    if (a.stats) k_march<true><<<grid_blocks, TRACE_THREADS, 0, s>>>(sc, a, cursors);
+    else k_march<false><<<grid_blocks, TRACE_THREADS, 0, s>>>(sc, a, cursors);
+    k_march_apply<<<grid_blocks, 256, 0, s>>>(a, sc.marched);
 }
 void launch_trace_batch(const SceneView& sc, const void* rays32, size_t n, void* hits20, uint32_t* cursor, DeviceCounters* counters, int stats,
                         int grid_blocks, cudaStream_t s) {

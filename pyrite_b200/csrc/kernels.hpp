@@ -59,8 +59,12 @@ struct TraceArgs {
     DeviceCounters* counters;
     int stats;
     uint32_t refill_min, steps;  // lane-refill threshold and traversal steps between refill checks (tuning)
-    uint2* march_queue;          // (ray index, candidate mask) of rays that reached ray-marched leaves
-    uint32_t* march_count;       // device counter (zeroed before the launch)
+    // sphere tracing (stage 3): one work item per (ray, ray-marched shape) whose leaf the walk reached, in one queue per
+    // distance-estimator type so that the lanes of a warp run the same estimator
+    uint2* march_queue[2];       // (ray index, shape index); [0] Mandelbulb, [1] quaternion Julia
+    uint32_t* march_count;       // two device counters (zeroed before the launch)
+    uint32_t march_capacity;     // entries per queue
+    unsigned long long* march_key;  // per path ray: (distance bits, tie rank) of the best hit so far, merged with atomicMin
 };
 struct TraceTuning { uint32_t refill_min, steps; };
 TraceTuning trace_tuning();
