@@ -46,6 +46,8 @@ def small_scene_kwargs():
         "snowflake": dict(width=64, height=48, spp=4),
         "fractals": dict(width=48, height=32, spp=2),
         "dragon": dict(width=64, height=48, spp=4, mesh=scenes.dragon_mesh(300, 24)),
+        # limits: portrait film (the vertical AspectRatio branch, film.rs:203-246), maximum spectrum / light samples
+        "edge_portrait": dict(_scene="cornell", width=40, height=72, spp=4, spectrum_samples=16, light_samples=8, bounces=2),
         # bidirectional integrator
         "bd_cornell": dict(_scene="cornell", integrator="bidirectional", width=48, height=48, spp=4),
         "bd_cornell_fractal": dict(_scene="cornell", integrator="bidirectional", fractal=True, width=48, height=48, spp=2),
@@ -57,7 +59,7 @@ def small_scene_kwargs():
     }
 
 
-SCENE_NAMES = ["cornell", "spheres", "diamonds", "textures", "rgb_emission", "snowflake", "fractals", "dragon"]
+SCENE_NAMES = ["cornell", "spheres", "diamonds", "textures", "rgb_emission", "snowflake", "fractals", "dragon", "edge_portrait", "lua_orbs"]
 BIDIR_NAMES = ["bd_cornell", "bd_cornell_fractal", "bd_glass_dragon", "bd_diamonds", "bd_spheres", "bd_c5"]
 MESH_SCENES = ["cornell", "diamonds", "textures", "snowflake", "dragon", "spheres", "rgb_emission"]
 
@@ -68,6 +70,12 @@ def scene_ir(name, **override):
     from pyrite_b200 import project, scenes
 
     key = (name, tuple(sorted((k, v) for k, v in override.items() if not hasattr(v, "position"))))
+    if name == "lua_orbs":  # a project.lua through the Lua loader: directional light, bounds.sphere, clamp, curve spectra
+        from pyrite_b200 import lua_project
+
+        if key not in _ir_cache:
+            _ir_cache[key] = lua_project.load_project_ir(ROOT / "tests" / "golden" / "scenes" / "orbs.lua")
+        return _ir_cache[key]
     if key not in _ir_cache:
         kw = dict(small_scene_kwargs()[name])
         kw.update(override)

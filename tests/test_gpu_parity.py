@@ -17,7 +17,7 @@ from conftest import BIDIR_NAMES, SCENE_NAMES, scene_ir
 
 pytestmark = pytest.mark.gpu
 
-EXACT_SCENES = ["cornell", "spheres", "diamonds", "textures", "rgb_emission", "snowflake", "dragon"]
+EXACT_SCENES = ["cornell", "spheres", "diamonds", "textures", "rgb_emission", "snowflake", "dragon", "edge_portrait"]
 
 
 @pytest.mark.parametrize("name", SCENE_NAMES)
@@ -88,24 +88,24 @@ def luminance_stats(xo, xg):
 
 @pytest.mark.parametrize("name", SCENE_NAMES)
 def test_films_on_identical_streams(name, gpu_renderer_factory, oracle_factory):
-    spp = {"fractals": 8}.get(name, 16)
+    spp = {"fractals": 8, "lua_orbs": 8}.get(name, 16)
     r, o = gpu_renderer_factory(name), oracle_factory(name)
     r.render(seed=5, spp=spp)
     o.render(seed=5, spp=spp)
     fg, fo = r.film(), o.film()
-    if name != "fractals":
+    if name not in ("fractals", "lua_orbs"):
         assert np.array_equal(fg[..., 1], fo[..., 1]), "per-bin weights (sample counts) differ"
     xg, sg = r.develop()
     xo, so = o.develop()
     dmean, rmse, off = luminance_stats(xo, xg)
     print(f"{name}: mean-Y rel err {dmean:.2e}, RMSE/mean {rmse:.2e}, pixels off by >5% {off:.2%}")
-    if name == "fractals":
+    if name in ("fractals", "lua_orbs"):
         # the ray-marched normal is a difference of nearly equal distance estimates (shapes/mod.rs:387-405), so device-vs-glibc
         # ULPs decorrelate the bounce directions: compare against the oracle's own noise floor (independent-seed mode)
         o.render(seed=6, spp=spp)
         xo2, _ = o.develop()
         _, floor, _ = luminance_stats(xo, xo2)
-        print(f"fractals: oracle-vs-oracle noise floor RMSE/mean {floor:.2e}")
+        print(f"{name}: oracle-vs-oracle noise floor RMSE/mean {floor:.2e}")
         assert dmean <= max(1e-2, 2.0 * floor / np.sqrt(xo.shape[0] * xo.shape[1])) and rmse <= 1.5 * floor
     elif name == "textures":
         assert dmean <= 1e-2 and off <= 0.05
