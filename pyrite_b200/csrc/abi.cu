@@ -64,7 +64,7 @@ struct pyr_ctx {
     DeviceBuffer nodes, prims, tri_shade, tri_frames, planes, marched, materials, components, programs, code, spectra, spectrum_data,
         textures, texels, lamps, tiles, burns, xyz, d65;
     DeviceBuffer film, develop_params, counters, scalars, tile_first;
-    DeviceBuffer paths, pend, bidir, rays[2], hits, shadow_kinds, march_queue[2], march_key, light_vertices, cam_vertices, bin_count, bin_list;
+    DeviceBuffer paths, pend, bidir, rays[2], hits, shadow_kinds, march_queue[2], march_key, light_vertices, cam_vertices, bin_count, bin_list, live_list;
     uint32_t shadow_per_path = 1;
     DeviceBuffer scratch_a, scratch_b;
     uint32_t pool = 0;
@@ -74,10 +74,11 @@ struct pyr_ctx {
     unsigned long long* pinned = nullptr;  // [0] ray count, [1] next sample
 
     size_t film_floats() const { return (size_t)view.film.width * view.film.height * view.film.bins * 2; }
-    // scalars: [0..1] counts A {path rays, visibility rays}, [2..3] counts B, [4] trace cursor, [6..7] next_sample (u64), [8..9] march counts, [10..11] march cursors
+    // scalars: [0..1] counts A {path rays, visibility rays}, [2..3] counts B, [4] trace cursor, [6..7] next_sample (u64), [8..9] march counts, [10..11] march cursors, [12..13] live-slot counts
     uint32_t* count(int i) const { return scalars.as<uint32_t>() + 2 * i; }
     uint32_t* cursor() const { return scalars.as<uint32_t>() + 4; }
     uint32_t* march_count() const { return scalars.as<uint32_t>() + 8; }
+    uint32_t* live_count(int i) const { return scalars.as<uint32_t>() + 12 + i; }
     unsigned long long* next_sample() const { return (unsigned long long*)(scalars.as<uint32_t>() + 6); }
 };
 
@@ -129,6 +130,7 @@ void ensure_pool(pyr_ctx* ctx, uint32_t pool) {
     ctx->pend.ensure((size_t)pool * MAX_LIGHT_SAMPLES * pending_light_bytes());
     ctx->bin_count.ensure(NUM_BINS * sizeof(uint32_t));
     ctx->bin_list.ensure((size_t)NUM_BINS * pool * sizeof(uint32_t));
+    ctx->live_list.ensure((size_t)pool * sizeof(uint32_t));
     if (bidir) ctx->bidir.ensure((size_t)pool * bidir_state_bytes());
     ctx->rays[0].ensure(ray_cap * sizeof(Ray));
     ctx->rays[1].ensure(ray_cap * sizeof(Ray));
@@ -216,7 +218,7 @@ void pyr_shutdown(pyr_ctx* ctx) {
     DeviceBuffer* all[] = {&ctx->nodes, &ctx->prims, &ctx->tri_shade, &ctx->tri_frames, &ctx->planes, &ctx->marched, &ctx->materials,
                            &ctx->components, &ctx->programs, &ctx->code, &ctx->spectra, &ctx->spectrum_data, &ctx->textures, &ctx->texels,
                            &ctx->lamps, &ctx->tiles, &ctx->burns, &ctx->xyz, &ctx->d65, &ctx->film, &ctx->develop_params, &ctx->counters,
-                           &ctx->scalars, &ctx->tile_first, &ctx->paths, &ctx->pend, &ctx->bidir, &ctx->bin_count, &ctx->bin_list, &ctx->rays[0], &ctx->rays[1], &ctx->hits, &ctx->shadow_kinds, &ctx->march_queue[0], &ctx->march_queue[1], &ctx->march_key, &ctx->light_vertices, &ctx->cam_vertices,
+                           &ctx->scalars, &ctx->tile_first, &ctx->paths, &ctx->pend, &ctx->bidir, &ctx->bin_count, &ctx->bin_list, &ctx->live_list, &ctx->rays[0], &ctx->rays[1], &ctx->hits, &ctx->shadow_kinds, &ctx->march_queue[0], &ctx->march_queue[1], &ctx->march_key, &ctx->light_vertices, &ctx->cam_vertices,
                            &ctx->scratch_a, &ctx->scratch_b};
     for (DeviceBuffer* b : all) b->release();
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -382,7 +384,7 @@ pyr_status pyr_render(pyr_ctx* ctx, const pyr_render_params* params, pyr_progres
         ensure_pool(ctx, pool);
         if (p.reset_film) CU(cudaMemsetAsync(ctx->film.p, 0, ctx->film_floats() * sizeof(float), s));
         CU(cudaMemsetAsync(ctx->scalars.p, 0, 16 * sizeof(uint32_t), s));
-        launch_pool_reset(ctx->paths.as<PathCore>(), pool, s);
+        launch_pool_reset(ctx->paths.as<PathCore>(), pool, ctx->live_list.as<uint32_t>(), ctx->live_count(0), s);
 
         const int trace_blocks = ctx->sm_count * trace_blocks_per_sm();
         const int stats = (p.flags & PYR_RENDER_STATS) ? 1 : 0;
@@ -402,6 +404,7 @@ pyr_status pyr_render(pyr_ctx* ctx, const pyr_render_params* params, pyr_progres
             for (int b = 0; b < BATCH; ++b) {
                 const int nxt = cur ^ 1;
                 CU(cudaMemsetAsync(ctx->count(nxt), 0, 2 * sizeof(uint32_t), s));
+                CU(cudaMemsetAsync(ctx->live_count(nxt), 0, sizeof(uint32_t), s));
                 WaveArgs a{};
                 a.paths = ctx->paths.as<PathCore>();
                 a.pend = ctx->pend.as<PendingLight>();
@@ -428,6 +431,9 @@ pyr_status pyr_render(pyr_ctx* ctx, const pyr_render_params* params, pyr_progres
                 a.cam_stride = std::max<uint32_t>(R.bounces, 1);
                 a.ray_capacity = (uint32_t)(ctx->rays[0].bytes / sizeof(Ray));
                 if (timing) CU(cudaEventRecord(ctx->timing_events[3 * b], s));
+                a.live_list = ctx->live_list.as<uint32_t>();
+                a.live_count_in = ctx->live_count(cur);
+                a.live_count_out = ctx->live_count(nxt);
                 a.bin_count = ctx->bin_count.as<uint32_t>();
                 a.bin_list = ctx->bin_list.as<uint32_t>();
                 launch_bin(a, ctx->bin_count.as<uint32_t>(), ctx->bin_list.as<uint32_t>(), R.algorithm == 1, s);

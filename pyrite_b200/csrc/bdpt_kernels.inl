@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(WAVE_THREADS) k_wave_bidirectional(const Scene
         for (uint32_t j = 0; j < n_shadow; ++j) store_ray(a.rays_out + a.shadow_offset + shadow_at + j, out.shadow[j]);
     }
     if (valid && (alive || (flags_in & PS_ALIVE))) { a.paths[slot] = static_cast<const PathCore&>(ps); a.bidir[slot] = bd; }
+    append_live(a, slot, valid && alive);
     if (pc.de_evals) { atomicAdd(&a.counters->de_evals, (unsigned long long)pc.de_evals); atomicAdd(&a.counters->de_iterations, (unsigned long long)pc.de_iters); }
 }
 

@@ -104,9 +104,10 @@ __device__ __forceinline__ Ray load_ray(const Ray* src) {
     return r;
 }
 
-__global__ void k_pool_reset(PathCore* paths, uint32_t pool) {
+__global__ void k_pool_reset(PathCore* paths, uint32_t pool, uint32_t* live_list, uint32_t* live_count) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < pool) paths[i].flags = 0;
+    if (i < pool) { paths[i].flags = 0; live_list[i] = i; }  // every slot may start a path
+    if (i == 0) *live_count = pool;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -122,8 +123,12 @@ __device__ __forceinline__ uint32_t unblocked_count(const uint32_t* kinds, uint3
     return c;
 }
 __global__ void __launch_bounds__(256) k_bin(const PathCore* paths, const BidirState* bidir, uint32_t pool, const Hit* hits, const uint32_t* shadow_kinds,
-                                             uint32_t* bin_count, uint32_t* bin_list) {
-    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+                                             uint32_t* bin_count, uint32_t* bin_list, const uint32_t* live_list, const uint32_t* live_count) {
+    const uint32_t index = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n_live = *live_count;
+    if ((index & ~31u) >= n_live) return;  // whole warp beyond the live list
+    // while every slot is alive the list is a permutation of [0, pool): walk the slots in order instead (coalesced)
+    const uint32_t slot = index < n_live ? (n_live == pool ? index : live_list[index]) : 0xFFFFFFFFu;
     uint32_t key = 0xFFFFFFFFu;
     if (slot < pool) {
         const uint4 h0 = reinterpret_cast<const uint4*>(paths + slot)[1];  // pos[2], tile, flags
@@ -153,7 +158,18 @@ __global__ void __launch_bounds__(256) k_bin(const PathCore* paths, const BidirS
     if (key != 0xFFFFFFFFu) bin_list[(size_t)key * pool + base + __popc(peers & ((1u << lane_id()) - 1u))] = slot;
 }
 
-// thread -> slot through the bins: the concatenation of all bins is a permutation of [0, pool)
+// the slots still alive after this shade pass form the domain of the next k_bin
+__device__ __forceinline__ void append_live(const WaveArgs& a, uint32_t slot, bool alive) {
+    const unsigned mask = __ballot_sync(FULL, alive);
+    if (!mask) return;
+    uint32_t base = 0;
+    const int leader = __ffs(mask) - 1;
+    if ((int)lane_id() == leader) base = atomicAdd(a.live_count_out, (uint32_t)__popc(mask));
+    base = __shfl_sync(FULL, base, leader);
+    if (alive) a.live_list[base + __popc(mask & ((1u << lane_id()) - 1u))] = slot;
+}
+
+// thread -> slot through the bins: the concatenation of all bins is a permutation of the live list
 __device__ __forceinline__ uint32_t binned_slot(const WaveArgs& a, uint32_t g, bool& valid, bool& dead) {
     __shared__ uint32_t s_first[NUM_BINS + 1];
     if (threadIdx.x == 0) {
@@ -221,6 +237,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS) k_wave_simple(c
         for (uint32_t j = 0; j < n_shadow; ++j) store_ray(a.rays_out + a.shadow_offset + shadow_at + j, out.get_shadow(j));
     }
     if (valid && (alive || (flags_in & PS_ALIVE))) a.paths[slot] = static_cast<const PathCore&>(ps);
+    append_live(a, slot, valid && alive);
     if (pc.de_evals) { atomicAdd(&a.counters->de_evals, (unsigned long long)pc.de_evals); atomicAdd(&a.counters->de_iterations, (unsigned long long)pc.de_iters); }
 }
 
@@ -600,12 +617,12 @@ __global__ void k_camera_sample(const SceneView sc, uint64_t seed, uint32_t tile
 
 #include "bdpt_kernels.inl"
 
-void launch_pool_reset(PathCore* paths, uint32_t pool, cudaStream_t s) {
-    if (pool) k_pool_reset<<<(pool + 255) / 256, 256, 0, s>>>(paths, pool);
+void launch_pool_reset(PathCore* paths, uint32_t pool, uint32_t* live_list, uint32_t* live_count, cudaStream_t s) {
+    if (pool) k_pool_reset<<<(pool + 255) / 256, 256, 0, s>>>(paths, pool, live_list, live_count);
 }
 void launch_bin(const WaveArgs& a, uint32_t* bin_count, uint32_t* bin_list, int bidirectional, cudaStream_t s) {
     cudaMemsetAsync(bin_count, 0, NUM_BINS * sizeof(uint32_t), s);
-    k_bin<<<(a.pool + 255) / 256, 256, 0, s>>>(a.paths, bidirectional ? a.bidir : nullptr, a.pool, a.hits_in, a.shadow_kinds_in, bin_count, bin_list);
+    k_bin<<<(a.pool + 255) / 256, 256, 0, s>>>(a.paths, bidirectional ? a.bidir : nullptr, a.pool, a.hits_in, a.shadow_kinds_in, bin_count, bin_list, a.live_list, a.live_count_in);
 }
 void launch_wave_simple(const SceneView& sc, const WaveArgs& a, cudaStream_t s) {
     cudaFuncSetAttribute(k_wave_simple, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wave_smem(sc));

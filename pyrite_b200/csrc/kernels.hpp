@@ -45,6 +45,11 @@ struct WaveArgs {
     // slots grouped by shading state (k_bin): bucket b holds bin_count[b] slot ids at bin_list[b * pool ..]
     const uint32_t* bin_count;
     const uint32_t* bin_list;
+    // slots that can still do something: written by the shade kernel (slots alive after it), read by the next k_bin;
+    // once every sample has started the list shrinks with the paths still in flight
+    uint32_t* live_list;
+    const uint32_t* live_count_in;
+    uint32_t* live_count_out;
 };
 constexpr int NUM_BINS = 64;
 void launch_bin(const WaveArgs& a, uint32_t* bin_count, uint32_t* bin_list, int bidirectional, cudaStream_t s);
@@ -70,7 +75,7 @@ struct TraceTuning { uint32_t refill_min, steps; };
 TraceTuning trace_tuning();
 
 // the wavefront
-void launch_pool_reset(PathCore* paths, uint32_t pool, cudaStream_t s);
+void launch_pool_reset(PathCore* paths, uint32_t pool, uint32_t* live_list, uint32_t* live_count, cudaStream_t s);
 void launch_wave_simple(const SceneView& sc, const WaveArgs& a, cudaStream_t s);
 void launch_wave_bidirectional(const SceneView& sc, const WaveArgs& a, cudaStream_t s);
 void launch_trace(const SceneView& sc, const TraceArgs& a, int grid_blocks, cudaStream_t s);
