@@ -94,6 +94,7 @@ typedef struct pyr_counters {
     double trace_seconds, shade_seconds;
     uint64_t trace_launches, shade_launches;
     uint64_t node_fetches; /* 128-byte BVH nodes fetched (stats mode); nodes_visited counts the boxes tested */
+    uint64_t path_rays;    /* the part of `rays` that are path segments (closest-hit); the rest are visibility rays */
 } pyr_counters;
 
 /* renderer::Progress{progress: u8, message} (renderer/mod.rs:229-232); invoked on the calling

@@ -597,6 +597,7 @@ pyr_status pyr_counters_get(pyr_ctx* ctx, pyr_counters* out, int32_t reset) {
             out->de_evals = dc.de_evals;
             out->de_iterations = dc.de_iterations;
             out->node_fetches = dc.node_fetches;
+            out->path_rays = dc.path_rays;
         }
         if (reset) {
             CU(cudaMemsetAsync(ctx->counters.p, 0, sizeof(DeviceCounters), ctx->stream));

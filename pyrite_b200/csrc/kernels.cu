@@ -269,7 +269,10 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sc, const Ray*
     SharedStack stack;
     stack.entries = smem_stack + threadIdx.x;
     const uint32_t total = n_main + n_shadow;
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counters->rays, (unsigned long long)total);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        atomicAdd(&counters->rays, (unsigned long long)total);
+        atomicAdd(&counters->path_rays, (unsigned long long)n_main);
+    }
     unsigned long long nodes = 0, leaves = 0, evals = 0, iters = 0, fetches = 0;
     Traversal<STATS> tr;
     tr.done = true;

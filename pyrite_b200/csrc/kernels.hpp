@@ -15,7 +15,7 @@ struct CamVertex;
 
 // Device-side work counters (one instance per context).
 struct DeviceCounters {
-    unsigned long long rays, path_samples, nodes_visited, leaves_tested, de_evals, de_iterations, node_fetches;
+    unsigned long long rays, path_samples, nodes_visited, leaves_tested, de_evals, de_iterations, node_fetches, path_rays;
 };
 
 // Everything one wavefront iteration needs besides the scene.

@@ -5,7 +5,7 @@
 
 writes profiles/<tag>_launches.md (per-kernel totals and shares from the gpu__time_duration launch list),
 profiles/<tag>_kernels.md (key metrics of every kernel captured with --set full) and updates
-profiles/trace_traffic.json (DRAM bytes per k_trace launch, read by bench.py as roofline.traffic)."""
+profiles/kernel_traffic.json (DRAM bytes per launch of k_trace and k_wave_simple, read by bench.py as roofline.traffic)."""
 import argparse
 import csv
 import json
@@ -90,9 +90,15 @@ def kernels(rep, tag):
         out += [f"| dram bytes per launch (read + write) | {rd + wr:,.0f} | byte |", ""]
     (PROF / f"{tag}_kernels.md").write_text("\n".join(out) + "\n")
     print("\n".join(out))
+    keep = {}
     for k, v in traffic.items():
         if k.startswith("k_trace"):
-            (PROF / "trace_traffic.json").write_text(json.dumps({"kernel": k, "dram_bytes_per_launch": v, "source": f"profiles/{tag}_kernels.md"}) + "\n")
+            keep["k_trace"] = v
+        elif k.startswith("k_wave_simple"):
+            keep["k_wave_simple"] = v
+    if keep:
+        keep["source"] = f"profiles/{tag}_kernels.md (dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full)"
+        (PROF / "kernel_traffic.json").write_text(json.dumps(keep) + "\n")
 
 
 def main():
