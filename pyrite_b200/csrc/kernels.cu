@@ -90,14 +90,28 @@ __device__ __forceinline__ void locate_sample(const unsigned long long* tile_fir
     k = g - tile_first[lo];
 }
 
+// Path state and the ray / hit queues are touched once per iteration: they go through the caches with the
+// streaming hint (ld/st.global.cs) so that they do not evict the BVH and the thread-local lines from L2.
 __device__ __forceinline__ void store_ray(Ray* dst, const Ray& r) {
     float4* d = reinterpret_cast<float4*>(dst);
-    d[0] = make_float4(r.o[0], r.o[1], r.o[2], __uint_as_float(r.mode));
-    d[1] = make_float4(r.d[0], r.d[1], r.d[2], r.limit);
+    __stcs(d, make_float4(r.o[0], r.o[1], r.o[2], __uint_as_float(r.mode)));
+    __stcs(d + 1, make_float4(r.d[0], r.d[1], r.d[2], r.limit));
+}
+__device__ __forceinline__ void load_core(PathCore& dst, const PathCore* src) {
+    const float4* s = reinterpret_cast<const float4*>(src);
+    float4* d = reinterpret_cast<float4*>(&dst);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(PathCore) / 16); ++i) d[i] = __ldcs(s + i);
+}
+__device__ __forceinline__ void store_core(PathCore* dst, const PathCore& src) {
+    const float4* s = reinterpret_cast<const float4*>(&src);
+    float4* d = reinterpret_cast<float4*>(dst);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(PathCore) / 16); ++i) __stcs(d + i, s[i]);
 }
 __device__ __forceinline__ Ray load_ray(const Ray* src) {
     const float4* s = reinterpret_cast<const float4*>(src);
-    float4 a = s[0], b = s[1];
+    float4 a = __ldcs(s), b = __ldcs(s + 1);
     Ray r;
     r.o[0] = a.x; r.o[1] = a.y; r.o[2] = a.z; r.mode = __float_as_uint(a.w);
     r.d[0] = b.x; r.d[1] = b.y; r.d[2] = b.z; r.limit = b.w;
@@ -199,7 +213,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS) k_wave_simple(c
     // a whole warp of dead slots with no samples left to start has nothing to do (long-tailed scenes)
     if (__all_sync(FULL, !valid || dead) && *a.next_sample >= a.total_samples) return;
     PathState ps;
-    if (valid && !dead) static_cast<PathCore&>(ps) = a.paths[slot];
+    if (valid && !dead) load_core(ps, a.paths + slot);
     else ps.flags = 0;
     ps.pend = a.pend + (size_t)(valid ? slot : 0) * MAX_LIGHT_SAMPLES;
     ps.bd = nullptr;
@@ -236,7 +250,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS) k_wave_simple(c
         ps.shadow_base = shadow_at;
         for (uint32_t j = 0; j < n_shadow; ++j) store_ray(a.rays_out + a.shadow_offset + shadow_at + j, out.get_shadow(j));
     }
-    if (valid && (alive || (flags_in & PS_ALIVE))) a.paths[slot] = static_cast<const PathCore&>(ps);
+    if (valid && (alive || (flags_in & PS_ALIVE))) store_core(a.paths + slot, ps);
     append_live(a, slot, valid && alive);
     if (pc.de_evals) { atomicAdd(&a.counters->de_evals, (unsigned long long)pc.de_evals); atomicAdd(&a.counters->de_iterations, (unsigned long long)pc.de_iters); }
 }
