@@ -103,11 +103,12 @@ PYR_HD v3 lens_origin(const CameraRec& cam, Rng& rng) {
 
 struct CameraHooks {
     BidirCtx cx;
+    uint32_t n_spec;  // spectrum_samples
     PYR_HD void contribute_done(PathState& ps) {
         if (!ps.bd->cam_store_pending) return;
         CamVertex& c = cx.cv[ps.bd->n_cam_stored - 1];
         c.use_additional = (ps.flags & PS_USE_ADDITIONAL) ? 1u : 0u;
-        for (int k = 0; k < MAX_SPECTRUM_SAMPLES; ++k) { c.bright[k] = ps.bright[k]; c.refl[k] = ps.refl[k]; }
+        for (uint32_t k = 0; k < n_spec; ++k) { c.bright[k] = ps.bright[k]; c.refl[k] = ps.refl[k]; }
         ps.bd->cam_store_pending = 0;
     }
     PYR_HD void pushed_emission(PathState& ps) { ps.bd->n_cam += 1; }
@@ -257,7 +258,7 @@ PYR_HD void generate_bidirectional(const SceneView& sc, uint64_t seed, uint32_t 
     const uint32_t S = sc.renderer.spectrum_samples;
     uint32_t pick = sample_wavelengths(sc, rng, ps.wl);
     hero_first(ps.wl, S, pick);
-    for (int k = 0; k < MAX_SPECTRUM_SAMPLES; ++k) { ps.bright[k] = 0.0f; ps.refl[k] = 1.0f; }
+    for (uint32_t k = 0; k < S; ++k) { ps.bright[k] = 0.0f; ps.refl[k] = 1.0f; }
     const float wavelength = ps.wl[0];
     v3 co, cd;
     camera_ray(sc.camera, ps.pos[0], ps.pos[1], rng, co, cd);
@@ -400,7 +401,7 @@ PYR_HD void shade_bidirectional(const SceneView& sc, PathState& ps, const BidirC
     if (ps.bd->phase == PH_CAMERA) {
         ShadeOut so;
         so.stage_base = sc.vm_regs * 128u;
-        CameraHooks hooks{cx};
+        CameraHooks hooks{cx, sc.renderer.spectrum_samples};
         const bool more = camera_step(sc, ps, main_ray, main_hit, shadow_rays, shadow_kinds, so, pc, hooks);
         if (more) {
             out.alive = 1; out.has_main = so.has_main; out.main = so.main; out.n_shadow = so.n_shadow;

@@ -9,7 +9,8 @@ __global__ void __launch_bounds__(WAVE_THREADS) k_wave_bidirectional(const Scene
     if (__all_sync(FULL, !valid || dead) && *a.next_sample >= a.total_samples) return;
     const uint32_t s = valid ? slot : 0;
     PathState ps;
-    load_core(ps, a.paths + s);
+    bind_spectral(sc, ps);
+    load_core(sc, ps, a.paths + s);
     ps.pend = a.pend + (size_t)s * MAX_LIGHT_SAMPLES;
     BidirState bd = a.bidir[s];
     ps.bd = &bd;
@@ -47,7 +48,7 @@ __global__ void __launch_bounds__(WAVE_THREADS) k_wave_bidirectional(const Scene
         ps.shadow_base = shadow_at;
         for (uint32_t j = 0; j < n_shadow; ++j) store_ray(a.rays_out + a.shadow_offset + shadow_at + j, out.shadow[j]);
     }
-    if (valid && (alive || (flags_in & PS_ALIVE))) { store_core(a.paths + slot, ps); a.bidir[slot] = bd; }
+    if (valid && (alive || (flags_in & PS_ALIVE))) { store_core(sc, a.paths + slot, ps); a.bidir[slot] = bd; }
     append_live(a, slot, valid && alive);
     if (pc.de_evals) { atomicAdd(&a.counters->de_evals, (unsigned long long)pc.de_evals); atomicAdd(&a.counters->de_iterations, (unsigned long long)pc.de_iters); }
 }

@@ -31,7 +31,7 @@ constexpr unsigned FULL = 0xffffffffu;
 inline size_t vm_smem(const SceneView& sc) { return (size_t)sc.vm_regs * WAVE_THREADS * sizeof(float4); }
 inline size_t wave_smem(const SceneView& sc) {
     return vm_smem(sc) + (size_t)2 * (sc.renderer.light_samples ? sc.renderer.light_samples : 1) * WAVE_THREADS * sizeof(float4) +
-           (size_t)sc.renderer.spectrum_samples * WAVE_THREADS * sizeof(float);
+           (size_t)4 * sc.renderer.spectrum_samples * WAVE_THREADS * sizeof(float);  // colour cache + wl / bright / refl
 }
 
 struct FilmAdd {
@@ -97,17 +97,59 @@ __device__ __forceinline__ void store_ray(Ray* dst, const Ray& r) {
     __stcs(d, make_float4(r.o[0], r.o[1], r.o[2], __uint_as_float(r.mode)));
     __stcs(d + 1, make_float4(r.d[0], r.d[1], r.d[2], r.limit));
 }
-__device__ __forceinline__ void load_core(PathCore& dst, const PathCore* src) {
-    const float4* s = reinterpret_cast<const float4*>(src);
-    float4* d = reinterpret_cast<float4*>(&dst);
-#pragma unroll
-    for (int i = 0; i < (int)(sizeof(PathCore) / 16); ++i) d[i] = __ldcs(s + i);
+// Dynamic shared memory of the shade kernels, in float4 units: VM registers [vm_regs][thread]; staged visibility
+// rays [2 * light_samples][thread]; then floats: the fold's colour cache [S][thread] and the path's wl / bright / refl
+// arrays [3 * S][thread].
+__device__ __forceinline__ float* spectral_base(const SceneView& sc) {
+#if defined(__CUDA_ARCH__)
+    const uint32_t L = sc.renderer.light_samples ? sc.renderer.light_samples : 1u;
+    float* floats = reinterpret_cast<float*>(pyr_dyn_smem + (sc.vm_regs + 2u * L) * PYR_BLOCK);
+    return floats + sc.renderer.spectrum_samples * PYR_BLOCK + threadIdx.x;
+#else
+    return nullptr;
+#endif
 }
-__device__ __forceinline__ void store_core(PathCore* dst, const PathCore& src) {
-    const float4* s = reinterpret_cast<const float4*>(&src);
-    float4* d = reinterpret_cast<float4*>(dst);
+__device__ __forceinline__ void bind_spectral(const SceneView& sc, PathState& ps) {
+    float* base = spectral_base(sc);
+    const uint32_t S = sc.renderer.spectrum_samples;
+    ps.wl.base = base;
+    ps.bright.base = base + S * WAVE_THREADS;
+    ps.refl.base = base + 2u * S * WAVE_THREADS;
+}
+// header -> registers, per-wavelength arrays -> shared memory (16-byte streaming loads)
+__device__ __forceinline__ void load_core(const SceneView& sc, PathState& ps, const PathCore* src) {
+    const float4* s = reinterpret_cast<const float4*>(src);
+    float4* h = reinterpret_cast<float4*>(static_cast<PathHeader*>(&ps));
 #pragma unroll
-    for (int i = 0; i < (int)(sizeof(PathCore) / 16); ++i) __stcs(d + i, s[i]);
+    for (int i = 0; i < (int)(sizeof(PathHeader) / 16); ++i) h[i] = __ldcs(s + i);
+    const uint32_t S = sc.renderer.spectrum_samples;
+    const float4* arrays = s + sizeof(PathHeader) / 16;
+    for (uint32_t q = 0; q * 4 < S; ++q) {
+        const float4 w = __ldcs(arrays + q), b = __ldcs(arrays + 4 + q), r = __ldcs(arrays + 8 + q);
+        const float wv[4] = {w.x, w.y, w.z, w.w}, bv[4] = {b.x, b.y, b.z, b.w}, rv[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j)
+            if (q * 4 + j < S) { ps.wl[q * 4 + j] = wv[j]; ps.bright[q * 4 + j] = bv[j]; ps.refl[q * 4 + j] = rv[j]; }
+    }
+}
+__device__ __forceinline__ void store_core(const SceneView& sc, PathCore* dst, const PathState& ps) {
+    float4* d = reinterpret_cast<float4*>(dst);
+    const float4* h = reinterpret_cast<const float4*>(static_cast<const PathHeader*>(&ps));
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(PathHeader) / 16); ++i) __stcs(d + i, h[i]);
+    const uint32_t S = sc.renderer.spectrum_samples;
+    float4* arrays = d + sizeof(PathHeader) / 16;
+    for (uint32_t q = 0; q * 4 < S; ++q) {
+        float wv[4], bv[4], rv[4];
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) {
+            const bool in = q * 4 + j < S;
+            wv[j] = in ? ps.wl[q * 4 + j] : 0.0f; bv[j] = in ? ps.bright[q * 4 + j] : 0.0f; rv[j] = in ? ps.refl[q * 4 + j] : 0.0f;
+        }
+        __stcs(arrays + q, make_float4(wv[0], wv[1], wv[2], wv[3]));
+        __stcs(arrays + 4 + q, make_float4(bv[0], bv[1], bv[2], bv[3]));
+        __stcs(arrays + 8 + q, make_float4(rv[0], rv[1], rv[2], rv[3]));
+    }
 }
 __device__ __forceinline__ Ray load_ray(const Ray* src) {
     const float4* s = reinterpret_cast<const float4*>(src);
@@ -213,7 +255,8 @@ __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS) k_wave_simple(c
     // a whole warp of dead slots with no samples left to start has nothing to do (long-tailed scenes)
     if (__all_sync(FULL, !valid || dead) && *a.next_sample >= a.total_samples) return;
     PathState ps;
-    if (valid && !dead) load_core(ps, a.paths + slot);
+    bind_spectral(sc, ps);
+    if (valid && !dead) load_core(sc, ps, a.paths + slot);
     else ps.flags = 0;
     ps.pend = a.pend + (size_t)(valid ? slot : 0) * MAX_LIGHT_SAMPLES;
     ps.bd = nullptr;
@@ -250,7 +293,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS) k_wave_simple(c
         ps.shadow_base = shadow_at;
         for (uint32_t j = 0; j < n_shadow; ++j) store_ray(a.rays_out + a.shadow_offset + shadow_at + j, out.get_shadow(j));
     }
-    if (valid && (alive || (flags_in & PS_ALIVE))) store_core(a.paths + slot, ps);
+    if (valid && (alive || (flags_in & PS_ALIVE))) store_core(sc, a.paths + slot, ps);
     append_live(a, slot, valid && alive);
     if (pc.de_evals) { atomicAdd(&a.counters->de_evals, (unsigned long long)pc.de_evals); atomicAdd(&a.counters->de_iterations, (unsigned long long)pc.de_iters); }
 }

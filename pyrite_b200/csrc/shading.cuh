@@ -17,9 +17,8 @@ struct PendingLight {          // tracer.rs:193-200 `DirectLight`, waiting for i
 };
 enum : uint32_t { PS_USE_ADDITIONAL = 1u, PS_SAMPLE_LIGHT = 2u, PS_HAS_MAIN = 4u, PS_PENDING_FOLD = 8u, PS_ALIVE = 16u };
 
-// What is stored per path slot in HBM: 256 B, copied to thread-local storage with 16-byte loads at
-// the start of a wavefront iteration and written back at its end.
-struct alignas(16) PathCore {
+// What is stored per path slot in HBM: a 64-byte header and the three per-wavelength arrays, 256 B.
+struct alignas(16) PathHeader {
     Rng rng;
     float pos[2];              // film position in view coordinates (Tile::sample_point)
     uint32_t tile, flags;
@@ -27,6 +26,8 @@ struct alignas(16) PathCore {
     float pending_brdf;
     uint32_t shadow_base;      // index of this path's first visibility ray in the shadow region
     uint32_t pad[2];
+};
+struct alignas(16) PathCore : PathHeader {
     float wl[MAX_SPECTRUM_SAMPLES];      // [0] = hero wavelength, then the additional ones (simple.rs:105-107)
     float bright[MAX_SPECTRUM_SAMPLES];  // Sample::brightness
     float refl[MAX_SPECTRUM_SAMPLES];    // the running reflectance of renderer/algorithm.rs:14-100
@@ -38,8 +39,20 @@ struct alignas(16) BidirState {
     uint32_t cam_store_pending, pad2;
     Rng rng_saved;
 };
-// What the stage functions see: the thread's copy of the core plus where the colder records live.
-struct PathState : PathCore {
+// A per-wavelength array of the thread.  In the kernels it lives in dynamic shared memory, [wavelength][thread]
+// (dynamically indexed thread-local arrays would otherwise go through local memory); on the host it is plain memory.
+struct SpecArray {
+    float* base;
+#if defined(__CUDA_ARCH__)
+    __device__ __forceinline__ float& operator[](uint32_t k) const { return base[k * PYR_BLOCK]; }
+#else
+    float& operator[](uint32_t k) const { return base[k]; }
+#endif
+};
+// What the stage functions see: the thread's copy of the header, its per-wavelength arrays, and where the colder
+// records live.
+struct PathState : PathHeader {
+    SpecArray wl, bright, refl;
     PendingLight* pend;        // MAX_LIGHT_SAMPLES records per path (HBM)
     BidirState* bd;
 };
@@ -111,7 +124,8 @@ PYR_HD void camera_ray(const CameraRec& cam, float tx, float ty, Rng& rng, v3& o
     dir_out = transform_vector(cam.m, normalize(direction));
 }
 // Film::sample_many_wavelengths (film.rs:68-83) + the hero pick / swap_remove (simple.rs:105-107)
-PYR_HD uint32_t sample_wavelengths(const SceneView& sc, Rng& rng, float* wl) {
+template <class W>
+PYR_HD uint32_t sample_wavelengths(const SceneView& sc, Rng& rng, W wl) {
     const uint32_t S = sc.renderer.spectrum_samples;
     float step_size = sc.film.wavelength_width / (float)S;
     float from = sc.film.wavelength_start;
@@ -122,7 +136,8 @@ PYR_HD uint32_t sample_wavelengths(const SceneView& sc, Rng& rng, float* wl) {
     }
     return (uint32_t)rng.gen_range_usize(S);
 }
-PYR_HD void hero_first(float* wl, uint32_t S, uint32_t pick) {
+template <class W>
+PYR_HD void hero_first(W wl, uint32_t S, uint32_t pick) {
     float hero = wl[pick];
     wl[pick] = wl[S - 1];             // swap_remove
     for (uint32_t i = S - 1; i > 0; --i) wl[i] = wl[i - 1];
@@ -419,8 +434,8 @@ PYR_HD LampSample lamp_sample(const SceneView& sc, const LampRec& lamp, Rng& rng
 // ---------------------------------------------------------------- the contribute fold (renderer/algorithm.rs:14-100)
 // values[k] = color(wl[k]) for k < n: the program record is fetched once and the memoised re-run
 // is used for k > 0
-template <class Sink>
-PYR_HD void eval_spectral_each(const SceneView& sc, int32_t color, const VmInputs& base, const float* wl, uint32_t n, RegFile R, Sink&& sink) {
+template <class W, class Sink>
+PYR_HD void eval_spectral_each(const SceneView& sc, int32_t color, const VmInputs& base, W wl, uint32_t n, RegFile R, Sink&& sink) {
     const ProgramRec p = sc.programs[color];
     if (p.is_constant) { for (uint32_t k = 0; k < n; ++k) sink(k, p.value); return; }
     VmInputs in = base;
@@ -429,7 +444,8 @@ PYR_HD void eval_spectral_each(const SceneView& sc, int32_t color, const VmInput
         sink(k, run_program(sc, p, in, R, k > 0));
     }
 }
-PYR_HD void eval_spectral(const SceneView& sc, int32_t color, const VmInputs& base, const float* wl, uint32_t n, float* values, RegFile R) {
+template <class W>
+PYR_HD void eval_spectral(const SceneView& sc, int32_t color, const VmInputs& base, W wl, uint32_t n, float* values, RegFile R) {
     eval_spectral_each(sc, color, base, wl, n, R, [&](uint32_t k, float v) { values[k] = v; });
 }
 // brightness[k] += color(wl[k]) * probability * reflectance[k] for k < n

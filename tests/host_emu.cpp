@@ -100,6 +100,10 @@ int emu_render(void* h, uint64_t seed, uint32_t spp_override, uint32_t offset, u
         std::vector<Hit> hits(rays.size());
         std::vector<uint32_t> kinds(rays.size());
         auto ps = std::make_unique<PathState>();
+        std::vector<float> spectral(3 * MAX_SPECTRUM_SAMPLES);
+        ps->wl.base = spectral.data();
+        ps->bright.base = spectral.data() + MAX_SPECTRUM_SAMPLES;
+        ps->refl.base = spectral.data() + 2 * MAX_SPECTRUM_SAMPLES;
         std::vector<PendingLight> pend(MAX_LIGHT_SAMPLES);
         BidirState bd{};
         ps->pend = pend.data();
