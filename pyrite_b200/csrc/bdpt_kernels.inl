@@ -1,7 +1,7 @@
 // included by kernels.cu inside namespace pyr: the bidirectional wavefront kernel
 namespace {
 
-__global__ void __launch_bounds__(WAVE_THREADS) k_wave_bidirectional(const SceneView sc, const WaveArgs a) {
+__global__ void __launch_bounds__(WAVE_THREADS) k_wave_bidirectional(const __grid_constant__ SceneView sc, const __grid_constant__ WaveArgs a) {
     const uint32_t g_thread = blockIdx.x * blockDim.x + threadIdx.x;
     if (g_thread == 0) *a.trace_cursor = 0;
     bool valid, dead;

@@ -247,7 +247,7 @@ __device__ __forceinline__ uint32_t binned_slot(const WaveArgs& a, uint32_t g, b
 }
 
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS) k_wave_simple(const SceneView sc, const WaveArgs a) {
+__global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS) k_wave_simple(const __grid_constant__ SceneView sc, const __grid_constant__ WaveArgs a) {
     const uint32_t g_thread = blockIdx.x * blockDim.x + threadIdx.x;
     if (g_thread == 0) *a.trace_cursor = 0;
     bool valid, dead;
@@ -437,7 +437,7 @@ struct EmitHit {
 };
 
 template <bool STATS>
-__global__ void __launch_bounds__(TRACE_THREADS) k_trace(const SceneView sc, const TraceArgs a) {
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace(const __grid_constant__ SceneView sc, const __grid_constant__ TraceArgs a) {
     EmitHit emit{a.hits, a.shadow_kinds, a.shadow_offset, a.march_queue[0], a.march_queue[1], a.march_count, a.march_capacity, a.march_key, sc.marched};
     trace_persistent<STATS>(sc, a.rays, a.count[0], a.count[1], a.shadow_offset, a.cursor, a.counters, false, a.refill_min, a.steps, emit);
 }
@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(const SceneView sc, con
 // lengths (a handful to thousands of steps) and escape times (2 to `iterations` trips) vary per ray, so any coarser
 // unit leaves most lanes waiting.  Results merge per ray with a 64-bit atomicMin on (distance, tie rank).
 template <bool STATS>
-__global__ void __launch_bounds__(TRACE_THREADS) k_march(const SceneView sc, const TraceArgs a, uint32_t* cursors) {
+__global__ void __launch_bounds__(TRACE_THREADS) k_march(const __grid_constant__ SceneView sc, const __grid_constant__ TraceArgs a, uint32_t* cursors) {
     // every warp works on one estimator type at a time (half of them start with each) and moves to the other queue
     // when its own is empty, so that both queues drain together and their long tails overlap
     uint32_t TYPE = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) & 1u;
@@ -612,7 +612,7 @@ struct EmitAbiHit {
     }
 };
 template <bool STATS>
-__global__ void __launch_bounds__(TRACE_THREADS) k_trace_batch(const SceneView sc, const Ray* rays, uint32_t n, AbiHit* hits, uint32_t* cursor,
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace_batch(const __grid_constant__ SceneView sc, const Ray* rays, uint32_t n, AbiHit* hits, uint32_t* cursor,
                                                                DeviceCounters* counters, uint32_t refill_min, uint32_t steps) {
     EmitAbiHit emit{hits, sc.prims, &sc};
     trace_persistent<STATS>(sc, rays, n, 0u, 0u, cursor, counters, true, refill_min, steps, emit);
