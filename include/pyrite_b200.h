@@ -124,7 +124,8 @@ pyr_status pyr_project_info_get(const pyr_ctx* ctx, pyr_project_info* out);
 /* World::intersect (world.rs:273-299) over a batch.  Host buffers; copies are part of the call. */
 pyr_status pyr_trace(pyr_ctx* ctx, const pyr_ray* rays, size_t n, pyr_hit* hits_out);
 /* Same, on buffers already resident in device memory (`repeat` >= 1 back-to-back launches); the
- * device time of the launches is reported in pyr_counters.render_seconds. */
+ * device time of the launches is reported in pyr_counters.render_seconds.  `d_rays` must be
+ * 32-byte aligned (rays are fetched with 256-bit loads); cudaMalloc / torch allocations are. */
 pyr_status pyr_trace_device(pyr_ctx* ctx, const void* d_rays, size_t n, void* d_hits, uint32_t repeat);
 /* pyr_trace that also counts the BVH boxes tested and leaves tested into pyr_counters (slower). */
 pyr_status pyr_trace_stats(pyr_ctx* ctx, const pyr_ray* rays, size_t n, pyr_hit* hits_out);

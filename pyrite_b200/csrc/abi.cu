@@ -296,6 +296,7 @@ pyr_status pyr_trace_device(pyr_ctx* ctx, const void* d_rays, size_t n, void* d_
         if (n > 0xFFFFFFF0ull) throw ir::BuildError("ray batch too large");
         if (n == 0) return;
         if (!d_rays || !d_hits) throw ir::BuildError("null ray or hit buffer");
+        if ((uintptr_t)d_rays & 31u) throw ir::BuildError("the device ray buffer must be 32-byte aligned");
         const int blocks = ctx->sm_count * trace_blocks_per_sm();
         CU(cudaEventRecord(ctx->ev0, ctx->stream));
         for (uint32_t r = 0; r < (repeat ? repeat : 1u); ++r) {

@@ -392,7 +392,7 @@ PYR_HD void shade_bidirectional(const SceneView& sc, PathState& ps, const BidirC
     out.alive = 0; out.has_main = 0; out.n_shadow = 0;
     const uint32_t S = sc.renderer.spectrum_samples;
     if (ps.bd->phase == PH_LAMP) {
-        if (lamp_step(sc, ps, cx, *main_ray, *main_hit, out, pc)) return;
+        if (lamp_step(sc, ps, cx, load_record_stream(main_ray), load_record(main_hit), out, pc)) return;
         finish_lamp_path(sc, ps, cx.lv);
         ps.light_events = 0;
         begin_camera(ps, out);
@@ -467,7 +467,7 @@ PYR_HD void shade_bidirectional(const SceneView& sc, PathState& ps, const BidirC
             const v3 view_plane_target = (-local_target) / local_target.z;
             const float px = view_plane_target.x * sc.camera.view_plane, py = (-view_plane_target.y) * sc.camera.view_plane;
             if (!(px > -1.0f && px < 1.0f && py > -1.0f && py < 1.0f)) continue;
-            const v3 world_origin = ld3(shadow_rays[j].o);
+            const v3 world_origin = ld3(load_record_stream(shadow_rays + j).o);
             const float sq_distance = length2(world_origin - target);
             const float scale = 1.0f / sq_distance;
             const float brdf_in = vertex_brdf(v) / vertex_brdf(v);

@@ -6,50 +6,54 @@ __global__ void __launch_bounds__(WAVE_THREADS) k_wave_bidirectional(const __gri
     if (g_thread == 0) *a.trace_cursor = 0;
     bool valid, dead;
     const uint32_t slot = binned_slot(a, g_thread, valid, dead);
-    if (__all_sync(FULL, !valid || dead) && *a.next_sample >= a.total_samples) return;
+    const bool idle = __all_sync(FULL, !valid || dead) && *a.next_sample >= a.total_samples;
     const uint32_t s = valid ? slot : 0;
     PathState ps;
     bind_spectral(sc, ps);
-    load_core(sc, ps, a.paths + s);
-    ps.pend = a.pend + (size_t)s * MAX_LIGHT_SAMPLES;
-    BidirState bd = a.bidir[s];
+    ps.flags = 0;
+    BidirState bd;
     ps.bd = &bd;
-    const uint32_t flags_in = ps.flags;
-    BidirCtx cx;
-    cx.lv = a.light_vertices + (size_t)s * a.light_stride;
-    cx.cv = a.cam_vertices + (size_t)s * a.cam_stride;
-    FilmAdd add{a.film};
+    uint32_t flags_in = 0;
     BidirOut out;
     out.alive = 0; out.has_main = 0; out.n_shadow = 0;
     PathCounters pc;
     pc.de_evals = 0; pc.de_iters = 0;
-
-    bool alive = valid && (ps.flags & PS_ALIVE);
-    if (alive) {
-        shade_bidirectional(sc, ps, cx, a.rays_in + ps.ray_base, a.hits_in + ps.ray_base, a.rays_in + a.shadow_offset + ps.shadow_base,
-                            a.shadow_kinds_in + ps.shadow_base, out, add, pc);
-        alive = out.alive != 0;
-        if (alive) ps.flags |= PS_ALIVE; else ps.flags = 0;
-        if (alive && bd.phase >= PH_CONNECT) ps.n_pending = out.n_shadow;  // k_bin counts the unblocked ones
-    }
-    unsigned long long g = 0;
-    if (claim_sample(a.next_sample, a.total_samples, valid && !alive, g)) {
-        uint32_t tile; unsigned long long k;
-        locate_sample(a.tile_first, sc.n_tiles, g, tile, k);
-        generate_bidirectional(sc, a.seed, tile, (uint64_t)a.sample_offset + k * a.sample_stride, ps, cx, out);
-        ps.flags |= PS_ALIVE;
-        alive = true;
+    bool alive = false;
+    if (!idle) {
+        load_core(sc, ps, a.paths + s);
+        ps.pend = a.pend + (size_t)s * MAX_LIGHT_SAMPLES;
+        bd = a.bidir[s];
+        flags_in = ps.flags;
+        BidirCtx cx;
+        cx.lv = a.light_vertices + (size_t)s * a.light_stride;
+        cx.cv = a.cam_vertices + (size_t)s * a.cam_stride;
+        FilmAdd add{a.film};
+        alive = valid && (ps.flags & PS_ALIVE);
+        if (alive) {
+            shade_bidirectional(sc, ps, cx, a.rays_in + ps.ray_base, a.hits_in + ps.ray_base, a.rays_in + a.shadow_offset + ps.shadow_base,
+                                a.shadow_kinds_in + ps.shadow_base, out, add, pc);
+            alive = out.alive != 0;
+            if (alive) ps.flags |= PS_ALIVE; else ps.flags = 0;
+            if (alive && bd.phase >= PH_CONNECT) ps.n_pending = out.n_shadow;  // k_bin counts the unblocked ones
+        }
+        unsigned long long g = 0;
+        if (claim_sample(a.next_sample, a.total_samples, valid && !alive, g)) {
+            uint32_t tile; unsigned long long k;
+            locate_sample(a.tile_first, sc.n_tiles, g, tile, k);
+            generate_bidirectional(sc, a.seed, tile, (uint64_t)a.sample_offset + k * a.sample_stride, ps, cx, out);
+            ps.flags |= PS_ALIVE;
+            alive = true;
+        }
     }
     const uint32_t n_main = alive ? out.has_main : 0u, n_shadow = alive ? out.n_shadow : 0u;
-    const uint32_t main_at = queue_reserve(a.count_out, n_main);
-    const uint32_t shadow_at = queue_reserve(a.count_out + 1, n_shadow);
-    if (n_main) { ps.ray_base = main_at; store_ray(a.rays_out + main_at, out.main); }
+    const Reservation at = block_reserve(a, n_main, n_shadow, valid && alive);
+    if (n_main) { ps.ray_base = at.main_at; store_ray(a.rays_out + at.main_at, out.main); }
     if (n_shadow) {
-        ps.shadow_base = shadow_at;
-        for (uint32_t j = 0; j < n_shadow; ++j) store_ray(a.rays_out + a.shadow_offset + shadow_at + j, out.shadow[j]);
+        ps.shadow_base = at.shadow_at;
+        for (uint32_t j = 0; j < n_shadow; ++j) store_ray(a.rays_out + a.shadow_offset + at.shadow_at + j, out.shadow[j]);
     }
     if (valid && (alive || (flags_in & PS_ALIVE))) { store_core(sc, a.paths + slot, ps); a.bidir[slot] = bd; }
-    append_live(a, slot, valid && alive);
+    if (valid && alive) a.live_list[at.live_at] = slot;
     if (pc.de_evals) { atomicAdd(&a.counters->de_evals, (unsigned long long)pc.de_evals); atomicAdd(&a.counters->de_iterations, (unsigned long long)pc.de_iters); }
 }
 

@@ -18,6 +18,56 @@ namespace pyr {
 #define PYR_INF __builtin_inff()
 #endif
 
+// ---------------------------------------------------------------- 32-byte records
+// Path headers, rays, hits and pending lights are 32-byte aligned records that one thread moves whole.  sm_100
+// has 256-bit global loads / stores (LDG.E.256 / STG.E.256): one request and one full 32-byte sector per record
+// instead of two half-sector 128-bit accesses.  `_stream` marks data that is written once and read once by the
+// next kernel (evict-first).
+struct alignas(32) Vec8 { float v[8]; };
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ Vec8 ld256(const void* p) {
+    Vec8 r;
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7]) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ Vec8 ld256_stream(const void* p) {
+    Vec8 r;
+    asm volatile("ld.global.cs.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7]) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st256(void* p, const Vec8& r) {
+    asm volatile("st.global.v8.f32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};"
+                 :: "f"(r.v[0]), "f"(r.v[1]), "f"(r.v[2]), "f"(r.v[3]), "f"(r.v[4]), "f"(r.v[5]), "f"(r.v[6]), "f"(r.v[7]), "l"(p) : "memory");
+}
+__device__ __forceinline__ void st256_stream(void* p, const Vec8& r) {
+    asm volatile("st.global.cs.v8.f32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};"
+                 :: "f"(r.v[0]), "f"(r.v[1]), "f"(r.v[2]), "f"(r.v[3]), "f"(r.v[4]), "f"(r.v[5]), "f"(r.v[6]), "f"(r.v[7]), "l"(p) : "memory");
+}
+#else
+inline Vec8 ld256(const void* p) { Vec8 r; __builtin_memcpy(&r, p, 32); return r; }
+inline Vec8 ld256_stream(const void* p) { return ld256(p); }
+inline void st256(void* p, const Vec8& r) { __builtin_memcpy(p, &r, 32); }
+inline void st256_stream(void* p, const Vec8& r) { st256(p, r); }
+#endif
+template <class T> PYR_HD T from_vec8(const Vec8& v) {
+    static_assert(sizeof(T) == 32, "32-byte record");
+    T r;
+    __builtin_memcpy(&r, &v, 32);
+    return r;
+}
+template <class T> PYR_HD Vec8 to_vec8(const T& r) {
+    static_assert(sizeof(T) == 32, "32-byte record");
+    Vec8 v;
+    __builtin_memcpy(&v, &r, 32);
+    return v;
+}
+template <class T> PYR_HD T load_record(const T* p) { return from_vec8<T>(ld256(p)); }
+template <class T> PYR_HD T load_record_stream(const T* p) { return from_vec8<T>(ld256_stream(p)); }
+template <class T> PYR_HD void store_record(T* p, const T& r) { st256(p, to_vec8(r)); }
+template <class T> PYR_HD void store_record_stream(T* p, const T& r) { st256_stream(p, to_vec8(r)); }
+
 // ---------------------------------------------------------------- libm
 // The reference's f32::sin / cos / acos / atan2 / exp / powf resolve to glibc's float functions, which
 // are correctly rounded in all but rare cases; CUDA's float versions are 1-2 ULP.  On the device the

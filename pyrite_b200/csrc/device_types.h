@@ -207,13 +207,13 @@ struct SceneView {
 // ray of tracer.rs:381-389 - only "is there a hit with DIST_EPSILON < t and t*t < limit" is
 // needed, which equals the reference's closest-hit test `hit.distance^2 >= sq - eps`; mode 2: the
 // same with `t < limit` (bidirectional.rs:346-351, cameras.rs:138-142).
-struct Ray {
+struct alignas(32) Ray {   // one 32-byte sector: moved with single 256-bit loads / stores
     float o[3];
     uint32_t mode;
     float d[3];
     float limit;
 };
-struct Hit {            // 32 B
+struct alignas(32) Hit {  // 32 B, one sector
     float t, u, v;
     uint32_t rank;      // primitive rank, plane index, or 0xFFFFFFFF
     uint32_t kind;      // PYR_KIND_*

@@ -55,16 +55,6 @@ __device__ __forceinline__ uint32_t warp_exclusive_scan(uint32_t n, uint32_t& to
     return inc - n;
 }
 
-// Reserve `n` consecutive queue entries for this thread: one atomicAdd per warp.
-__device__ __forceinline__ uint32_t queue_reserve(uint32_t* counter, uint32_t n) {
-    uint32_t total;
-    uint32_t offset = warp_exclusive_scan(n, total);
-    uint32_t base = 0;
-    if (lane_id() == 31 && total) base = atomicAdd(counter, total);
-    base = __shfl_sync(FULL, base, 31);
-    return base + offset;
-}
-
 // Hand out global path-sample indices to the lanes that want one.
 __device__ __forceinline__ bool claim_sample(unsigned long long* next, unsigned long long total, bool want, unsigned long long& index) {
     unsigned mask = __ballot_sync(FULL, want);
@@ -92,11 +82,7 @@ __device__ __forceinline__ void locate_sample(const unsigned long long* tile_fir
 
 // Path state and the ray / hit queues are touched once per iteration: they go through the caches with the
 // streaming hint (ld/st.global.cs) so that they do not evict the BVH and the thread-local lines from L2.
-__device__ __forceinline__ void store_ray(Ray* dst, const Ray& r) {
-    float4* d = reinterpret_cast<float4*>(dst);
-    __stcs(d, make_float4(r.o[0], r.o[1], r.o[2], __uint_as_float(r.mode)));
-    __stcs(d + 1, make_float4(r.d[0], r.d[1], r.d[2], r.limit));
-}
+__device__ __forceinline__ void store_ray(Ray* dst, const Ray& r) { store_record_stream(dst, r); }
 // Dynamic shared memory of the shade kernels, in float4 units: VM registers [vm_regs][thread]; staged visibility
 // rays [2 * light_samples][thread]; then floats: the fold's colour cache [S][thread] and the path's wl / bright / refl
 // arrays [3 * S][thread].
@@ -116,49 +102,37 @@ __device__ __forceinline__ void bind_spectral(const SceneView& sc, PathState& ps
     ps.bright.base = base + S * WAVE_THREADS;
     ps.refl.base = base + 2u * S * WAVE_THREADS;
 }
-// header -> registers, per-wavelength arrays -> shared memory (16-byte streaming loads)
+// header -> registers, per-wavelength arrays -> shared memory; 32-byte chunks
 __device__ __forceinline__ void load_core(const SceneView& sc, PathState& ps, const PathCore* src) {
-    const float4* s = reinterpret_cast<const float4*>(src);
-    float4* h = reinterpret_cast<float4*>(static_cast<PathHeader*>(&ps));
+    static_assert(sizeof(PathHeader) == 64, "two chunks");
+    const Vec8* s = reinterpret_cast<const Vec8*>(src);
+    Vec8* h = reinterpret_cast<Vec8*>(static_cast<PathHeader*>(&ps));
+    h[0] = ld256_stream(s);
+    h[1] = ld256_stream(s + 1);
+    const uint32_t n = 3u * sc.renderer.spectrum_samples;
+    float* spectral = ps.wl.base;  // wl | bright | refl are contiguous in shared memory, stride S like the record
+    for (uint32_t c = 0; c * 8 < n; ++c) {
+        const Vec8 v = ld256_stream(s + 2 + c);
 #pragma unroll
-    for (int i = 0; i < (int)(sizeof(PathHeader) / 16); ++i) h[i] = __ldcs(s + i);
-    const uint32_t S = sc.renderer.spectrum_samples;
-    const float4* arrays = s + sizeof(PathHeader) / 16;
-    for (uint32_t q = 0; q * 4 < S; ++q) {
-        const float4 w = __ldcs(arrays + q), b = __ldcs(arrays + 4 + q), r = __ldcs(arrays + 8 + q);
-        const float wv[4] = {w.x, w.y, w.z, w.w}, bv[4] = {b.x, b.y, b.z, b.w}, rv[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-        for (uint32_t j = 0; j < 4; ++j)
-            if (q * 4 + j < S) { ps.wl[q * 4 + j] = wv[j]; ps.bright[q * 4 + j] = bv[j]; ps.refl[q * 4 + j] = rv[j]; }
+        for (uint32_t j = 0; j < 8; ++j)
+            if (c * 8 + j < n) spectral[(c * 8 + j) * WAVE_THREADS] = v.v[j];
     }
 }
 __device__ __forceinline__ void store_core(const SceneView& sc, PathCore* dst, const PathState& ps) {
-    float4* d = reinterpret_cast<float4*>(dst);
-    const float4* h = reinterpret_cast<const float4*>(static_cast<const PathHeader*>(&ps));
+    Vec8* d = reinterpret_cast<Vec8*>(dst);
+    const Vec8* h = reinterpret_cast<const Vec8*>(static_cast<const PathHeader*>(&ps));
+    st256_stream(d, h[0]);
+    st256_stream(d + 1, h[1]);
+    const uint32_t n = 3u * sc.renderer.spectrum_samples;
+    const float* spectral = ps.wl.base;
+    for (uint32_t c = 0; c * 8 < n; ++c) {
+        Vec8 v;
 #pragma unroll
-    for (int i = 0; i < (int)(sizeof(PathHeader) / 16); ++i) __stcs(d + i, h[i]);
-    const uint32_t S = sc.renderer.spectrum_samples;
-    float4* arrays = d + sizeof(PathHeader) / 16;
-    for (uint32_t q = 0; q * 4 < S; ++q) {
-        float wv[4], bv[4], rv[4];
-#pragma unroll
-        for (uint32_t j = 0; j < 4; ++j) {
-            const bool in = q * 4 + j < S;
-            wv[j] = in ? ps.wl[q * 4 + j] : 0.0f; bv[j] = in ? ps.bright[q * 4 + j] : 0.0f; rv[j] = in ? ps.refl[q * 4 + j] : 0.0f;
-        }
-        __stcs(arrays + q, make_float4(wv[0], wv[1], wv[2], wv[3]));
-        __stcs(arrays + 4 + q, make_float4(bv[0], bv[1], bv[2], bv[3]));
-        __stcs(arrays + 8 + q, make_float4(rv[0], rv[1], rv[2], rv[3]));
+        for (uint32_t j = 0; j < 8; ++j) v.v[j] = c * 8 + j < n ? spectral[(c * 8 + j) * WAVE_THREADS] : 0.0f;
+        st256_stream(d + 2 + c, v);
     }
 }
-__device__ __forceinline__ Ray load_ray(const Ray* src) {
-    const float4* s = reinterpret_cast<const float4*>(src);
-    float4 a = __ldcs(s), b = __ldcs(s + 1);
-    Ray r;
-    r.o[0] = a.x; r.o[1] = a.y; r.o[2] = a.z; r.mode = __float_as_uint(a.w);
-    r.d[0] = b.x; r.d[1] = b.y; r.d[2] = b.z; r.limit = b.w;
-    return r;
-}
+__device__ __forceinline__ Ray load_ray(const Ray* src) { return load_record_stream(src); }
 
 __global__ void k_pool_reset(PathCore* paths, uint32_t pool, uint32_t* live_list, uint32_t* live_count) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -214,24 +188,54 @@ __global__ void __launch_bounds__(256) k_bin(const PathCore* paths, const BidirS
     if (key != 0xFFFFFFFFu) bin_list[(size_t)key * pool + base + __popc(peers & ((1u << lane_id()) - 1u))] = slot;
 }
 
-// the slots still alive after this shade pass form the domain of the next k_bin
-__device__ __forceinline__ void append_live(const WaveArgs& a, uint32_t slot, bool alive) {
-    const unsigned mask = __ballot_sync(FULL, alive);
-    if (!mask) return;
-    uint32_t base = 0;
-    const int leader = __ffs(mask) - 1;
-    if ((int)lane_id() == leader) base = atomicAdd(a.live_count_out, (uint32_t)__popc(mask));
-    base = __shfl_sync(FULL, base, leader);
-    if (alive) a.live_list[base + __popc(mask & ((1u << lane_id()) - 1u))] = slot;
+// Queue space for one block of a shade kernel: path rays, visibility rays and the live-slot list (the slots still
+// alive after this pass are the domain of the next k_bin).  Warp totals meet in shared memory and one thread
+// issues the block's atomics back to back, so a block pays one L2 round trip instead of three per warp.
+struct Reservation { uint32_t main_at, shadow_at, live_at; };
+__device__ __forceinline__ Reservation block_reserve(const WaveArgs& a, uint32_t n_main, uint32_t n_shadow, bool alive) {
+    constexpr int WARPS = WAVE_THREADS / 32;
+    __shared__ uint32_t s_total[3][WARPS];
+    __shared__ uint32_t s_base[3];
+    const uint32_t warp = threadIdx.x >> 5;
+    uint32_t total_main, total_shadow;
+    Reservation r;
+    r.main_at = warp_exclusive_scan(n_main, total_main);
+    r.shadow_at = warp_exclusive_scan(n_shadow, total_shadow);
+    const unsigned live_mask = __ballot_sync(FULL, alive);
+    r.live_at = __popc(live_mask & ((1u << lane_id()) - 1u));
+    if (lane_id() == 0) { s_total[0][warp] = total_main; s_total[1][warp] = total_shadow; s_total[2][warp] = __popc(live_mask); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t[3] = {0, 0, 0};
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) { t[0] += s_total[0][w]; t[1] += s_total[1][w]; t[2] += s_total[2][w]; }
+        // count_out[0] / [1] are adjacent and 8-byte aligned: one 64-bit add reserves both regions
+        unsigned long long both = 0;
+        uint32_t live = 0;
+        if (t[0] | t[1]) both = atomicAdd(reinterpret_cast<unsigned long long*>(a.count_out), (unsigned long long)t[0] | ((unsigned long long)t[1] << 32));
+        if (t[2]) live = atomicAdd(a.live_count_out, t[2]);
+        s_base[0] = (uint32_t)both; s_base[1] = (uint32_t)(both >> 32); s_base[2] = live;
+    }
+    __syncthreads();
+    uint32_t before[3] = {s_base[0], s_base[1], s_base[2]};
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w)
+        if ((uint32_t)w < warp) { before[0] += s_total[0][w]; before[1] += s_total[1][w]; before[2] += s_total[2][w]; }
+    r.main_at += before[0]; r.shadow_at += before[1]; r.live_at += before[2];
+    return r;
 }
 
 // thread -> slot through the bins: the concatenation of all bins is a permutation of the live list
 __device__ __forceinline__ uint32_t binned_slot(const WaveArgs& a, uint32_t g, bool& valid, bool& dead) {
     __shared__ uint32_t s_first[NUM_BINS + 1];
-    if (threadIdx.x == 0) {
-        uint32_t acc = 0;
-        for (int b = 0; b < NUM_BINS; ++b) { s_first[b] = acc; acc += a.bin_count[b]; }
-        s_first[NUM_BINS] = acc;
+    static_assert(NUM_BINS == 64, "two bins per lane of the first warp");
+    if (threadIdx.x < 32) {
+        const uint2 c = reinterpret_cast<const uint2*>(a.bin_count)[threadIdx.x];
+        uint32_t total;
+        const uint32_t before = warp_exclusive_scan(c.x + c.y, total);
+        s_first[2 * threadIdx.x] = before;
+        s_first[2 * threadIdx.x + 1] = before + c.x;
+        if (threadIdx.x == 31) s_first[NUM_BINS] = total;
     }
     __syncthreads();
     valid = g < s_first[NUM_BINS];
@@ -253,48 +257,50 @@ __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS) k_wave_simple(c
     bool valid, dead;
     const uint32_t slot = binned_slot(a, g_thread, valid, dead);
     // a whole warp of dead slots with no samples left to start has nothing to do (long-tailed scenes)
-    if (__all_sync(FULL, !valid || dead) && *a.next_sample >= a.total_samples) return;
+    const bool idle = __all_sync(FULL, !valid || dead) && *a.next_sample >= a.total_samples;
     PathState ps;
     bind_spectral(sc, ps);
-    if (valid && !dead) load_core(sc, ps, a.paths + slot);
-    else ps.flags = 0;
-    ps.pend = a.pend + (size_t)(valid ? slot : 0) * MAX_LIGHT_SAMPLES;
-    ps.bd = nullptr;
-    const uint32_t flags_in = ps.flags;
-    FilmAdd add{a.film};
+    ps.flags = 0;
+    uint32_t flags_in = 0;
     ShadeOut out;
     out.alive = 0; out.has_main = 0; out.n_shadow = 0;
     out.stage_base = sc.vm_regs * WAVE_THREADS;
     PathCounters pc;
     pc.de_evals = 0; pc.de_iters = 0;
-
-    bool alive = valid && (ps.flags & PS_ALIVE);
-    if (alive) {
-        shade_simple(sc, ps, a.rays_in + ps.ray_base, a.hits_in + ps.ray_base, a.rays_in + a.shadow_offset + ps.shadow_base,
-                     a.shadow_kinds_in + ps.shadow_base, out, add, pc);
-        alive = out.alive != 0;
-        if (!alive) ps.flags = 0;
-    }
-    unsigned long long g = 0;
-    if (claim_sample(a.next_sample, a.total_samples, valid && !alive, g)) {
-        uint32_t tile; unsigned long long k;
-        locate_sample(a.tile_first, sc.n_tiles, g, tile, k);
-        generate_simple(sc, a.seed, tile, (uint64_t)a.sample_offset + k * a.sample_stride, ps, out.main);
-        ps.flags |= PS_ALIVE;
-        out.has_main = 1; out.n_shadow = 0; out.alive = 1;
-        alive = true;
+    bool alive = false;
+    if (!idle) {
+        if (valid && !dead) load_core(sc, ps, a.paths + slot);
+        ps.pend = a.pend + (size_t)(valid ? slot : 0) * MAX_LIGHT_SAMPLES;
+        ps.bd = nullptr;
+        flags_in = ps.flags;
+        FilmAdd add{a.film};
+        alive = valid && (ps.flags & PS_ALIVE);
+        if (alive) {
+            shade_simple(sc, ps, a.rays_in + ps.ray_base, a.hits_in + ps.ray_base, a.rays_in + a.shadow_offset + ps.shadow_base,
+                         a.shadow_kinds_in + ps.shadow_base, out, add, pc);
+            alive = out.alive != 0;
+            if (!alive) ps.flags = 0;
+        }
+        unsigned long long g = 0;
+        if (claim_sample(a.next_sample, a.total_samples, valid && !alive, g)) {
+            uint32_t tile; unsigned long long k;
+            locate_sample(a.tile_first, sc.n_tiles, g, tile, k);
+            generate_simple(sc, a.seed, tile, (uint64_t)a.sample_offset + k * a.sample_stride, ps, out.main);
+            ps.flags |= PS_ALIVE;
+            out.has_main = 1; out.n_shadow = 0; out.alive = 1;
+            alive = true;
+        }
     }
     // path rays and visibility rays go to separate queue regions so that trace packets are homogeneous
     const uint32_t n_main = alive ? out.has_main : 0u, n_shadow = alive ? out.n_shadow : 0u;
-    const uint32_t main_at = queue_reserve(a.count_out, n_main);
-    const uint32_t shadow_at = queue_reserve(a.count_out + 1, n_shadow);
-    if (n_main) { ps.ray_base = main_at; store_ray(a.rays_out + main_at, out.main); }
+    const Reservation at = block_reserve(a, n_main, n_shadow, valid && alive);
+    if (n_main) { ps.ray_base = at.main_at; store_ray(a.rays_out + at.main_at, out.main); }
     if (n_shadow) {
-        ps.shadow_base = shadow_at;
-        for (uint32_t j = 0; j < n_shadow; ++j) store_ray(a.rays_out + a.shadow_offset + shadow_at + j, out.get_shadow(j));
+        ps.shadow_base = at.shadow_at;
+        for (uint32_t j = 0; j < n_shadow; ++j) store_ray(a.rays_out + a.shadow_offset + at.shadow_at + j, out.get_shadow(j));
     }
     if (valid && (alive || (flags_in & PS_ALIVE))) store_core(sc, a.paths + slot, ps);
-    append_live(a, slot, valid && alive);
+    if (valid && alive) a.live_list[at.live_at] = slot;
     if (pc.de_evals) { atomicAdd(&a.counters->de_evals, (unsigned long long)pc.de_evals); atomicAdd(&a.counters->de_iterations, (unsigned long long)pc.de_iters); }
 }
 
@@ -430,9 +436,9 @@ struct EmitHit {
             if (at < shadow_offset) march_key[at] = pack_hit(tr.t, tr.kind, tr.rank);
         }
         if (at >= shadow_offset) { shadow_kinds[at - shadow_offset] = tr.kind; return; }  // visibility rays only report blocked / unblocked
-        float4* dst = reinterpret_cast<float4*>(hits + at);
-        dst[0] = make_float4(tr.t, tr.u, tr.v, __uint_as_float(tr.rank));
-        dst[1] = make_float4(__uint_as_float(tr.kind), 0.0f, 0.0f, 0.0f);
+        Hit h;
+        h.t = tr.t; h.u = tr.u; h.v = tr.v; h.rank = tr.rank; h.kind = tr.kind; h.nodes = 0; h.leaves = 0; h.pad = 0;
+        store_record(hits + at, h);
     }
 };
 

@@ -8,7 +8,7 @@
 namespace pyr {
 
 // ---------------------------------------------------------------- path state (one per path sample in flight)
-struct PendingLight {          // tracer.rs:193-200 `DirectLight`, waiting for its visibility ray
+struct alignas(32) PendingLight {   // 32 B; tracer.rs:193-200 `DirectLight`, waiting for its visibility ray
     int32_t color_program;
     uint32_t dispersed;
     float normal[3];
@@ -18,7 +18,7 @@ struct PendingLight {          // tracer.rs:193-200 `DirectLight`, waiting for i
 enum : uint32_t { PS_USE_ADDITIONAL = 1u, PS_SAMPLE_LIGHT = 2u, PS_HAS_MAIN = 4u, PS_PENDING_FOLD = 8u, PS_ALIVE = 16u };
 
 // What is stored per path slot in HBM: a 64-byte header and the three per-wavelength arrays, 256 B.
-struct alignas(16) PathHeader {
+struct alignas(32) PathHeader {
     Rng rng;
     float pos[2];              // film position in view coordinates (Tile::sample_point)
     uint32_t tile, flags;
@@ -27,10 +27,11 @@ struct alignas(16) PathHeader {
     uint32_t shadow_base;      // index of this path's first visibility ray in the shadow region
     uint32_t pad[2];
 };
-struct alignas(16) PathCore : PathHeader {
-    float wl[MAX_SPECTRUM_SAMPLES];      // [0] = hero wavelength, then the additional ones (simple.rs:105-107)
-    float bright[MAX_SPECTRUM_SAMPLES];  // Sample::brightness
-    float refl[MAX_SPECTRUM_SAMPLES];    // the running reflectance of renderer/algorithm.rs:14-100
+struct alignas(32) PathCore : PathHeader {
+    // wl[S] | bright[S] | refl[S], packed with stride S = spectrum_samples: wl[0] is the hero wavelength, then the
+    // additional ones (simple.rs:105-107); bright = Sample::brightness; refl = the running reflectance of
+    // renderer/algorithm.rs:14-100.  ceil(3 S / 8) 32-byte chunks are moved per pass.
+    float spectral[3 * MAX_SPECTRUM_SAMPLES];
 };
 // bidirectional integrator only (bdpt.cuh)
 struct alignas(16) BidirState {
@@ -502,7 +503,7 @@ PYR_HD void next_event(const SceneView& sc, PathState& ps, float wavelength, v3 
         float scale = ls.weight * probability * (2.0f * fabsf(dot(ls.direction, normal)));  // lambertian(ray_in, normal, ray_out)
         pl.probability = scale * material_probability;
         uint32_t j = out.n_shadow++;
-        ps.pend[j] = pl;
+        store_record_stream(ps.pend + j, pl);
         // blocked <=> a hit with t > eps and t^2 < sq_distance - eps (tracer.rs:381-389); lamps without a
         // distance (directional) are blocked by any hit
         out.put_shadow(j, make_ray(position, ls.direction, 1, ls.has_sq ? ls.sq_distance - DIST_EPSILON : PYR_INF));
@@ -565,14 +566,14 @@ PYR_HD bool camera_step(const SceneView& sc, PathState& ps, const Ray* main_ray,
 #endif
         for (uint32_t j = 0; j < ps.n_pending; ++j) {
             if (shadow_kinds[j] != KIND_MISS) continue;  // blocked
-            const PendingLight pl = ps.pend[j];
+            const PendingLight pl = load_record_stream(ps.pend + j);
             const uint32_t m = pl.dispersed ? 1u : n;
             if (pl.color_program != cached_program || m > cached_n) {
                 const ProgramRec p = sc.programs[pl.color_program];
                 const bool wavelength_only = p.is_constant || !(p.reads & (IN_NORMAL | IN_INCIDENT | IN_TEXTURE));
                 VmInputs in;
                 in.wavelength = 0.0f; in.normal = ld3(pl.normal); in.tex[0] = pl.tex[0]; in.tex[1] = pl.tex[1];
-                in.incident = wavelength_only ? mk3(0, 0, 0) : ld3(shadow_rays[j].d);  // the ray is only fetched when the colour looks at it
+                in.incident = wavelength_only ? mk3(0, 0, 0) : ld3(load_record_stream(shadow_rays + j).d);  // the ray is only fetched when the colour looks at it
                 eval_spectral_each(sc, pl.color_program, in, ps.wl, m, R, [&](uint32_t k, float v) { PYR_C(k) = v; });
                 cached_program = wavelength_only ? pl.color_program : -1;
                 cached_n = m;
@@ -587,8 +588,9 @@ PYR_HD bool camera_step(const SceneView& sc, PathState& ps, const Ray* main_ray,
     }
     if (!(ps.flags & PS_HAS_MAIN)) return false;
 
-    const v3 o = ld3(main_ray->o), d = ld3(main_ray->d);
-    const Hit h = *main_hit;
+    const Ray incoming = load_record_stream(main_ray);
+    const v3 o = ld3(incoming.o), d = ld3(incoming.d);
+    const Hit h = load_record(main_hit);
     const float wavelength = ps.wl[0];
     if (h.kind == KIND_MISS) {  // tracer.rs:322-342
         int32_t color = sc.sky_program;
