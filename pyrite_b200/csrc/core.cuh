@@ -37,6 +37,12 @@ __device__ __forceinline__ Vec8 ld256_stream(const void* p) {
                  : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7]) : "l"(p));
     return r;
 }
+__device__ __forceinline__ Vec8 ld256_readonly(const void* p) {  // scene data: the non-coherent path, like __ldg
+    Vec8 r;
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7]) : "l"(p));
+    return r;
+}
 __device__ __forceinline__ void st256(void* p, const Vec8& r) {
     asm volatile("st.global.v8.f32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};"
                  :: "f"(r.v[0]), "f"(r.v[1]), "f"(r.v[2]), "f"(r.v[3]), "f"(r.v[4]), "f"(r.v[5]), "f"(r.v[6]), "f"(r.v[7]), "l"(p) : "memory");
@@ -48,6 +54,7 @@ __device__ __forceinline__ void st256_stream(void* p, const Vec8& r) {
 #else
 inline Vec8 ld256(const void* p) { Vec8 r; __builtin_memcpy(&r, p, 32); return r; }
 inline Vec8 ld256_stream(const void* p) { return ld256(p); }
+inline Vec8 ld256_readonly(const void* p) { return ld256(p); }
 inline void st256(void* p, const Vec8& r) { __builtin_memcpy(p, &r, 32); }
 inline void st256_stream(void* p, const Vec8& r) { st256(p, r); }
 #endif
@@ -712,13 +719,12 @@ PYR_HD bool occludes(uint32_t mode, float t, float limit) { return mode == 1 ? (
 // 16-byte loads through the read-only path on the device
 PYR_HD Node4 fetch_node(const Node4* p) {
 #if defined(__CUDA_ARCH__)
-    const float4* q = reinterpret_cast<const float4*>(p);
-    const float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3), e = __ldg(q + 4), f = __ldg(q + 5);
-    const int4 ch = __ldg(reinterpret_cast<const int4*>(q + 6));
+    const Vec8 a = ld256_readonly(p), b = ld256_readonly(reinterpret_cast<const Vec8*>(p) + 1), c = ld256_readonly(reinterpret_cast<const Vec8*>(p) + 2),
+               d = ld256_readonly(reinterpret_cast<const Vec8*>(p) + 3);
     Node4 n;
-    n.lo_x = mk4(a.x, a.y, a.z, a.w); n.lo_y = mk4(b.x, b.y, b.z, b.w); n.lo_z = mk4(c.x, c.y, c.z, c.w);
-    n.hi_x = mk4(d.x, d.y, d.z, d.w); n.hi_y = mk4(e.x, e.y, e.z, e.w); n.hi_z = mk4(f.x, f.y, f.z, f.w);
-    n.child[0] = ch.x; n.child[1] = ch.y; n.child[2] = ch.z; n.child[3] = ch.w;
+    n.lo_x = mk4(a.v[0], a.v[1], a.v[2], a.v[3]); n.lo_y = mk4(a.v[4], a.v[5], a.v[6], a.v[7]); n.lo_z = mk4(b.v[0], b.v[1], b.v[2], b.v[3]);
+    n.hi_x = mk4(b.v[4], b.v[5], b.v[6], b.v[7]); n.hi_y = mk4(c.v[0], c.v[1], c.v[2], c.v[3]); n.hi_z = mk4(c.v[4], c.v[5], c.v[6], c.v[7]);
+    n.child[0] = __float_as_int(d.v[0]); n.child[1] = __float_as_int(d.v[1]); n.child[2] = __float_as_int(d.v[2]); n.child[3] = __float_as_int(d.v[3]);
     return n;
 #else
     return *p;

@@ -40,7 +40,7 @@ struct alignas(16) Prim { f4 a, b, c; };
 // ancestors' tests changes nothing: a child box lies inside its parent's and the slab test is monotone.
 // 128 B = eight 16-byte loads, boxes stored component-wise (lo_x[4], lo_y[4], ...).
 //   child[k] >= 0: Node4 index; < 0: leaf, rank = ~child; NODE4_EMPTY: no child in this slot
-struct alignas(16) Node4 {
+struct alignas(32) Node4 {
     f4 lo_x, lo_y, lo_z, hi_x, hi_y, hi_z;
     int32_t child[4];
     uint32_t pad[4];

@@ -154,17 +154,18 @@ __device__ __forceinline__ uint32_t unblocked_count(const uint32_t* kinds, uint3
 }
 __global__ void __launch_bounds__(256) k_bin(const PathCore* paths, const BidirState* bidir, uint32_t pool, const Hit* hits, const uint32_t* shadow_kinds,
                                              uint32_t* bin_count, uint32_t* bin_list, const uint32_t* live_list, const uint32_t* live_count) {
+    // block-level counting sort step: keys are counted in shared memory, one global atomic per non-empty bin and block
+    __shared__ uint32_t s_count[NUM_BINS], s_base[NUM_BINS];
+    if (threadIdx.x < NUM_BINS) s_count[threadIdx.x] = 0;
+    __syncthreads();
     const uint32_t index = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_live = *live_count;
-    if ((index & ~31u) >= n_live) return;  // whole warp beyond the live list
     // while every slot is alive the list is a permutation of [0, pool): walk the slots in order instead (coalesced)
     const uint32_t slot = index < n_live ? (n_live == pool ? index : live_list[index]) : 0xFFFFFFFFu;
     uint32_t key = 0xFFFFFFFFu;
     if (slot < pool) {
-        const uint4 h0 = reinterpret_cast<const uint4*>(paths + slot)[1];  // pos[2], tile, flags
-        const uint4 h1 = reinterpret_cast<const uint4*>(paths + slot)[2];  // bounce, light_events, n_pending, ray_base
-        const uint4 h2 = reinterpret_cast<const uint4*>(paths + slot)[3];  // pending_brdf, shadow_base
-        const uint32_t flags = h0.w, n_pending = h1.z, ray_base = h1.w, shadow_base = h2.y;
+        const uint4 h = __ldg(reinterpret_cast<const uint4*>(paths + slot) + 2);  // flags, n_pending, ray_base, shadow_base
+        const uint32_t flags = h.x, n_pending = h.y, ray_base = h.z, shadow_base = h.w;
         if (!(flags & PS_ALIVE)) key = 0;
         else {
             const uint32_t phase = bidir ? bidir[slot].phase : PH_CAMERA;
@@ -180,12 +181,19 @@ __global__ void __launch_bounds__(256) k_bin(const PathCore* paths, const BidirS
             }
         }
     }
+    const bool have = key != 0xFFFFFFFFu;
     const unsigned peers = __match_any_sync(FULL, key);
     const int leader = __ffs(peers) - 1;
     uint32_t base = 0;
-    if ((int)lane_id() == leader && key != 0xFFFFFFFFu) base = atomicAdd(&bin_count[key], (uint32_t)__popc(peers));
-    base = __shfl_sync(FULL, base, leader);
-    if (key != 0xFFFFFFFFu) bin_list[(size_t)key * pool + base + __popc(peers & ((1u << lane_id()) - 1u))] = slot;
+    if ((int)lane_id() == leader && have) base = atomicAdd(&s_count[key], (uint32_t)__popc(peers));
+    base = __shfl_sync(FULL, base, leader) + __popc(peers & ((1u << lane_id()) - 1u));
+    __syncthreads();
+    if (threadIdx.x < NUM_BINS) {
+        const uint32_t c = s_count[threadIdx.x];
+        s_base[threadIdx.x] = c ? atomicAdd(&bin_count[threadIdx.x], c) : 0u;
+    }
+    __syncthreads();
+    if (have) bin_list[(size_t)key * pool + s_base[key] + base] = slot;
 }
 
 // Queue space for one block of a shade kernel: path rays, visibility rays and the live-slot list (the slots still

@@ -21,10 +21,12 @@ enum : uint32_t { PS_USE_ADDITIONAL = 1u, PS_SAMPLE_LIGHT = 2u, PS_HAS_MAIN = 4u
 struct alignas(32) PathHeader {
     Rng rng;
     float pos[2];              // film position in view coordinates (Tile::sample_point)
-    uint32_t tile, flags;
-    uint32_t bounce, light_events, n_pending, ray_base;
-    float pending_brdf;
+    uint32_t tile, bounce;
+    // the four words k_bin reads (one 16-byte load, bytes 32..47 of the record)
+    uint32_t flags, n_pending, ray_base;
     uint32_t shadow_base;      // index of this path's first visibility ray in the shadow region
+    uint32_t light_events;
+    float pending_brdf;
     uint32_t pad[2];
 };
 struct alignas(32) PathCore : PathHeader {
