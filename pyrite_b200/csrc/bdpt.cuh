@@ -29,7 +29,7 @@ enum : uint32_t { VT_DIFFUSE = 0, VT_SPECULAR = 1, VT_EMISSION = 2 };
 // One stored vertex of the lamp subpath (tracer.rs:157-167 `Bounce`; lamp paths carry no direct light), plus
 // its colour program evaluated at the path's wavelengths: connect_paths and light tracing re-fold the tail of
 // the lamp path for every connection (bidirectional.rs:373-389, 276-292), always with the same colours. 144 B.
-struct alignas(16) LightVertex {
+struct alignas(16) LightVertexHead {   // 80 B: what a thread keeps in registers
     float position[3];
     uint32_t type;
     float normal[3];
@@ -40,14 +40,18 @@ struct alignas(16) LightVertex {
     uint32_t dispersed;
     float tex[2];
     uint32_t pad[2];
-    float color[MAX_SPECTRUM_SAMPLES];  // color(wl[k]), filled by finish_lamp_path
+};
+struct alignas(16) LightVertex : LightVertexHead {
+    float color[MAX_SPECTRUM_SAMPLES];  // color(wl[k]), filled by finish_lamp_path; read in place (never copied to a thread)
 };
 // A diffuse camera-subpath vertex with the sample state right after its `contribute`. 160 B.
-struct alignas(16) CamVertex {
+struct alignas(32) CamVertexHead {
     float position[3];
     float brdf;           // bounce.ty.brdf(..) = 2 |out . normal|
     float normal[3];
     uint32_t use_additional;
+};
+struct alignas(32) CamVertex : CamVertexHead {
     float bright[MAX_SPECTRUM_SAMPLES];
     float refl[MAX_SPECTRUM_SAMPLES];
 };
@@ -61,32 +65,32 @@ struct BidirOut {
 struct BidirCtx {
     LightVertex* lv;   // this path's lamp vertices
     CamVertex* cv;     // this path's stored camera vertices
+    SpecArray bright, refl;  // detached sample state of one connection / light-traced sample (shared memory in the kernel)
 };
 
 PYR_HD void st3(float* dst, v3 v) { dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; }
-PYR_HD float vertex_brdf(const LightVertex& v) {  // BounceType::brdf: lambertian(_, normal, out) = 2 |out . normal|
+PYR_HD float vertex_brdf(const LightVertexHead& v) {  // BounceType::brdf: lambertian(_, normal, out) = 2 |out . normal|
     return v.type == VT_DIFFUSE ? 2.0f * fabsf(dot(ld3(v.out), ld3(v.normal))) : 1.0f;
 }
 
 // `contribute` (renderer/algorithm.rs:14-100) of a lamp-subpath bounce on a detached sample state
-PYR_HD void contribute_vertex(const LightVertex& v, uint32_t n, float* bright, float* refl) {
+PYR_HD void contribute_vertex(const LightVertexHead& v, const float* color, uint32_t n, SpecArray bright, SpecArray refl) {
     if (v.type == VT_EMISSION) {
-        for (uint32_t k = 0; k < n; ++k) bright[k] += v.color[k] * v.probability * refl[k];
+        for (uint32_t k = 0; k < n; ++k) bright[k] += color[k] * v.probability * refl[k];
     } else {
-        for (uint32_t k = 0; k < n; ++k) refl[k] *= v.color[k] * v.probability;
         const float brdf = vertex_brdf(v);
-        for (uint32_t k = 0; k < n; ++k) refl[k] *= brdf;
+        for (uint32_t k = 0; k < n; ++k) { refl[k] *= color[k] * v.probability; refl[k] *= brdf; }
     }
 }
 // the fold over lamp_path[first..] shared by connect_paths (:373-389) and light tracing (:276-292)
 PYR_HD void fold_lamp_tail(const SceneView& sc, const LightVertex* lv, uint32_t first, uint32_t n_light, bool& use_additional,
-                           float* bright, float* refl, float brdf_in) {
+                           SpecArray bright, SpecArray refl, float brdf_in) {
     const uint32_t S = sc.renderer.spectrum_samples;
     for (uint32_t k = first; k < n_light; ++k) {
-        const LightVertex v = lv[k];
+        const LightVertexHead v = lv[k];
         use_additional = !v.dispersed && use_additional;
         const uint32_t n = use_additional ? S : 1u;
-        contribute_vertex(v, n, bright, refl);
+        contribute_vertex(v, lv[k].color, n, bright, refl);
         if (k == first) for (uint32_t j = 0; j < n; ++j) refl[j] *= brdf_in;
     }
 }
@@ -412,16 +416,17 @@ PYR_HD void shade_bidirectional(const SceneView& sc, PathState& ps, const BidirC
         return;
     }
     uint32_t lamp_index[BDPT_STAGE];
-    float bright[MAX_SPECTRUM_SAMPLES], refl[MAX_SPECTRUM_SAMPLES];
+    const SpecArray bright = cx.bright, refl = cx.refl;
     if (ps.bd->phase == PH_CONNECT) {  // evaluate the connections whose visibility rays were just traced
         uint32_t next;
         const uint32_t n = stage_connections(ps, cx, ps.bd->conn_light, nullptr, lamp_index, next);
-        const CamVertex c = cx.cv[ps.bd->conn_cam];
+        const CamVertex& stored = cx.cv[ps.bd->conn_cam];
+        const CamVertexHead c = stored;
         const v3 from = ld3(c.position), cn = ld3(c.normal);
         const float weight = 1.0f / (float)(ps.bd->n_cam * ps.bd->n_light);  // bidirectional.rs:217-218
         for (uint32_t j = 0; j < n; ++j) {
             if (shadow_kinds[j] != KIND_MISS) continue;
-            const LightVertex v = cx.lv[lamp_index[j]];
+            const LightVertexHead v = cx.lv[lamp_index[j]];
             v3 direction = ld3(v.position) - from;
             float sq_distance = length2(direction);
             float distance = sqrtf(sq_distance);
@@ -431,7 +436,7 @@ PYR_HD void shade_bidirectional(const SceneView& sc, PathState& ps, const BidirC
             float brdf_out = (2.0f * fabsf(dot(dir, cn))) / c.brdf;
             float scale = cos_in * cos_out * brdf_out / (2.0f * PYR_PI * sq_distance);
             float brdf_in = vertex_brdf(v) / vertex_brdf(v);
-            for (uint32_t k = 0; k < S; ++k) { bright[k] = c.bright[k]; refl[k] = c.refl[k] * scale; }
+            for (uint32_t k = 0; k < S; ++k) { bright[k] = stored.bright[k]; refl[k] = stored.refl[k] * scale; }
             bool use_additional = c.use_additional != 0;
             fold_lamp_tail(sc, cx.lv, lamp_index[j], ps.bd->n_light, use_additional, bright, refl, brdf_in);
             film_expose(sc.film, ps.pos[0], ps.pos[1], bright[0], ps.wl[0], weight, add);
@@ -456,7 +461,7 @@ PYR_HD void shade_bidirectional(const SceneView& sc, PathState& ps, const BidirC
         const float weight = 1.0f / (float)ps.bd->n_light;
         for (uint32_t j = 0; j < n; ++j) {
             if (shadow_kinds[j] != KIND_MISS) continue;
-            const LightVertex v = cx.lv[lamp_index[j]];
+            const LightVertexHead v = cx.lv[lamp_index[j]];
             const v3 target = ld3(v.position);
             v3 local_target = transform_point(sc.camera.inv, target);
             const v3 origin = lens[j];

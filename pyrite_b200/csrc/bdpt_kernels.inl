@@ -27,6 +27,8 @@ __global__ void __launch_bounds__(WAVE_THREADS) k_wave_bidirectional(const __gri
         BidirCtx cx;
         cx.lv = a.light_vertices + (size_t)s * a.light_stride;
         cx.cv = a.cam_vertices + (size_t)s * a.cam_stride;
+        cx.bright.base = ps.refl.base + sc.renderer.spectrum_samples * WAVE_THREADS;  // two more [S][thread] arrays behind wl | bright | refl
+        cx.refl.base = cx.bright.base + sc.renderer.spectrum_samples * WAVE_THREADS;
         FilmAdd add{a.film};
         alive = valid && (ps.flags & PS_ALIVE);
         if (alive) {
@@ -59,9 +61,10 @@ __global__ void __launch_bounds__(WAVE_THREADS) k_wave_bidirectional(const __gri
 
 }  // namespace
 
+inline size_t bidir_smem(const SceneView& sc) { return wave_smem(sc) + (size_t)2 * sc.renderer.spectrum_samples * WAVE_THREADS * sizeof(float); }
 void launch_wave_bidirectional(const SceneView& sc, const WaveArgs& a, cudaStream_t s) {
-    cudaFuncSetAttribute(k_wave_bidirectional, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wave_smem(sc));
-    k_wave_bidirectional<<<(a.pool + WAVE_THREADS - 1) / WAVE_THREADS, WAVE_THREADS, wave_smem(sc), s>>>(sc, a);
+    cudaFuncSetAttribute(k_wave_bidirectional, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bidir_smem(sc));
+    k_wave_bidirectional<<<(a.pool + WAVE_THREADS - 1) / WAVE_THREADS, WAVE_THREADS, bidir_smem(sc), s>>>(sc, a);
 }
 size_t cam_vertex_bytes() { return sizeof(CamVertex); }
 int bdpt_stage_rays() { return BDPT_STAGE; }

@@ -110,7 +110,8 @@ int emu_render(void* h, uint64_t seed, uint32_t spp_override, uint32_t offset, u
         ps->bd = &bd;
         std::vector<LightVertex> lv(sc.renderer.light_bounces + 1);
         std::vector<CamVertex> cv(sc.renderer.bounces > 0 ? sc.renderer.bounces : 1);
-        BidirCtx cx{lv.data(), cv.data()};
+        std::vector<float> scratch(2 * MAX_SPECTRUM_SAMPLES);
+        BidirCtx cx{lv.data(), cv.data(), {scratch.data()}, {scratch.data() + MAX_SPECTRUM_SAMPLES}};
         for (uint32_t t = 0; t < sc.n_tiles; ++t) {
             const uint64_t iterations = (uint64_t)sc.tiles[t].width * sc.tiles[t].height * spp;
             for (uint64_t i = offset; i < iterations; i += stride) {
