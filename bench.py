@@ -219,6 +219,9 @@ def run_product(args):
 
     # ---- end-to-end through the public API with host buffers: render step + develop + image download
     e2e_steps = max(1, min(args.steps, 4))
+    if rank == 0:  # the images land in page-locked host memory
+        host_xyz = torch.empty((info.height, info.width, 3), dtype=torch.float32, pin_memory=True).numpy()
+        host_srgb = torch.empty((info.height, info.width, 3), dtype=torch.uint8, pin_memory=True).numpy()
     barrier()
     r.counters(reset=True)
     te0 = time.time()
@@ -227,7 +230,7 @@ def run_product(args):
         if world > 1:
             reduce_film(film, dst=0)
         if rank == 0:
-            xyz, srgb = r.develop()
+            xyz, srgb = r.develop(out_xyz=host_xyz, out_srgb=host_srgb)
     barrier()
     te1 = time.time()
     ce = r.counters()
@@ -263,12 +266,14 @@ def run_product(args):
                  "avg_launch_ms": 1e3 * trace_s / trace_n, "share_of_step": trace_s / max(c["trace_seconds"] + c["shade_seconds"], 1e-12),
                  "mrays_per_s": c["rays"] / max(trace_s, 1e-12) / 1e6,
                  "note": "algorithmic node/primitive bytes; the ncu capture shows that L2/L1 serve most of them (traffic = DRAM bytes per launch)"}
-        # the shade stage (k_bin + k_wave_simple): per path iteration the 256 B core is read and written, the path ray and its hit are read,
-        # the next ray is written; per visibility ray 4 B result in, 32 B ray + 36 B pending light out and back in; per sample S film atomics
+        # the shade stage (k_bin + k_wave_simple): per path iteration the path record (64 B header + ceil(3 S / 8) 32-byte chunks of
+        # wavelengths / brightness / reflectance) is read and written, the path ray and its hit are read, the next ray is written; per
+        # visibility ray 4 B result in, 32 B ray + 32 B pending light out and the light back in; per sample S film atomics of 8 B
         S = info.spectrum_samples
+        core_bytes = 64 + 32 * ((3 * S + 7) // 8)
         path_iterations = c["path_rays"] + c["path_samples"]
         shadow = c["rays"] - c["path_rays"]
-        shade_bytes = path_iterations * 512 + c["path_rays"] * (32 + 32 + 32) + shadow * (4 + 32 + 72) + c["path_samples"] * S * 8
+        shade_bytes = path_iterations * 2 * core_bytes + c["path_rays"] * (32 + 32 + 32) + shadow * (4 + 32 + 64) + c["path_samples"] * S * 8
         shade_s, shade_n = c["shade_seconds"], max(c["shade_launches"], 1)
         shade_achieved = shade_bytes / max(shade_s, 1e-12) / 1e9
         shade = {"bound": "hbm", "kernel": "k_bin + k_wave_simple", "achieved": shade_achieved, "peak": peak, "unit": "GB/s", "frac": shade_achieved / peak,
@@ -294,10 +299,10 @@ def run_product(args):
                        "step": f"{spp_step} spp per GPU per step ({256 // max(spp_step, 1)} steps = the 256-spp config on 1 GPU)",
                        "parallelism": f"sample-pass sharding over {world} GPU(s), one NCCL film reduce at the end",
                        "l2": "working set (film 1.06 GB + path pool + 150 MB BVH) exceeds the 126 MB L2; no flush needed",
-                       "pool_paths": args.pool or (1 << 21)},
+                       "pool_paths": args.pool or "library default: 2^24 paths in flight (capped by a sixth of device memory and by the step's path samples)"},
             "clocks": clocks,
             "e2e": {"value": e2e_mrays, "unit": "Mrays/s", "h2d_bytes_per_step": 32, "d2h_bytes_per_step": pixels * 15,
-                    "what": "pyr_render step + pyr_film_develop + XYZ f32 and sRGB u8 image download to host, wall clock"},
+                    "what": "pyr_render step + pyr_film_develop + XYZ f32 and sRGB u8 image download to pinned host memory, wall clock"},
             "gpu_launches": launches,
             "roofline": roofline,
             "cpu_baseline": cpu,
@@ -315,7 +320,7 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
-    ap.add_argument("--spp-per-step", type=int, default=8)
+    ap.add_argument("--spp-per-step", type=int, default=32, help="sample passes per GPU per step (8 steps of 32 = the 256-spp C2 job)")
     ap.add_argument("--pool", type=int, default=0, help="paths in flight (0 = library default)")
     ap.add_argument("--cpu-fraction", type=int, default=1, help="the CPU legs render every N-th path sample of a pass")
     ap.add_argument("--cpu-spp", type=int, default=4, help="sample passes of the cpu_baseline leg (4 passes = about 15 s on 16 cores)")

@@ -232,10 +232,19 @@ class Renderer:
         assert nbytes.value == int(np.prod(self.film_shape)) * 4
         return DeviceFilm(ptr.value, self.film_shape)
 
-    def develop(self, step_size: float = 2.0, want_xyz: bool = True, want_srgb: bool = True):
+    def develop(self, step_size: float = 2.0, want_xyz: bool = True, want_srgb: bool = True, out_xyz=None, out_srgb=None):
+        """Film -> (XYZ f32, sRGB u8) images on the host.  `out_xyz` / `out_srgb`: caller-owned C-contiguous arrays of the
+        image shape to download into (page-locked ones make the copies DMA transfers); otherwise fresh arrays."""
         i = self.info
-        xyz = np.empty((i.height, i.width, 3), dtype=np.float32) if want_xyz else None
-        srgb = np.empty((i.height, i.width, 3), dtype=np.uint8) if want_srgb else None
+        xyz = srgb = None
+        if want_xyz:
+            xyz = out_xyz if out_xyz is not None else np.empty((i.height, i.width, 3), dtype=np.float32)
+            if xyz.dtype != np.float32 or xyz.shape != (i.height, i.width, 3) or not xyz.flags.c_contiguous:
+                raise ValueError("out_xyz must be a C-contiguous float32 array of shape (height, width, 3)")
+        if want_srgb:
+            srgb = out_srgb if out_srgb is not None else np.empty((i.height, i.width, 3), dtype=np.uint8)
+            if srgb.dtype != np.uint8 or srgb.shape != (i.height, i.width, 3) or not srgb.flags.c_contiguous:
+                raise ValueError("out_srgb must be a C-contiguous uint8 array of shape (height, width, 3)")
         self._check(self.L.pyr_film_develop(self.h, step_size, _ptr(xyz) if want_xyz else None, _ptr(srgb) if want_srgb else None))
         return xyz, srgb
 

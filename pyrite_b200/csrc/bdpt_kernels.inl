@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(WAVE_THREADS) k_wave_bidirectional(const __gri
 inline size_t bidir_smem(const SceneView& sc) { return wave_smem(sc) + (size_t)2 * sc.renderer.spectrum_samples * WAVE_THREADS * sizeof(float); }
 void launch_wave_bidirectional(const SceneView& sc, const WaveArgs& a, cudaStream_t s) {
     cudaFuncSetAttribute(k_wave_bidirectional, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bidir_smem(sc));
-    k_wave_bidirectional<<<(a.pool + WAVE_THREADS - 1) / WAVE_THREADS, WAVE_THREADS, bidir_smem(sc), s>>>(sc, a);
+    k_wave_bidirectional<<<(a.grid_paths + WAVE_THREADS - 1) / WAVE_THREADS, WAVE_THREADS, bidir_smem(sc), s>>>(sc, a);
 }
 size_t cam_vertex_bytes() { return sizeof(CamVertex); }
 int bdpt_stage_rays() { return BDPT_STAGE; }

@@ -696,11 +696,11 @@ void launch_pool_reset(PathCore* paths, uint32_t pool, uint32_t* live_list, uint
 }
 void launch_bin(const WaveArgs& a, uint32_t* bin_count, uint32_t* bin_list, int bidirectional, cudaStream_t s) {
     cudaMemsetAsync(bin_count, 0, NUM_BINS * sizeof(uint32_t), s);
-    k_bin<<<(a.pool + 255) / 256, 256, 0, s>>>(a.paths, bidirectional ? a.bidir : nullptr, a.pool, a.hits_in, a.shadow_kinds_in, bin_count, bin_list, a.live_list, a.live_count_in);
+    k_bin<<<(a.grid_paths + 255) / 256, 256, 0, s>>>(a.paths, bidirectional ? a.bidir : nullptr, a.pool, a.hits_in, a.shadow_kinds_in, bin_count, bin_list, a.live_list, a.live_count_in);
 }
 void launch_wave_simple(const SceneView& sc, const WaveArgs& a, cudaStream_t s) {
     cudaFuncSetAttribute(k_wave_simple, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wave_smem(sc));
-    k_wave_simple<<<(a.pool + WAVE_THREADS - 1) / WAVE_THREADS, WAVE_THREADS, wave_smem(sc), s>>>(sc, a);
+    k_wave_simple<<<(a.grid_paths + WAVE_THREADS - 1) / WAVE_THREADS, WAVE_THREADS, wave_smem(sc), s>>>(sc, a);
 }
 TraceTuning trace_tuning() {
     static TraceTuning t = [] {

@@ -24,6 +24,7 @@ struct WaveArgs {
     PendingLight* pend;        // pool * MAX_LIGHT_SAMPLES
     BidirState* bidir;         // bidirectional only
     uint32_t pool;
+    uint32_t grid_paths;       // upper bound of the live-slot count of this pass (sizes the k_bin / shade grids)
     const Ray* rays_in;        // rays traced in the previous iteration (read by the shade stage)
     const Hit* hits_in;
     const uint32_t* shadow_kinds_in;  // hit kind per visibility ray of the previous pass (KIND_MISS = unblocked)
