@@ -9,10 +9,10 @@ from pyrite_b200 import api, project, scenes
 
 CONFIGS = {
     "C1 cornell 512x512 simple (64 spp)": (lambda: scenes.cornell(width=512, height=512, spp=64), 64),
-    "C2 dragon 1920x1080 simple": (lambda: scenes.dragon(spp=256), 8),
-    "C3 diamonds 1920x1080 simple, dispersion, S=1, B=256": (lambda: scenes.diamonds(width=1920, height=1080, spp=200), 8),
-    "C4 mandelbulb + julia 3840x2160 simple": (lambda: scenes.fractals(), 2),
-    "C5 textured cornell + dragon 3840x2160 bidirectional": (lambda: scenes.bdpt_cornell_dragon(), 1),
+    "C2 dragon 1920x1080 simple": (lambda: scenes.dragon(spp=256), 32),
+    "C3 diamonds 1920x1080 simple, dispersion, S=1, B=256": (lambda: scenes.diamonds(width=1920, height=1080, spp=200), 50),
+    "C4 mandelbulb + julia 3840x2160 simple": (lambda: scenes.fractals(), 4),
+    "C5 textured cornell + dragon 3840x2160 bidirectional": (lambda: scenes.bdpt_cornell_dragon(), 2),
 }
 out = {}
 for name, (make, spp) in CONFIGS.items():
