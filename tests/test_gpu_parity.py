@@ -154,6 +154,46 @@ def test_sample_pass_sharding_is_additive(gpu_renderer_factory):
     assert np.allclose(whole[..., 0], parts[..., 0], rtol=1e-4, atol=1e-5)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["cornell", "diamonds", "bd_cornell"])
+def test_pool_size_does_not_change_the_job(name, gpu_renderer_factory):
+    """Paths in flight only change how the job is cut into wavefront iterations: streams are keyed by sample index, so
+    ray counts and film weights are identical and the accumulators differ by float atomics order only."""
+    if name not in SCENE_NAMES and name not in BIDIR_NAMES:
+        pytest.skip("scene not in this build")
+    r = gpu_renderer_factory(name)
+    films, rays = [], []
+    for pool in (0, 4096, 1000):  # library default, a small pool, a ragged one (rounded up to 1024)
+        r.counters(reset=True)
+        r.render(seed=21, spp=3, pool_paths=pool)
+        c = r.counters()
+        films.append(r.film())
+        rays.append((c["rays"], c["path_samples"], c["path_rays"]))
+    assert rays[0] == rays[1] == rays[2]
+    for f in films[1:]:
+        if name.startswith("bd_"):  # connection weights 1/(len_camera * len_lamp) are not dyadic: their sums depend on the order too
+            assert np.allclose(films[0][..., 1], f[..., 1], rtol=2e-4, atol=1e-5)
+        else:
+            assert np.array_equal(films[0][..., 1], f[..., 1])
+        assert np.allclose(films[0][..., 0], f[..., 0], rtol=2e-4, atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_trace_device_wants_aligned_rays(gpu_renderer_factory):
+    import torch
+    from pyrite_b200 import api
+    r = gpu_renderer_factory("cornell")
+    rays = np.zeros(66, api.RAY_DTYPE)
+    rays["o"] = (0.0, 0.0, 5.0)
+    rays["d"] = (0.0, 0.0, -1.0)
+    buf = torch.from_numpy(rays.view(np.uint8).copy()).to("cuda:0")
+    hits = torch.zeros(20 * 66, dtype=torch.uint8, device="cuda:0")
+    assert buf.data_ptr() % 32 == 0
+    r.trace_device(buf.data_ptr(), 64, hits.data_ptr())
+    with pytest.raises(api.PyriteError, match="32-byte aligned"):
+        r.trace_device(buf.data_ptr() + 16, 64, hits.data_ptr())
+
+
 def test_film_expose_and_develop(gpu_renderer_factory, oracle_factory):
     r, o = gpu_renderer_factory("cornell"), oracle_factory("cornell")
     rs = np.random.RandomState(4)
