@@ -65,7 +65,7 @@ struct pyr_ctx {
     DeviceBuffer nodes, prims, tri_shade, tri_frames, planes, marched, materials, components, programs, code, spectra, spectrum_data,
         textures, texels, lamps, tiles, burns, xyz, d65;
     DeviceBuffer film, develop_params, counters, scalars, tile_first;
-    DeviceBuffer paths, pend, bidir, rays[2], hits, shadow_kinds, march_queue[2], march_key, light_vertices, cam_vertices, bin_count, bin_list, live_list;
+    DeviceBuffer paths, pend, bidir, rays[2], hits, shadow_kinds, march_queue[2], march_key, light_vertices, cam_vertices, bin_count, bin_first, bin_fill, bin_keys, bin_list, live_list;
     uint32_t shadow_per_path = 1;
     DeviceBuffer scratch_a, scratch_b;
     uint32_t pool = 0;
@@ -129,8 +129,11 @@ void ensure_pool(pyr_ctx* ctx, uint32_t pool) {
     const size_t ray_cap = (size_t)pool * (1 + ctx->shadow_per_path);
     ctx->paths.ensure((size_t)pool * path_state_bytes());
     ctx->pend.ensure((size_t)pool * MAX_LIGHT_SAMPLES * pending_light_bytes());
-    ctx->bin_count.ensure(NUM_BINS * sizeof(uint32_t));
-    ctx->bin_list.ensure((size_t)NUM_BINS * pool * sizeof(uint32_t));
+    ctx->bin_count.ensure(NUM_KEYS * sizeof(uint32_t));
+    ctx->bin_first.ensure((NUM_KEYS + 1) * sizeof(uint32_t));
+    ctx->bin_fill.ensure(NUM_KEYS * sizeof(uint32_t));
+    ctx->bin_keys.ensure((size_t)pool * sizeof(uint16_t));
+    ctx->bin_list.ensure((size_t)pool * sizeof(uint32_t));
     ctx->live_list.ensure((size_t)pool * sizeof(uint32_t));
     if (bidir) ctx->bidir.ensure((size_t)pool * bidir_state_bytes());
     ctx->rays[0].ensure(ray_cap * sizeof(Ray));
@@ -158,7 +161,7 @@ size_t pool_bytes_per_path(const pyr_ctx* ctx) {
     const RendererRec& R = ctx->view.renderer;
     const bool bidir = R.algorithm == 1;
     const size_t shadow = bidir ? (size_t)bdpt_stage_rays() : std::max<uint32_t>(R.light_samples, 1);
-    size_t b = path_state_bytes() + MAX_LIGHT_SAMPLES * pending_light_bytes() + (NUM_BINS + 1) * sizeof(uint32_t) +
+    size_t b = path_state_bytes() + MAX_LIGHT_SAMPLES * pending_light_bytes() + 2 * sizeof(uint32_t) + sizeof(uint16_t) +
                (1 + shadow) * 2 * sizeof(Ray) + sizeof(Hit) + shadow * sizeof(uint32_t);
     if (ctx->view.n_marched) b += (1 + shadow) * std::min<uint32_t>(ctx->view.n_marched, 4) * 2 * sizeof(uint2) + sizeof(unsigned long long);
     if (bidir) b += bidir_state_bytes() + (size_t)(R.light_bounces + 1) * light_vertex_bytes() + (size_t)std::max<uint32_t>(R.bounces, 1) * cam_vertex_bytes();
@@ -229,7 +232,7 @@ void pyr_shutdown(pyr_ctx* ctx) {
     DeviceBuffer* all[] = {&ctx->nodes, &ctx->prims, &ctx->tri_shade, &ctx->tri_frames, &ctx->planes, &ctx->marched, &ctx->materials,
                            &ctx->components, &ctx->programs, &ctx->code, &ctx->spectra, &ctx->spectrum_data, &ctx->textures, &ctx->texels,
                            &ctx->lamps, &ctx->tiles, &ctx->burns, &ctx->xyz, &ctx->d65, &ctx->film, &ctx->develop_params, &ctx->counters,
-                           &ctx->scalars, &ctx->tile_first, &ctx->paths, &ctx->pend, &ctx->bidir, &ctx->bin_count, &ctx->bin_list, &ctx->live_list, &ctx->rays[0], &ctx->rays[1], &ctx->hits, &ctx->shadow_kinds, &ctx->march_queue[0], &ctx->march_queue[1], &ctx->march_key, &ctx->light_vertices, &ctx->cam_vertices,
+                           &ctx->scalars, &ctx->tile_first, &ctx->paths, &ctx->pend, &ctx->bidir, &ctx->bin_count, &ctx->bin_first, &ctx->bin_fill, &ctx->bin_keys, &ctx->bin_list, &ctx->live_list, &ctx->rays[0], &ctx->rays[1], &ctx->hits, &ctx->shadow_kinds, &ctx->march_queue[0], &ctx->march_queue[1], &ctx->march_key, &ctx->light_vertices, &ctx->cam_vertices,
                            &ctx->scratch_a, &ctx->scratch_b};
     for (DeviceBuffer* b : all) b->release();
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -408,6 +411,11 @@ pyr_status pyr_render(pyr_ctx* ctx, const pyr_render_params* params, pyr_progres
                 CU(cudaEventCreate(&e));
                 ctx->timing_events.push_back(e);
             }
+        const BinBuffers bins{ctx->bin_count.as<uint32_t>(), ctx->bin_first.as<uint32_t>(), ctx->bin_fill.as<uint32_t>(), ctx->bin_keys.as<uint16_t>(),
+                              ctx->bin_list.as<uint32_t>()};
+        CU(cudaMemsetAsync(bins.count, 0, NUM_KEYS * sizeof(uint32_t), s));
+        uint32_t cluster_shift = 0;  // the hit primitive's rank >> shift = one of (at most) BIN_CLUSTERS subtrees of the BVH
+        while ((ctx->view.n_prims >> cluster_shift) > BIN_CLUSTERS) ++cluster_shift;
         CU(cudaEventRecord(ctx->ev0, s));
         int cur = 0;
         uint32_t grid_paths = pool;  // once every sample has been started the live-slot count only falls: the last value read bounds the grids
@@ -448,9 +456,9 @@ pyr_status pyr_render(pyr_ctx* ctx, const pyr_render_params* params, pyr_progres
                 a.live_list = ctx->live_list.as<uint32_t>();
                 a.live_count_in = ctx->live_count(cur);
                 a.live_count_out = ctx->live_count(nxt);
-                a.bin_count = ctx->bin_count.as<uint32_t>();
+                a.bin_first = ctx->bin_first.as<uint32_t>();
                 a.bin_list = ctx->bin_list.as<uint32_t>();
-                launch_bin(a, ctx->bin_count.as<uint32_t>(), ctx->bin_list.as<uint32_t>(), R.algorithm == 1, s);
+                launch_bin(a, bins, cluster_shift, R.algorithm == 1, s);
                 if (R.algorithm == 0) launch_wave_simple(ctx->view, a, s); else launch_wave_bidirectional(ctx->view, a, s);
                 if (timing) CU(cudaEventRecord(ctx->timing_events[3 * b + 1], s));
                 TraceArgs t{};
@@ -473,7 +481,7 @@ pyr_status pyr_render(pyr_ctx* ctx, const pyr_render_params* params, pyr_progres
                 if (timing) CU(cudaEventRecord(ctx->timing_events[3 * b + 2], s));
                 cur = nxt;
                 ++iterations;
-                launches += 3;
+                launches += 5;
             }
             CU(cudaGetLastError());
             CU(cudaMemcpyAsync(&ctx->pinned[0], ctx->count(cur), 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));

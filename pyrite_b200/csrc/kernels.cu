@@ -143,57 +143,135 @@ __global__ void k_pool_reset(PathCore* paths, uint32_t pool, uint32_t* live_list
 // ------------------------------------------------------------------------------------------
 // Shading-state key of a path slot: threads of a warp that share it take the same way through the
 // shade stage (regenerate / miss / surface hit, and the number of unblocked light samples to fold).
-__device__ __forceinline__ uint32_t hit_class(const Hit* hits, uint32_t at) {
-    const uint32_t kind = __ldg(&hits[at].kind);
-    return kind == KIND_MISS ? 1u : (kind == KIND_PLANE ? 2u : (kind == KIND_RAY_MARCHED ? 4u : 3u));
-}
 __device__ __forceinline__ uint32_t unblocked_count(const uint32_t* kinds, uint32_t at, uint32_t n) {
     uint32_t c = 0;
     for (uint32_t j = 0; j < n; ++j) c += __ldg(&kinds[at + j]) == KIND_MISS ? 1u : 0u;
     return c;
 }
-__global__ void __launch_bounds__(256) k_bin(const PathCore* paths, const BidirState* bidir, uint32_t pool, const Hit* hits, const uint32_t* shadow_kinds,
-                                             uint32_t* bin_count, uint32_t* bin_list, const uint32_t* live_list, const uint32_t* live_count) {
-    // block-level counting sort step: keys are counted in shared memory, one global atomic per non-empty bin and block
-    __shared__ uint32_t s_count[NUM_BINS], s_base[NUM_BINS];
-    if (threadIdx.x < NUM_BINS) s_count[threadIdx.x] = 0;
-    __syncthreads();
-    const uint32_t index = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t n_live = *live_count;
+// Shading-state key x spatial cluster of a live slot.  The cluster is the top bits of the hit primitive's rank: ranks are
+// the BVH's leaf pre-order, so equal top bits mean the same subtree, i.e. the same region of the scene - the next path ray
+// and the visibility rays of neighbouring threads then start close together (and, for the light samples, head for the same
+// lamp), which keeps the lanes of a traversal warp on the same nodes, and their surface / material records share cache lines.
+__device__ __forceinline__ uint32_t bin_key(const PathCore* paths, const BidirState* bidir, uint32_t slot, const Hit* hits, const uint32_t* shadow_kinds,
+                                            uint32_t cluster_shift) {
+    const uint4 h = __ldg(reinterpret_cast<const uint4*>(paths + slot) + 2);  // flags, n_pending, ray_base, shadow_base
+    const uint32_t flags = h.x, n_pending = h.y, ray_base = h.z, shadow_base = h.w;
+    if (!(flags & PS_ALIVE)) return 0;
+    const uint32_t phase = bidir ? bidir[slot].phase : PH_CAMERA;
+    uint32_t state, cluster = 0;
+    if (phase == PH_CAMERA || phase == PH_LAMP) {
+        uint32_t hc = 0;
+        if (phase == PH_LAMP || (flags & PS_HAS_MAIN)) {
+            const uint32_t kind = __ldg(&hits[ray_base].kind);
+            hc = kind == KIND_MISS ? 1u : (kind == KIND_PLANE ? 2u : (kind == KIND_RAY_MARCHED ? 4u : 3u));
+            if (hc == 3u) cluster = min(__ldg(&hits[ray_base].rank) >> cluster_shift, BIN_CLUSTERS - 1u);
+            else if (hc == 2u) cluster = __ldg(&hits[ray_base].rank) & (BIN_CLUSTERS - 1u);
+        }
+        if (phase == PH_CAMERA) {
+            const uint32_t lit = (flags & PS_PENDING_FOLD) ? min(unblocked_count(shadow_kinds, shadow_base, n_pending), 4u) : 0u;
+            state = 1u + hc * 5u + lit;   // 1 .. 25
+        } else {
+            state = 26u + hc;             // 27 .. 30
+        }
+    } else {
+        const uint32_t lit = min(unblocked_count(shadow_kinds, shadow_base, n_pending), 14u) >> 1;
+        state = (phase == PH_CONNECT ? 32u : 40u) + lit;  // 32 .. 47
+    }
+    return state * BIN_CLUSTERS + cluster;
+}
+
+// Counting sort of the live slots by key, in three small kernels per iteration:
+//   k_bin_keys     key per live-list entry (2 bytes) + per-block histogram in shared memory, flushed with one atomic per
+//                  non-empty key and block
+//   k_bin_scan     one block: exclusive scan of the key counts -> first[]; clears the counters for the next iteration
+//   k_bin_scatter  per-block histogram again (from the stored keys), one atomic per non-empty key and block reserves the
+//                  block's range in each key's run, then the slot ids are scattered into ONE pool-sized list
+constexpr int BIN_THREADS = 256, BIN_ITEMS = 8;
+__device__ __forceinline__ uint32_t live_slot(const uint32_t* live_list, uint32_t n_live, uint32_t pool, uint32_t index) {
     // while every slot is alive the list is a permutation of [0, pool): walk the slots in order instead (coalesced)
-    const uint32_t slot = index < n_live ? (n_live == pool ? index : live_list[index]) : 0xFFFFFFFFu;
-    uint32_t key = 0xFFFFFFFFu;
-    if (slot < pool) {
-        const uint4 h = __ldg(reinterpret_cast<const uint4*>(paths + slot) + 2);  // flags, n_pending, ray_base, shadow_base
-        const uint32_t flags = h.x, n_pending = h.y, ray_base = h.z, shadow_base = h.w;
-        if (!(flags & PS_ALIVE)) key = 0;
-        else {
-            const uint32_t phase = bidir ? bidir[slot].phase : PH_CAMERA;
-            if (phase == PH_CAMERA) {
-                const uint32_t hc = (flags & PS_HAS_MAIN) ? hit_class(hits, ray_base) : 0u;
-                const uint32_t lit = (flags & PS_PENDING_FOLD) ? min(unblocked_count(shadow_kinds, shadow_base, n_pending), 4u) : 0u;
-                key = 1u + hc * 5u + lit;                                        // 1 .. 25
-            } else if (phase == PH_LAMP) {
-                key = 26u + hit_class(hits, ray_base);                          // 27 .. 30
-            } else {
-                const uint32_t lit = min(unblocked_count(shadow_kinds, shadow_base, n_pending), 14u) >> 1;
-                key = (phase == PH_CONNECT ? 32u : 40u) + lit;                 // 32 .. 47
-            }
+    return n_live == pool ? index : live_list[index];
+}
+__global__ void __launch_bounds__(BIN_THREADS) k_bin_keys(const PathCore* paths, const BidirState* bidir, uint32_t pool, const Hit* hits, const uint32_t* shadow_kinds,
+                                                          uint32_t cluster_shift, uint32_t* bin_count, uint16_t* keys, const uint32_t* live_list,
+                                                          const uint32_t* live_count) {
+    extern __shared__ uint32_t s_bins[];  // [NUM_KEYS]
+    uint32_t* const s_count = s_bins;
+    for (uint32_t k = threadIdx.x; k < NUM_KEYS; k += BIN_THREADS) s_count[k] = 0;
+    __syncthreads();
+    const uint32_t n_live = *live_count;
+    const uint32_t first = blockIdx.x * (BIN_THREADS * BIN_ITEMS);
+#pragma unroll 2
+    for (int i = 0; i < BIN_ITEMS; ++i) {
+        const uint32_t index = first + i * BIN_THREADS + threadIdx.x;
+        if (index < n_live) {
+            const uint32_t key = bin_key(paths, bidir, live_slot(live_list, n_live, pool, index), hits, shadow_kinds, cluster_shift);
+            keys[index] = (uint16_t)key;
+            atomicAdd(&s_count[key], 1u);
         }
     }
-    const bool have = key != 0xFFFFFFFFu;
-    const unsigned peers = __match_any_sync(FULL, key);
-    const int leader = __ffs(peers) - 1;
-    uint32_t base = 0;
-    if ((int)lane_id() == leader && have) base = atomicAdd(&s_count[key], (uint32_t)__popc(peers));
-    base = __shfl_sync(FULL, base, leader) + __popc(peers & ((1u << lane_id()) - 1u));
     __syncthreads();
-    if (threadIdx.x < NUM_BINS) {
-        const uint32_t c = s_count[threadIdx.x];
-        s_base[threadIdx.x] = c ? atomicAdd(&bin_count[threadIdx.x], c) : 0u;
+    for (uint32_t k = threadIdx.x; k < NUM_KEYS; k += BIN_THREADS) {
+        const uint32_t c = s_count[k];
+        if (c) atomicAdd(&bin_count[k], c);
+    }
+}
+__global__ void __launch_bounds__(1024) k_bin_scan(uint32_t* bin_count, uint32_t* bin_first, uint32_t* bin_fill) {
+    constexpr int PER = (NUM_KEYS + 1023) / 1024;
+    __shared__ uint32_t s_warp[32];
+    uint32_t c[PER], sum = 0;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) { c[j] = threadIdx.x * PER + j < NUM_KEYS ? bin_count[threadIdx.x * PER + j] : 0u; sum += c[j]; }
+    uint32_t warp_total;
+    uint32_t before = warp_exclusive_scan(sum, warp_total);
+    if (lane_id() == 31) s_warp[threadIdx.x >> 5] = warp_total;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t t;
+        const uint32_t w = warp_exclusive_scan(s_warp[threadIdx.x], t);
+        s_warp[threadIdx.x] = w;
+        if (threadIdx.x == 31) bin_first[NUM_KEYS] = t;
     }
     __syncthreads();
-    if (have) bin_list[(size_t)key * pool + s_base[key] + base] = slot;
+    before += s_warp[threadIdx.x >> 5];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+        if (threadIdx.x * PER + j >= NUM_KEYS) break;
+        bin_first[threadIdx.x * PER + j] = before;
+        before += c[j];
+        bin_count[threadIdx.x * PER + j] = 0;
+        bin_fill[threadIdx.x * PER + j] = 0;
+    }
+}
+__global__ void __launch_bounds__(BIN_THREADS) k_bin_scatter(uint32_t pool, const uint16_t* keys, const uint32_t* bin_first, uint32_t* bin_fill, uint32_t* bin_list,
+                                                             const uint32_t* live_list, const uint32_t* live_count) {
+    extern __shared__ uint32_t s_bins[];  // [2][NUM_KEYS]
+    uint32_t* const s_count = s_bins;
+    uint32_t* const s_base = s_bins + NUM_KEYS;
+    for (uint32_t k = threadIdx.x; k < NUM_KEYS; k += BIN_THREADS) s_count[k] = 0;
+    __syncthreads();
+    const uint32_t n_live = *live_count;
+    const uint32_t first = blockIdx.x * (BIN_THREADS * BIN_ITEMS);
+    uint32_t key[BIN_ITEMS], local[BIN_ITEMS];
+#pragma unroll
+    for (int i = 0; i < BIN_ITEMS; ++i) {
+        const uint32_t index = first + i * BIN_THREADS + threadIdx.x;
+        key[i] = 0xFFFFFFFFu;
+        if (index < n_live) {
+            key[i] = keys[index];
+            local[i] = atomicAdd(&s_count[key[i]], 1u);
+        }
+    }
+    __syncthreads();
+    for (uint32_t k = threadIdx.x; k < NUM_KEYS; k += BIN_THREADS) {
+        const uint32_t c = s_count[k];
+        if (c) s_base[k] = bin_first[k] + atomicAdd(&bin_fill[k], c);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < BIN_ITEMS; ++i) {
+        const uint32_t index = first + i * BIN_THREADS + threadIdx.x;
+        if (key[i] != 0xFFFFFFFFu) bin_list[s_base[key[i]] + local[i]] = live_slot(live_list, n_live, pool, index);
+    }
 }
 
 // Queue space for one block of a shade kernel: path rays, visibility rays and the live-slot list (the slots still
@@ -233,29 +311,11 @@ __device__ __forceinline__ Reservation block_reserve(const WaveArgs& a, uint32_t
     return r;
 }
 
-// thread -> slot through the bins: the concatenation of all bins is a permutation of the live list
+// thread -> slot through the sorted list (a permutation of the live list); the run of key 0 holds the slots without a live path
 __device__ __forceinline__ uint32_t binned_slot(const WaveArgs& a, uint32_t g, bool& valid, bool& dead) {
-    __shared__ uint32_t s_first[NUM_BINS + 1];
-    static_assert(NUM_BINS == 64, "two bins per lane of the first warp");
-    if (threadIdx.x < 32) {
-        const uint2 c = reinterpret_cast<const uint2*>(a.bin_count)[threadIdx.x];
-        uint32_t total;
-        const uint32_t before = warp_exclusive_scan(c.x + c.y, total);
-        s_first[2 * threadIdx.x] = before;
-        s_first[2 * threadIdx.x + 1] = before + c.x;
-        if (threadIdx.x == 31) s_first[NUM_BINS] = total;
-    }
-    __syncthreads();
-    valid = g < s_first[NUM_BINS];
-    dead = false;
-    if (!valid) return 0;
-    int lo = 0, hi = NUM_BINS;  // s_first[lo] <= g < s_first[hi]
-    while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (s_first[mid] <= g) lo = mid; else hi = mid;
-    }
-    dead = lo == 0;  // bin 0: slots without a live path
-    return a.bin_list[(size_t)lo * a.pool + (g - s_first[lo])];
+    valid = g < __ldg(a.bin_first + NUM_KEYS);
+    dead = g < __ldg(a.bin_first + 1);
+    return valid ? a.bin_list[g] : 0u;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -694,9 +754,14 @@ __global__ void k_camera_sample(const SceneView sc, uint64_t seed, uint32_t tile
 void launch_pool_reset(PathCore* paths, uint32_t pool, uint32_t* live_list, uint32_t* live_count, cudaStream_t s) {
     if (pool) k_pool_reset<<<(pool + 255) / 256, 256, 0, s>>>(paths, pool, live_list, live_count);
 }
-void launch_bin(const WaveArgs& a, uint32_t* bin_count, uint32_t* bin_list, int bidirectional, cudaStream_t s) {
-    cudaMemsetAsync(bin_count, 0, NUM_BINS * sizeof(uint32_t), s);
-    k_bin<<<(a.grid_paths + 255) / 256, 256, 0, s>>>(a.paths, bidirectional ? a.bidir : nullptr, a.pool, a.hits_in, a.shadow_kinds_in, bin_count, bin_list, a.live_list, a.live_count_in);
+void launch_bin(const WaveArgs& a, const BinBuffers& b, uint32_t cluster_shift, int bidirectional, cudaStream_t s) {
+    const unsigned blocks = (a.grid_paths + BIN_THREADS * BIN_ITEMS - 1) / (BIN_THREADS * BIN_ITEMS);
+    cudaFuncSetAttribute(k_bin_keys, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NUM_KEYS * sizeof(uint32_t)));
+    k_bin_keys<<<blocks, BIN_THREADS, NUM_KEYS * sizeof(uint32_t), s>>>(a.paths, bidirectional ? a.bidir : nullptr, a.pool, a.hits_in, a.shadow_kinds_in, cluster_shift, b.count, b.keys,
+                                              a.live_list, a.live_count_in);
+    k_bin_scan<<<1, 1024, 0, s>>>(b.count, b.first, b.fill);
+    cudaFuncSetAttribute(k_bin_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * NUM_KEYS * sizeof(uint32_t)));
+    k_bin_scatter<<<blocks, BIN_THREADS, 2 * NUM_KEYS * sizeof(uint32_t), s>>>(a.pool, b.keys, b.first, b.fill, b.list, a.live_list, a.live_count_in);
 }
 void launch_wave_simple(const SceneView& sc, const WaveArgs& a, cudaStream_t s) {
     cudaFuncSetAttribute(k_wave_simple, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wave_smem(sc));

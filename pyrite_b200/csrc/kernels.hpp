@@ -43,8 +43,9 @@ struct WaveArgs {
     CamVertex* cam_vertices;      // bidirectional: pool * cam_stride stored camera-subpath vertices
     uint32_t light_stride, cam_stride;
     uint32_t ray_capacity;
-    // slots grouped by shading state (k_bin): bucket b holds bin_count[b] slot ids at bin_list[b * pool ..]
-    const uint32_t* bin_count;
+    // live slots sorted by (shading state, spatial cluster) (k_bin_*): bin_first[k] = start of key k's run in bin_list,
+    // bin_first[NUM_KEYS] = number of entries
+    const uint32_t* bin_first;
     const uint32_t* bin_list;
     // slots that can still do something: written by the shade kernel (slots alive after it), read by the next k_bin;
     // once every sample has started the list shrinks with the paths still in flight
@@ -52,8 +53,21 @@ struct WaveArgs {
     const uint32_t* live_count_in;
     uint32_t* live_count_out;
 };
-constexpr int NUM_BINS = 64;
-void launch_bin(const WaveArgs& a, uint32_t* bin_count, uint32_t* bin_list, int bidirectional, cudaStream_t s);
+#ifndef PYR_BIN_CLUSTERS
+#define PYR_BIN_CLUSTERS 16
+#endif
+#ifndef PYR_BIN_STATES
+#define PYR_BIN_STATES 48
+#endif
+constexpr uint32_t BIN_STATES = PYR_BIN_STATES, BIN_CLUSTERS = PYR_BIN_CLUSTERS, NUM_KEYS = BIN_STATES * BIN_CLUSTERS;
+struct BinBuffers {
+    uint32_t* count;  // [NUM_KEYS], zero between iterations (k_bin_scan clears it)
+    uint32_t* first;  // [NUM_KEYS + 1]
+    uint32_t* fill;   // [NUM_KEYS]
+    uint16_t* keys;   // [pool], by live-list position
+    uint32_t* list;   // [pool]
+};
+void launch_bin(const WaveArgs& a, const BinBuffers& b, uint32_t cluster_shift, int bidirectional, cudaStream_t s);
 
 struct TraceArgs {
     const Ray* rays;
