@@ -424,8 +424,6 @@ pyr_status pyr_render(pyr_ctx* ctx, const pyr_render_params* params, pyr_progres
         for (;;) {
             for (int b = 0; b < BATCH; ++b) {
                 const int nxt = cur ^ 1;
-                CU(cudaMemsetAsync(ctx->count(nxt), 0, 2 * sizeof(uint32_t), s));
-                CU(cudaMemsetAsync(ctx->live_count(nxt), 0, sizeof(uint32_t), s));
                 WaveArgs a{};
                 a.paths = ctx->paths.as<PathCore>();
                 a.pend = ctx->pend.as<PendingLight>();

@@ -1,13 +1,16 @@
 // sm_100a kernels of the wavefront render path.  Compiled with -fmad=false: the reference never
 // contracts a*b+c and hit/primitive IDs must come out bit-exact.
 //
+//   k_bin_*         a counting sort of the live path slots by (shading state, BVH-subtree cluster of the hit)
 //   k_wave_simple   stage 1 + 4 + 5 + 6: regenerate finished path slots (camera ray, wavelengths),
-//                   shade the closest hits of the previous trace pass (surface data, expression VM,
-//                   BSDF scatter, next-event estimation, the `contribute` fold), expose finished
-//                   samples on the film, and append the next rays to the ray queue with a
-//                   warp-level prefix sum + one atomic per warp
-//   k_trace         stage 2 + 3: World::intersect for every queued ray (planes, BVH walk, triangle /
-//                   sphere tests, sphere tracing); persistent warps pull 32-ray packets
+//   k_wave_bidirectional   shade the closest hits of the previous trace pass (surface data, expression VM,
+//                   BSDF scatter, next-event estimation, the `contribute` fold; lamp subpaths, connections and
+//                   light tracing for BDPT), expose finished samples on the film, and append the next rays to
+//                   the ray queue with warp-level prefix sums + one atomic per block
+//   k_trace         stage 2: World::intersect for every queued ray (planes, 4-wide BVH walk, triangle /
+//                   sphere tests); persistent warps hand ray indices to lanes as they finish
+//   k_march         stage 3: sphere tracing of the ray-marched candidates the walk found, flattened to
+//                   distance-estimator iterations; k_march_apply merges the winners into the hit records
 //   k_develop       stage 6 tail: spectral film -> CIE XYZ -> sRGB
 #include <cuda_runtime.h>
 
@@ -215,7 +218,9 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_keys(const PathCore* paths,
         if (c) atomicAdd(&bin_count[k], c);
     }
 }
-__global__ void __launch_bounds__(1024) k_bin_scan(uint32_t* bin_count, uint32_t* bin_first, uint32_t* bin_fill) {
+__global__ void __launch_bounds__(1024) k_bin_scan(uint32_t* bin_count, uint32_t* bin_first, uint32_t* bin_fill, uint32_t* queue_counts, uint32_t* live_count_out) {
+    // also clears what the shade pass of this iteration counts into: its ray-queue counters and its live-slot count
+    if (threadIdx.x == 0) { queue_counts[0] = 0; queue_counts[1] = 0; *live_count_out = 0; }
     constexpr int PER = (NUM_KEYS + 1023) / 1024;
     __shared__ uint32_t s_warp[32];
     uint32_t c[PER], sum = 0;
@@ -759,7 +764,7 @@ void launch_bin(const WaveArgs& a, const BinBuffers& b, uint32_t cluster_shift, 
     cudaFuncSetAttribute(k_bin_keys, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NUM_KEYS * sizeof(uint32_t)));
     k_bin_keys<<<blocks, BIN_THREADS, NUM_KEYS * sizeof(uint32_t), s>>>(a.paths, bidirectional ? a.bidir : nullptr, a.pool, a.hits_in, a.shadow_kinds_in, cluster_shift, b.count, b.keys,
                                               a.live_list, a.live_count_in);
-    k_bin_scan<<<1, 1024, 0, s>>>(b.count, b.first, b.fill);
+    k_bin_scan<<<1, 1024, 0, s>>>(b.count, b.first, b.fill, a.count_out, a.live_count_out);
     cudaFuncSetAttribute(k_bin_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * NUM_KEYS * sizeof(uint32_t)));
     k_bin_scatter<<<blocks, BIN_THREADS, 2 * NUM_KEYS * sizeof(uint32_t), s>>>(a.pool, b.keys, b.first, b.fill, b.list, a.live_list, a.live_count_in);
 }
