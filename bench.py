@@ -266,7 +266,7 @@ def run_product(args):
                  "avg_launch_ms": 1e3 * trace_s / trace_n, "share_of_step": trace_s / max(c["trace_seconds"] + c["shade_seconds"], 1e-12),
                  "mrays_per_s": c["rays"] / max(trace_s, 1e-12) / 1e6,
                  "note": "algorithmic node/primitive bytes; the ncu capture shows that L2/L1 serve most of them (traffic = DRAM bytes per launch)"}
-        # the shade stage (k_bin + k_wave_simple): per path iteration the path record (64 B header + ceil(3 S / 8) 32-byte chunks of
+        # the shade stage (k_bin_keys / _scan / _scatter + k_wave_simple): per path iteration the path record (64 B header + ceil(3 S / 8) 32-byte chunks of
         # wavelengths / brightness / reflectance) is read and written, the path ray and its hit are read, the next ray is written; per
         # visibility ray 4 B result in, 32 B ray + 32 B pending light out and the light back in; per sample S film atomics of 8 B
         S = info.spectrum_samples
@@ -276,7 +276,7 @@ def run_product(args):
         shade_bytes = path_iterations * 2 * core_bytes + c["path_rays"] * (32 + 32 + 32) + shadow * (4 + 32 + 64) + c["path_samples"] * S * 8
         shade_s, shade_n = c["shade_seconds"], max(c["shade_launches"], 1)
         shade_achieved = shade_bytes / max(shade_s, 1e-12) / 1e9
-        shade = {"bound": "hbm", "kernel": "k_bin + k_wave_simple", "achieved": shade_achieved, "peak": peak, "unit": "GB/s", "frac": shade_achieved / peak,
+        shade = {"bound": "hbm", "kernel": "k_bin_* + k_wave_simple", "achieved": shade_achieved, "peak": peak, "unit": "GB/s", "frac": shade_achieved / peak,
                  "traffic": traffic.get("k_wave_simple"), "peak_source": peak_src, "bytes_per_path_iteration": shade_bytes / max(path_iterations, 1),
                  "path_iterations_per_launch": path_iterations / shade_n, "avg_launch_ms": 1e3 * shade_s / shade_n,
                  "share_of_step": shade_s / max(c["trace_seconds"] + c["shade_seconds"], 1e-12)}
