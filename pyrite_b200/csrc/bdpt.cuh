@@ -29,7 +29,7 @@ enum : uint32_t { VT_DIFFUSE = 0, VT_SPECULAR = 1, VT_EMISSION = 2 };
 // One stored vertex of the lamp subpath (tracer.rs:157-167 `Bounce`; lamp paths carry no direct light), plus
 // its colour program evaluated at the path's wavelengths: connect_paths and light tracing re-fold the tail of
 // the lamp path for every connection (bidirectional.rs:373-389, 276-292), always with the same colours. 144 B.
-struct alignas(16) LightVertexHead {   // 80 B: what a thread keeps in registers
+struct alignas(32) LightVertexHead {   // 96 B: what a thread keeps in registers; the first 32 B are what the staging loops read
     float position[3];
     uint32_t type;
     float normal[3];
@@ -39,11 +39,20 @@ struct alignas(16) LightVertexHead {   // 80 B: what a thread keeps in registers
     float out[3];         // BounceType::Diffuse(_, out)
     uint32_t dispersed;
     float tex[2];
-    uint32_t pad[2];
+    uint32_t pad[6];
 };
-struct alignas(16) LightVertex : LightVertexHead {
+struct alignas(32) LightVertex : LightVertexHead {
     float color[MAX_SPECTRUM_SAMPLES];  // color(wl[k]), filled by finish_lamp_path; read in place (never copied to a thread)
 };
+// position, type and normal of a lamp vertex: one 32-byte load
+struct VertexGeometry { v3 position; uint32_t type; v3 normal; };
+PYR_HD VertexGeometry vertex_geometry(const Vec8& q) {
+    VertexGeometry g;
+    g.position = mk3(q.v[0], q.v[1], q.v[2]);
+    g.type = f_bits(q.v[3]);
+    g.normal = mk3(q.v[4], q.v[5], q.v[6]);
+    return g;
+}
 // A diffuse camera-subpath vertex with the sample state right after its `contribute`. 160 B.
 struct alignas(32) CamVertexHead {
     float position[3];
@@ -75,11 +84,20 @@ PYR_HD float vertex_brdf(const LightVertexHead& v) {  // BounceType::brdf: lambe
 
 // `contribute` (renderer/algorithm.rs:14-100) of a lamp-subpath bounce on a detached sample state
 PYR_HD void contribute_vertex(const LightVertexHead& v, const float* color, uint32_t n, SpecArray bright, SpecArray refl) {
+    // the colours come in with two 32-byte loads issued together, not one dependent 4-byte load per wavelength
+    static_assert(MAX_SPECTRUM_SAMPLES == 16, "two chunks");
+    Vec8 c[2];
+    c[0] = ld256(color);
+    if (n > 8) c[1] = ld256(color + 8);
     if (v.type == VT_EMISSION) {
-        for (uint32_t k = 0; k < n; ++k) bright[k] += color[k] * v.probability * refl[k];
+#pragma unroll
+        for (uint32_t k = 0; k < MAX_SPECTRUM_SAMPLES; ++k)
+            if (k < n) bright[k] += c[k >> 3].v[k & 7] * v.probability * refl[k];
     } else {
         const float brdf = vertex_brdf(v);
-        for (uint32_t k = 0; k < n; ++k) { refl[k] *= color[k] * v.probability; refl[k] *= brdf; }
+#pragma unroll
+        for (uint32_t k = 0; k < MAX_SPECTRUM_SAMPLES; ++k)
+            if (k < n) { refl[k] *= c[k >> 3].v[k & 7] * v.probability; refl[k] *= brdf; }
     }
 }
 // the fold over lamp_path[first..] shared by connect_paths (:373-389) and light tracing (:276-292)
@@ -169,15 +187,18 @@ PYR_HD uint32_t stage_connections(const PathState& ps, const BidirCtx& cx, uint3
     const CamVertex& c = cx.cv[ps.bd->conn_cam];
     const v3 from = ld3(c.position), cn = ld3(c.normal);
     uint32_t n = 0, i = from_light;
-    for (; i < ps.bd->n_light && n < (uint32_t)BDPT_STAGE; ++i) {
-        const LightVertex& v = cx.lv[i];
+    const uint32_t n_light = ps.bd->n_light;
+    Vec8 fetched = ld256(cx.lv + (i < n_light ? i : 0u));
+    for (; i < n_light && n < (uint32_t)BDPT_STAGE; ++i) {
+        const VertexGeometry v = vertex_geometry(fetched);
+        if (i + 1 < n_light) fetched = ld256(cx.lv + i + 1);  // the next vertex is on its way while this one is examined
         if (v.type == VT_SPECULAR) continue;
-        v3 direction = ld3(v.position) - from;
+        v3 direction = v.position - from;
         float sq_distance = length2(direction);
         float distance = sqrtf(sq_distance);
         v3 dir = direction / distance;
         if (dot(cn, dir) <= 0.0f) continue;
-        if (dot(ld3(v.normal), -dir) <= 0.0f) continue;
+        if (dot(v.normal, -dir) <= 0.0f) continue;
         if (rays) rays[n] = make_ray(from, dir, 2, distance - DIST_EPSILON);  // blocked <=> a hit closer than distance - eps
         if (lamp_index) lamp_index[n] = i;
         ++n;
@@ -204,10 +225,13 @@ PYR_HD uint32_t stage_visibility(const SceneView& sc, const PathState& ps, const
                                  uint32_t* lamp_index, v3* lens, uint32_t& next) {
     uint32_t n = 0, i = from_light;
     if (!sc.camera.inv_ok) { next = ps.bd->n_light; return 0; }
-    for (; i < ps.bd->n_light && n < (uint32_t)BDPT_STAGE; ++i) {
-        const LightVertex& v = cx.lv[i];
+    const uint32_t n_light = ps.bd->n_light;
+    Vec8 fetched = ld256(cx.lv + (i < n_light ? i : 0u));
+    for (; i < n_light && n < (uint32_t)BDPT_STAGE; ++i) {
+        const VertexGeometry v = vertex_geometry(fetched);
+        if (i + 1 < n_light) fetched = ld256(cx.lv + i + 1);
         if (v.type != VT_DIFFUSE) continue;
-        const v3 target = ld3(v.position);
+        const v3 target = v.position;
         v3 local_target = transform_point(sc.camera.inv, target);
         if (local_target.z >= 0.0f) continue;
         const v3 origin = lens_origin(sc.camera, rng);
