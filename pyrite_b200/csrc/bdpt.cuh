@@ -82,6 +82,15 @@ PYR_HD float vertex_brdf(const LightVertexHead& v) {  // BounceType::brdf: lambe
     return v.type == VT_DIFFUSE ? 2.0f * fabsf(dot(ld3(v.out), ld3(v.normal))) : 1.0f;
 }
 
+PYR_HD LightVertexHead load_head(const LightVertex* p) {
+    static_assert(sizeof(LightVertexHead) == 96, "three chunks");
+    const Vec8 a = ld256(p), b = ld256(reinterpret_cast<const Vec8*>(p) + 1), c = ld256(reinterpret_cast<const Vec8*>(p) + 2);
+    LightVertexHead h;
+    __builtin_memcpy(&h, &a, 32);
+    __builtin_memcpy(reinterpret_cast<char*>(&h) + 32, &b, 32);
+    __builtin_memcpy(reinterpret_cast<char*>(&h) + 64, &c, 32);
+    return h;
+}
 // `contribute` (renderer/algorithm.rs:14-100) of a lamp-subpath bounce on a detached sample state
 PYR_HD void contribute_vertex(const LightVertexHead& v, const float* color, uint32_t n, SpecArray bright, SpecArray refl) {
     // the colours come in with two 32-byte loads issued together, not one dependent 4-byte load per wavelength
@@ -105,7 +114,7 @@ PYR_HD void fold_lamp_tail(const SceneView& sc, const LightVertex* lv, uint32_t 
                            SpecArray bright, SpecArray refl, float brdf_in) {
     const uint32_t S = sc.renderer.spectrum_samples;
     for (uint32_t k = first; k < n_light; ++k) {
-        const LightVertexHead v = lv[k];
+        const LightVertexHead v = load_head(lv + k);
         use_additional = !v.dispersed && use_additional;
         const uint32_t n = use_additional ? S : 1u;
         contribute_vertex(v, lv[k].color, n, bright, refl);
@@ -130,7 +139,14 @@ struct CameraHooks {
         if (!ps.bd->cam_store_pending) return;
         CamVertex& c = cx.cv[ps.bd->n_cam_stored - 1];
         c.use_additional = (ps.flags & PS_USE_ADDITIONAL) ? 1u : 0u;
-        for (uint32_t k = 0; k < n_spec; ++k) { c.bright[k] = ps.bright[k]; c.refl[k] = ps.refl[k]; }
+        Vec8 b[2], r[2];
+#pragma unroll
+        for (uint32_t k = 0; k < MAX_SPECTRUM_SAMPLES; ++k) {
+            b[k >> 3].v[k & 7] = k < n_spec ? ps.bright[k] : 0.0f;
+            r[k >> 3].v[k & 7] = k < n_spec ? ps.refl[k] : 0.0f;
+        }
+        st256(c.bright, b[0]); st256(c.refl, r[0]);
+        if (n_spec > 8) { st256(c.bright + 8, b[1]); st256(c.refl + 8, r[1]); }
         ps.bd->cam_store_pending = 0;
     }
     PYR_HD void pushed_emission(PathState& ps) { ps.bd->n_cam += 1; }
@@ -450,7 +466,7 @@ PYR_HD void shade_bidirectional(const SceneView& sc, PathState& ps, const BidirC
         const float weight = 1.0f / (float)(ps.bd->n_cam * ps.bd->n_light);  // bidirectional.rs:217-218
         for (uint32_t j = 0; j < n; ++j) {
             if (shadow_kinds[j] != KIND_MISS) continue;
-            const LightVertexHead v = cx.lv[lamp_index[j]];
+            const LightVertexHead v = load_head(cx.lv + lamp_index[j]);
             v3 direction = ld3(v.position) - from;
             float sq_distance = length2(direction);
             float distance = sqrtf(sq_distance);
@@ -460,7 +476,15 @@ PYR_HD void shade_bidirectional(const SceneView& sc, PathState& ps, const BidirC
             float brdf_out = (2.0f * fabsf(dot(dir, cn))) / c.brdf;
             float scale = cos_in * cos_out * brdf_out / (2.0f * PYR_PI * sq_distance);
             float brdf_in = vertex_brdf(v) / vertex_brdf(v);
-            for (uint32_t k = 0; k < S; ++k) { bright[k] = stored.bright[k]; refl[k] = stored.refl[k] * scale; }
+            {
+                static_assert(MAX_SPECTRUM_SAMPLES == 16, "two chunks per array");
+                Vec8 b[2], r[2];
+                b[0] = ld256(stored.bright); r[0] = ld256(stored.refl);
+                if (S > 8) { b[1] = ld256(stored.bright + 8); r[1] = ld256(stored.refl + 8); }
+#pragma unroll
+                for (uint32_t k = 0; k < MAX_SPECTRUM_SAMPLES; ++k)
+                    if (k < S) { bright[k] = b[k >> 3].v[k & 7]; refl[k] = r[k >> 3].v[k & 7] * scale; }
+            }
             bool use_additional = c.use_additional != 0;
             fold_lamp_tail(sc, cx.lv, lamp_index[j], ps.bd->n_light, use_additional, bright, refl, brdf_in);
             film_expose(sc.film, ps.pos[0], ps.pos[1], bright[0], ps.wl[0], weight, add);
@@ -485,7 +509,7 @@ PYR_HD void shade_bidirectional(const SceneView& sc, PathState& ps, const BidirC
         const float weight = 1.0f / (float)ps.bd->n_light;
         for (uint32_t j = 0; j < n; ++j) {
             if (shadow_kinds[j] != KIND_MISS) continue;
-            const LightVertexHead v = cx.lv[lamp_index[j]];
+            const LightVertexHead v = load_head(cx.lv + lamp_index[j]);
             const v3 target = ld3(v.position);
             v3 local_target = transform_point(sc.camera.inv, target);
             const v3 origin = lens[j];
