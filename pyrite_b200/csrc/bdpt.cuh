@@ -91,6 +91,13 @@ PYR_HD LightVertexHead load_head(const LightVertex* p) {
     __builtin_memcpy(reinterpret_cast<char*>(&h) + 64, &c, 32);
     return h;
 }
+PYR_HD void store_head(LightVertex* p, const LightVertexHead& h) {
+    Vec8 a, b, c;
+    __builtin_memcpy(&a, &h, 32);
+    __builtin_memcpy(&b, reinterpret_cast<const char*>(&h) + 32, 32);
+    __builtin_memcpy(&c, reinterpret_cast<const char*>(&h) + 64, 32);
+    st256(p, a); st256(reinterpret_cast<Vec8*>(p) + 1, b); st256(reinterpret_cast<Vec8*>(p) + 2, c);
+}
 // `contribute` (renderer/algorithm.rs:14-100) of a lamp-subpath bounce on a detached sample state
 PYR_HD void contribute_vertex(const LightVertexHead& v, const float* color, uint32_t n, SpecArray bright, SpecArray refl) {
     // the colours come in with two 32-byte loads issued together, not one dependent 4-byte load per wavelength
@@ -183,17 +190,20 @@ PYR_HD void finish_lamp_path(const SceneView& sc, PathState& ps, LightVertex* lv
             if (from.type == VT_DIFFUSE) { from.out[0] = from.incident[0]; from.out[1] = from.incident[1]; from.out[2] = from.incident[2]; }
         }
     if (n > 1 && lv[n - 1].type == VT_EMISSION) n -= 1;
-    for (uint32_t i = 0; i < n / 2; ++i) { LightVertex t = lv[i]; lv[i] = lv[n - 1 - i]; lv[n - 1 - i] = t; }
+    for (uint32_t i = 0; i < n / 2; ++i) {  // the colours are not evaluated yet: only the heads move
+        const LightVertexHead a = load_head(lv + i), b = load_head(lv + n - 1 - i);
+        store_head(lv + i, b);
+        store_head(lv + n - 1 - i, a);
+    }
     ps.bd->n_light = n;
     // evaluate every vertex' colour once at the path's wavelengths (with the incident vectors as fixed up above)
     PYR_REGFILE(R);
     for (uint32_t i = 0; i < n; ++i) {
-        LightVertex& v = lv[i];
+        const LightVertexHead v = load_head(lv + i);
         VmInputs in;
         in.wavelength = 0.0f; in.incident = ld3(v.incident); in.normal = ld3(v.normal); in.tex[0] = v.tex[0]; in.tex[1] = v.tex[1];
-        float c[MAX_SPECTRUM_SAMPLES];
-        eval_spectral(sc, v.color_program, in, ps.wl, sc.renderer.spectrum_samples, c, R);
-        for (uint32_t k = 0; k < sc.renderer.spectrum_samples; ++k) v.color[k] = c[k];
+        float* const color = lv[i].color;
+        eval_spectral_each(sc, v.color_program, in, ps.wl, sc.renderer.spectrum_samples, R, [&](uint32_t k, float c) { color[k] = c; });
     }
 }
 
@@ -353,15 +363,16 @@ PYR_HD void generate_bidirectional(const SceneView& sc, uint64_t seed, uint32_t 
         return;
     }
     origin = origin + normal * DIST_EPSILON;
-    LightVertex first;
+    LightVertexHead first;
     st3(first.position, origin); first.type = VT_EMISSION;
     st3(first.normal, normal); first.color_program = color;
     first.incident[0] = first.incident[1] = first.incident[2] = 0.0f;
     first.probability = weight / (lamp_probability * material_probability);
     first.out[0] = first.out[1] = first.out[2] = 0.0f;
     first.dispersed = dispersed ? 1u : 0u;
-    first.tex[0] = tex[0]; first.tex[1] = tex[1]; first.pad[0] = first.pad[1] = 0;
-    cx.lv[0] = first;
+    first.tex[0] = tex[0]; first.tex[1] = tex[1];
+    for (uint32_t& w : first.pad) w = 0;
+    store_head(cx.lv, first);
     ps.bd->n_light = 1;
     if (sc.renderer.light_bounces == 0) {
         finish_lamp_path(sc, ps, cx.lv);
@@ -381,8 +392,8 @@ PYR_HD bool lamp_step(const SceneView& sc, PathState& ps, const BidirCtx& cx, co
     PYR_REGFILE(R);
     const v3 o = ld3(ray.o), d = ld3(ray.d);
     const float wavelength = ps.wl[0];
-    LightVertex nv;
-    nv.pad[0] = nv.pad[1] = 0;
+    LightVertexHead nv;
+    for (uint32_t& w : nv.pad) w = 0;
     st3(nv.incident, d);
     nv.out[0] = nv.out[1] = nv.out[2] = 0.0f;
     if (h.kind == KIND_MISS) {
@@ -390,7 +401,7 @@ PYR_HD bool lamp_step(const SceneView& sc, PathState& ps, const BidirCtx& cx, co
         nv.color_program = directional_color(sc, d, sc.sky_program);
         st3(nv.position, d * PYR_INF); st3(nv.normal, -d);
         nv.tex[0] = nv.tex[1] = 0.0f; nv.probability = 1.0f;
-        cx.lv[ps.bd->n_light++] = nv;
+        store_head(cx.lv + ps.bd->n_light++, nv);
         return false;
     }
     Surface s;
@@ -408,7 +419,7 @@ PYR_HD bool lamp_step(const SceneView& sc, PathState& ps, const BidirCtx& cx, co
     nv.color_program = comp.color_program;
     if (sct.emitted) {
         nv.type = VT_EMISSION; nv.dispersed = normal_dispersed ? 1u : 0u; nv.probability = component_prob;
-        cx.lv[ps.bd->n_light++] = nv;
+        store_head(cx.lv + ps.bd->n_light++, nv);
         return false;
     }
     if (ps.light_events < 2 && sct.has_brdf) {
@@ -419,7 +430,7 @@ PYR_HD bool lamp_step(const SceneView& sc, PathState& ps, const BidirCtx& cx, co
     st3(nv.out, sct.out);
     nv.dispersed = (sct.dispersed || normal_dispersed) ? 1u : 0u;
     nv.probability = sct.probability * component_prob;
-    cx.lv[ps.bd->n_light++] = nv;
+    store_head(cx.lv + ps.bd->n_light++, nv);
     ps.bd->lamp_bounces += 1;
     if (ps.bd->lamp_bounces < sc.renderer.light_bounces) {
         out.has_main = 1;

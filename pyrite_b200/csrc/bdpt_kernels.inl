@@ -22,7 +22,14 @@ __global__ void __launch_bounds__(WAVE_THREADS) k_wave_bidirectional(const __gri
     if (!idle) {
         load_core(sc, ps, a.paths + s);
         ps.pend = a.pend + (size_t)s * MAX_LIGHT_SAMPLES;
-        bd = a.bidir[s];
+        {
+            static_assert(sizeof(BidirState) == 96, "three chunks");
+            const Vec8* src = reinterpret_cast<const Vec8*>(a.bidir + s);
+            const Vec8 q0 = ld256_stream(src), q1 = ld256_stream(src + 1), q2 = ld256_stream(src + 2);
+            __builtin_memcpy(&bd, &q0, 32);
+            __builtin_memcpy(reinterpret_cast<char*>(&bd) + 32, &q1, 32);
+            __builtin_memcpy(reinterpret_cast<char*>(&bd) + 64, &q2, 32);
+        }
         flags_in = ps.flags;
         BidirCtx cx;
         cx.lv = a.light_vertices + (size_t)s * a.light_stride;
@@ -54,7 +61,13 @@ __global__ void __launch_bounds__(WAVE_THREADS) k_wave_bidirectional(const __gri
         ps.shadow_base = at.shadow_at;
         for (uint32_t j = 0; j < n_shadow; ++j) store_ray(a.rays_out + a.shadow_offset + at.shadow_at + j, out.shadow[j]);
     }
-    if (valid && (alive || (flags_in & PS_ALIVE))) { store_core(sc, a.paths + slot, ps); a.bidir[slot] = bd; }
+    if (valid && (alive || (flags_in & PS_ALIVE))) {
+        store_core(sc, a.paths + slot, ps);
+        Vec8 q[3];
+        __builtin_memcpy(q, &bd, 96);
+        Vec8* dst = reinterpret_cast<Vec8*>(a.bidir + slot);
+        st256_stream(dst, q[0]); st256_stream(dst + 1, q[1]); st256_stream(dst + 2, q[2]);
+    }
     if (valid && alive) a.live_list[at.live_at] = slot;
     if (pc.de_evals) { atomicAdd(&a.counters->de_evals, (unsigned long long)pc.de_evals); atomicAdd(&a.counters->de_iterations, (unsigned long long)pc.de_iters); }
 }

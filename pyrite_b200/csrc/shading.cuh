@@ -36,11 +36,12 @@ struct alignas(32) PathCore : PathHeader {
     float spectral[3 * MAX_SPECTRUM_SAMPLES];
 };
 // bidirectional integrator only (bdpt.cuh)
-struct alignas(16) BidirState {
+struct alignas(32) BidirState {   // 80 B of state, padded to three 32-byte chunks
     uint32_t phase, n_light, n_cam, n_cam_stored, lamp_bounces, conn_cam, conn_light, conn_next;
     float cam_o[3], cam_d[3];
     uint32_t cam_store_pending, pad2;
     Rng rng_saved;
+    uint32_t pad3[4];
 };
 // A per-wavelength array of the thread.  In the kernels it lives in dynamic shared memory, [wavelength][thread]
 // (dynamically indexed thread-local arrays would otherwise go through local memory); on the host it is plain memory.
