@@ -160,7 +160,11 @@ __device__ __forceinline__ uint32_t bin_key(const PathCore* paths, const BidirSt
     const uint4 h = __ldg(reinterpret_cast<const uint4*>(paths + slot) + 2);  // flags, n_pending, ray_base, shadow_base
     const uint32_t flags = h.x, n_pending = h.y, ray_base = h.z, shadow_base = h.w;
     if (!(flags & PS_ALIVE)) return 0;
-    const uint32_t phase = bidir ? bidir[slot].phase : PH_CAMERA;
+    uint32_t phase = PH_CAMERA, n_light = 0;
+    if (bidir) {
+        const uint2 b = __ldg(reinterpret_cast<const uint2*>(bidir + slot));  // phase, n_light
+        phase = b.x; n_light = b.y;
+    }
     uint32_t state, cluster = 0;
     if (phase == PH_CAMERA || phase == PH_LAMP) {
         uint32_t hc = 0;
@@ -179,6 +183,7 @@ __device__ __forceinline__ uint32_t bin_key(const PathCore* paths, const BidirSt
     } else {
         const uint32_t lit = min(unblocked_count(shadow_kinds, shadow_base, n_pending), 14u) >> 1;
         state = (phase == PH_CONNECT ? 32u : 40u) + lit;  // 32 .. 47
+        cluster = min(n_light, BIN_CLUSTERS - 1u);         // connection / splat loops run over the lamp path: equal lengths together
     }
     return state * BIN_CLUSTERS + cluster;
 }
