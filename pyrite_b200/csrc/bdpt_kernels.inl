@@ -5,6 +5,8 @@ __global__ void __launch_bounds__(WAVE_THREADS) k_wave_bidirectional(const __gri
     const uint32_t g_thread = blockIdx.x * blockDim.x + threadIdx.x;
     if (g_thread == 0) *a.trace_cursor = 0;
     bool valid, dead;
+    // blocks beyond the sorted list have nothing to do (the grid is sized by a bound of the live count that can be stale)
+    if (blockIdx.x * blockDim.x >= __ldg(a.bin_first + NUM_KEYS)) return;
     const uint32_t slot = binned_slot(a, g_thread, valid, dead);
     const bool idle = __all_sync(FULL, !valid || dead) && *a.next_sample >= a.total_samples;
     const uint32_t s = valid ? slot : 0;
