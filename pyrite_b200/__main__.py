@@ -18,6 +18,8 @@ def main(argv=None) -> int:
     ap.add_argument("--spp", type=int, default=0, help="override renderer.pixel_samples")
     ap.add_argument("--out", default=None, help="output image (default: render.png next to the project file, main.rs:180-184)")
     ap.add_argument("--no-preview", action="store_true")
+    ap.add_argument("--preview-interval", type=float, default=20.0, help="seconds between preview images (main.rs:261: 20)")
+    ap.add_argument("--pool", type=int, default=0, help="paths in flight (0 = library default); progress is reported between wavefront batches")
     args = ap.parse_args(argv)
 
     from PIL import Image
@@ -41,20 +43,21 @@ def main(argv=None) -> int:
     loaded = time.time()
     print(f"Project loading: {loaded - total_start:.3f} s  ({info.n_objects} objects, {info.n_bvh_nodes} BVH nodes, "
           f"{info.width}x{info.height}, {'bidirectional' if info.algorithm else 'simple'} x {args.spp or info.pixel_samples} spp)")
-    state = {"last": time.time(), "pct": -1}
+    state = {"last": time.time(), "pct": -1, "previews": 0}
 
     def progress(pct, message):
         if pct != state["pct"]:
             state["pct"] = pct
             print(f"\r{message}: {pct:3d}%", end="", flush=True)
-        if not args.no_preview and time.time() - state["last"] >= 20.0 and pct < 100:
-            _, srgb = r.develop(30.0, want_xyz=False)
+        if not args.no_preview and time.time() - state["last"] >= args.preview_interval and pct < 100:
+            _, srgb = r.develop(30.0, want_xyz=False)   # the preview integrates in 30 nm steps (main.rs:274-279)
             Image.fromarray(srgb).save(out)
             state["last"] = time.time()
+            state["previews"] += 1
         return False
 
     seed = args.seed if args.seed is not None else time.time_ns() & 0xFFFFFFFFFFFF
-    device_seconds = r.render(seed=seed, spp=args.spp, progress=progress)
+    device_seconds = r.render(seed=seed, spp=args.spp, pool_paths=args.pool, progress=progress)
     rendered = time.time()
     print()
     _, srgb = r.develop(2.0, want_xyz=False)
@@ -62,7 +65,7 @@ def main(argv=None) -> int:
     c = r.counters()
     print(f"Rendering: {rendered - loaded:.3f} s  (device {device_seconds:.3f} s, {c['rays'] / max(device_seconds, 1e-9) / 1e6:.0f} Mrays/s, "
           f"{c['path_samples'] / max(device_seconds, 1e-9) / 1e6:.1f} M path samples/s)")
-    print(f"Total: {time.time() - total_start:.3f} s; wrote {out}")
+    print(f"Total: {time.time() - total_start:.3f} s; wrote {out} ({state['previews']} previews on the way)")
     r.close()
     return 0
 

@@ -67,6 +67,7 @@ struct pyr_ctx {
     DeviceBuffer film, develop_params, counters, scalars, tile_first;
     DeviceBuffer paths, pend, bidir, rays[2], hits, shadow_kinds, march_queue[2], march_key, light_vertices, cam_vertices, bin_count, bin_first, bin_fill, bin_keys, bin_list, live_list;
     uint32_t shadow_per_path = 1;
+    uint32_t march_capacity[2] = {0, 0};
     DeviceBuffer scratch_a, scratch_b;
     uint32_t pool = 0;
     bool develop_params_valid = false;
@@ -113,12 +114,32 @@ void need_project(pyr_ctx* ctx) {
     if (!ctx->loaded) throw StateError("no project is loaded");
 }
 
+// Argument checks shared by pyr_trace, pyr_trace_stats and pyr_trace_device.  Returns false for an empty batch.
+bool check_trace_args(pyr_ctx* ctx, const void* rays, size_t n, const void* hits, bool device_buffers) {
+    need_project(ctx);
+    if (n > 0xFFFFFFF0ull) throw ir::BuildError("ray batch too large (at most 2^32 - 16 rays per call)");
+    if (n == 0) return false;
+    if (!rays || !hits) throw ir::BuildError("null ray or hit buffer");
+    if (device_buffers) {
+        if ((uintptr_t)rays & 31u) throw ir::BuildError("the device ray buffer must be 32-byte aligned");
+        if ((uintptr_t)hits & 3u) throw ir::BuildError("the device hit buffer must be 4-byte aligned");
+    }
+    return true;
+}
+
 void ensure_develop_params(pyr_ctx* ctx) {
     if (ctx->develop_params_valid) return;
     ctx->develop_params.ensure(4 * sizeof(float));
     launch_white_scan(ctx->view, ctx->develop_params.as<float>(), ctx->stream);
     CU(cudaGetLastError());
     ctx->develop_params_valid = true;
+}
+
+// ray-marched shapes per distance-estimator type: each (ray, shape) pair queues at most once, so rays x shapes-of-a-type
+// entries per queue can never overflow
+void marched_per_type(const pyr_ctx* ctx, size_t out[2]) {
+    out[0] = out[1] = 0;
+    for (const MarchedRec& m : ctx->scene.marched) out[m.estimator ? 1 : 0] += 1;
 }
 
 void ensure_pool(pyr_ctx* ctx, uint32_t pool) {
@@ -141,9 +162,12 @@ void ensure_pool(pyr_ctx* ctx, uint32_t pool) {
     ctx->hits.ensure((size_t)pool * sizeof(Hit));
     ctx->shadow_kinds.ensure((size_t)pool * ctx->shadow_per_path * sizeof(uint32_t));
     if (ctx->view.n_marched) {
-        const size_t items = ray_cap * std::min<uint32_t>(ctx->view.n_marched, 4);
-        ctx->march_queue[0].ensure(items * sizeof(uint2));
-        ctx->march_queue[1].ensure(items * sizeof(uint2));
+        size_t per_type[2];
+        marched_per_type(ctx, per_type);
+        ctx->march_queue[0].ensure(ray_cap * per_type[0] * sizeof(uint2));
+        ctx->march_queue[1].ensure(ray_cap * per_type[1] * sizeof(uint2));
+        ctx->march_capacity[0] = (uint32_t)std::min<size_t>(ray_cap * per_type[0], 0xFFFFFFFFull);
+        ctx->march_capacity[1] = (uint32_t)std::min<size_t>(ray_cap * per_type[1], 0xFFFFFFFFull);
         ctx->march_key.ensure((size_t)pool * sizeof(unsigned long long));
     }
     if (bidir) {
@@ -163,7 +187,7 @@ size_t pool_bytes_per_path(const pyr_ctx* ctx) {
     const size_t shadow = bidir ? (size_t)bdpt_stage_rays() : std::max<uint32_t>(R.light_samples, 1);
     size_t b = path_state_bytes() + MAX_LIGHT_SAMPLES * pending_light_bytes() + 2 * sizeof(uint32_t) + sizeof(uint16_t) +
                (1 + shadow) * 2 * sizeof(Ray) + sizeof(Hit) + shadow * sizeof(uint32_t);
-    if (ctx->view.n_marched) b += (1 + shadow) * std::min<uint32_t>(ctx->view.n_marched, 4) * 2 * sizeof(uint2) + sizeof(unsigned long long);
+    if (ctx->view.n_marched) b += (1 + shadow) * (size_t)ctx->view.n_marched * sizeof(uint2) + sizeof(unsigned long long);
     if (bidir) b += bidir_state_bytes() + (size_t)(R.light_bounces + 1) * light_vertex_bytes() + (size_t)std::max<uint32_t>(R.bounces, 1) * cam_vertex_bytes();
     return b;
 }
@@ -256,6 +280,14 @@ pyr_status pyr_project_load(pyr_ctx* ctx, const void* ir_blob, size_t bytes) {
         ir::Document doc = ir::decode(ir_blob, bytes);
         BakedScene baked = build_scene(doc);
         cudaStream_t s = ctx->stream;
+        // From here on the old project's buffers are freed / overwritten in place: the context holds NO project until the
+        // last upload has completed, so a failure half-way (out of device memory on a bigger scene) leaves it in the
+        // "nothing loaded" state - the next pyr_render / pyr_trace / pyr_film_* returns PYR_ERR_STATE instead of touching
+        // freed memory.
+        CU(cudaStreamSynchronize(s));
+        ctx->loaded = false;
+        ctx->pool = 0;
+        ctx->develop_params_valid = false;
         upload(ctx->nodes, baked.nodes, s);
         upload(ctx->prims, baked.prims, s);
         upload(ctx->tri_shade, baked.tri_shade, s);
@@ -306,11 +338,7 @@ pyr_status pyr_project_info_get(const pyr_ctx* ctx, pyr_project_info* out) {
 
 pyr_status pyr_trace_device(pyr_ctx* ctx, const void* d_rays, size_t n, void* d_hits, uint32_t repeat) {
     return guarded(ctx, [&] {
-        need_project(ctx);
-        if (n > 0xFFFFFFF0ull) throw ir::BuildError("ray batch too large");
-        if (n == 0) return;
-        if (!d_rays || !d_hits) throw ir::BuildError("null ray or hit buffer");
-        if ((uintptr_t)d_rays & 31u) throw ir::BuildError("the device ray buffer must be 32-byte aligned");
+        if (!check_trace_args(ctx, d_rays, n, d_hits, true)) return;
         const int blocks = ctx->sm_count * trace_blocks_per_sm();
         CU(cudaEventRecord(ctx->ev0, ctx->stream));
         for (uint32_t r = 0; r < (repeat ? repeat : 1u); ++r) {
@@ -329,9 +357,7 @@ pyr_status pyr_trace_device(pyr_ctx* ctx, const void* d_rays, size_t n, void* d_
 
 pyr_status pyr_trace_stats(pyr_ctx* ctx, const pyr_ray* rays, size_t n, pyr_hit* hits_out) {
     return guarded(ctx, [&] {
-        need_project(ctx);
-        if (n == 0) return;
-        if (!rays || !hits_out) throw ir::BuildError("null ray or hit buffer");
+        if (!check_trace_args(ctx, rays, n, hits_out, false)) return;
         ctx->scratch_a.ensure(n * sizeof(pyr_ray));
         ctx->scratch_b.ensure(n * sizeof(pyr_hit));
         CU(cudaMemcpyAsync(ctx->scratch_a.p, rays, n * sizeof(pyr_ray), cudaMemcpyHostToDevice, ctx->stream));
@@ -347,10 +373,7 @@ pyr_status pyr_trace_stats(pyr_ctx* ctx, const pyr_ray* rays, size_t n, pyr_hit*
 
 pyr_status pyr_trace(pyr_ctx* ctx, const pyr_ray* rays, size_t n, pyr_hit* hits_out) {
     return guarded(ctx, [&] {
-        need_project(ctx);
-        if (n == 0) return;
-        if (!rays || !hits_out) throw ir::BuildError("null ray or hit buffer");
-        if (n > 0xFFFFFFF0ull) throw ir::BuildError("ray batch too large");
+        if (!check_trace_args(ctx, rays, n, hits_out, false)) return;
         ctx->scratch_a.ensure(n * sizeof(pyr_ray));
         ctx->scratch_b.ensure(n * sizeof(pyr_hit));
         CU(cudaMemcpyAsync(ctx->scratch_a.p, rays, n * sizeof(pyr_ray), cudaMemcpyHostToDevice, ctx->stream));
@@ -471,7 +494,8 @@ pyr_status pyr_render(pyr_ctx* ctx, const pyr_render_params* params, pyr_progres
                 t.march_queue[0] = ctx->march_queue[0].as<uint2>();
                 t.march_queue[1] = ctx->march_queue[1].as<uint2>();
                 t.march_count = ctx->march_count();
-                t.march_capacity = (uint32_t)(ctx->march_queue[0].bytes / sizeof(uint2));
+                t.march_capacity[0] = ctx->march_capacity[0];
+                t.march_capacity[1] = ctx->march_capacity[1];
                 t.march_key = ctx->march_key.as<unsigned long long>();
                 if (ctx->view.n_marched) CU(cudaMemsetAsync(ctx->march_count(), 0, 4 * sizeof(uint32_t), s));
                 launch_trace(ctx->view, t, trace_blocks, s);
@@ -506,10 +530,16 @@ pyr_status pyr_render(pyr_ctx* ctx, const pyr_render_params* params, pyr_progres
             }
         }
         CU(cudaEventRecord(ctx->ev1, s));
+        if (ctx->view.n_marched)
+            CU(cudaMemcpyAsync(&ctx->pinned[3], &ctx->counters.as<DeviceCounters>()->march_overflow, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
         ctx->host_counters.render_seconds = ms * 1e-3;
+        if (ctx->view.n_marched && ctx->pinned[3]) {
+            CU(cudaMemsetAsync(&ctx->counters.as<DeviceCounters>()->march_overflow, 0, sizeof(unsigned long long), s));
+            throw StateError("the sphere-tracing queue overflowed: " + std::to_string(ctx->pinned[3]) + " candidates were dropped, the film is incomplete");
+        }
         ctx->host_counters.wavefront_iterations += iterations;
         ctx->host_counters.kernel_launches += launches;
         ctx->host_counters.path_samples += cancelled ? std::min<unsigned long long>(ctx->pinned[1], total) : total;
@@ -635,6 +665,7 @@ pyr_status pyr_counters_get(pyr_ctx* ctx, pyr_counters* out, int32_t reset) {
 pyr_status pyr_bvh_leaf_order(pyr_ctx* ctx, uint32_t* object_ids_out) {
     return guarded(ctx, [&] {
         need_project(ctx);
+        if (!object_ids_out && ctx->scene.n_objects) throw ir::BuildError("null output buffer");
         for (uint32_t obj = 0; obj < ctx->scene.n_objects; ++obj) object_ids_out[ctx->scene.rank_of_object[obj]] = obj;
     });
 }

@@ -492,9 +492,10 @@ struct EmitHit {
     uint2* march_queue0;
     uint2* march_queue1;
     uint32_t* march_count;
-    uint32_t march_capacity;
+    uint32_t march_capacity[2];
     unsigned long long* march_key;
     const MarchedRec* marched;
+    DeviceCounters* counters;
     template <class T>
     __device__ __forceinline__ void operator()(uint32_t at, const T& tr) const {
         // rays that reached ray-marched leaves (and are not decided yet) go on to the sphere-tracing kernels
@@ -511,7 +512,9 @@ struct EmitHit {
                 if ((int)lane_id() == leader) base = atomicAdd(march_count + type, (uint32_t)__popc(peers));
                 base = __shfl_sync(peers, base, leader);
                 const uint32_t pos = base + __popc(peers & ((1u << lane_id()) - 1u));
-                if (pos < march_capacity) (type ? march_queue1 : march_queue0)[pos] = make_uint2(at, shape);
+                // the queues hold rays x shapes-of-this-type entries, so this cannot overflow; if it ever does the render fails loudly
+                if (pos < march_capacity[type]) (type ? march_queue1 : march_queue0)[pos] = make_uint2(at, shape);
+                else atomicAdd(&counters->march_overflow, 1ull);
             }
             if (at < shadow_offset) march_key[at] = pack_hit(tr.t, tr.kind, tr.rank);
         }
@@ -524,7 +527,7 @@ struct EmitHit {
 
 template <bool STATS>
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace(const __grid_constant__ SceneView sc, const __grid_constant__ TraceArgs a) {
-    EmitHit emit{a.hits, a.shadow_kinds, a.shadow_offset, a.march_queue[0], a.march_queue[1], a.march_count, a.march_capacity, a.march_key, sc.marched};
+    EmitHit emit{a.hits, a.shadow_kinds, a.shadow_offset, a.march_queue[0], a.march_queue[1], a.march_count, {a.march_capacity[0], a.march_capacity[1]}, a.march_key, sc.marched, a.counters};
     trace_persistent<STATS>(sc, a.rays, a.count[0], a.count[1], a.shadow_offset, a.cursor, a.counters, false, a.refill_min, a.steps, emit);
 }
 
@@ -540,7 +543,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_march(const __grid_constant__
     // when its own is empty, so that both queues drain together and their long tails overlap
     uint32_t TYPE = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) & 1u;
     bool switched = false;
-    uint32_t n = min(a.march_count[TYPE], a.march_capacity);
+    uint32_t n = min(a.march_count[TYPE], a.march_capacity[TYPE]);
     const uint2* queue = a.march_queue[TYPE];
     uint32_t* cursor = cursors + TYPE;
     unsigned long long evals = 0, iters = 0;
@@ -592,7 +595,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_march(const __grid_constant__
                 if (switched) break;
                 switched = true;
                 TYPE ^= 1u;
-                n = min(a.march_count[TYPE], a.march_capacity);
+                n = min(a.march_count[TYPE], a.march_capacity[TYPE]);
                 queue = a.march_queue[TYPE];
                 cursor = cursors + TYPE;
                 exhausted = false;
@@ -665,7 +668,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_march(const __grid_constant__
 // Write the merged result back into the hit record of every path ray a marched shape won.
 __global__ void __launch_bounds__(256) k_march_apply(const TraceArgs a, const MarchedRec* marched) {
     for (int type = 0; type < 2; ++type) {
-        const uint32_t n = min(a.march_count[type], a.march_capacity);
+        const uint32_t n = min(a.march_count[type], a.march_capacity[type]);
         for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
             const uint2 item = a.march_queue[type][i];
             if (item.x >= a.shadow_offset) continue;

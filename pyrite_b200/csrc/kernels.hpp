@@ -16,6 +16,7 @@ struct CamVertex;
 // Device-side work counters (one instance per context).
 struct DeviceCounters {
     unsigned long long rays, path_samples, nodes_visited, leaves_tested, de_evals, de_iterations, node_fetches, path_rays;
+    unsigned long long march_overflow;  // sphere-tracing candidates that did not fit their queue (must stay 0: pyr_render fails otherwise)
 };
 
 // Everything one wavefront iteration needs besides the scene.
@@ -83,7 +84,7 @@ struct TraceArgs {
     // distance-estimator type so that the lanes of a warp run the same estimator
     uint2* march_queue[2];       // (ray index, shape index); [0] Mandelbulb, [1] quaternion Julia
     uint32_t* march_count;       // two device counters (zeroed before the launch)
-    uint32_t march_capacity;     // entries per queue
+    uint32_t march_capacity[2];  // entries per queue: rays x ray-marched shapes of that estimator type (an exact bound)
     unsigned long long* march_key;  // per path ray: (distance bits, tie rank) of the best hit so far, merged with atomicMin
 };
 struct TraceTuning { uint32_t refill_min, steps; };

@@ -97,7 +97,15 @@ class Cursor {
         const unsigned char* p = take(((size_t)n + 3) & ~(size_t)3);
         return std::string((const char*)p, n);
     }
+    // a count read from the blob is checked against the bytes that are left BEFORE anything is allocated:
+    // every record of `min_bytes` or more must still fit (a corrupt count cannot make the decoder zero-fill gigabytes)
+    size_t count(size_t min_bytes) {
+        const size_t n = u32();
+        if (min_bytes && n > left_ / min_bytes) throw BuildError("project IR is truncated (a table is longer than the blob)");
+        return n;
+    }
     template <class T> std::vector<T> block(size_t count) {
+        if (count > left_ / sizeof(T)) throw BuildError("project IR is truncated");
         std::vector<T> v(count);
         if (count) memcpy(v.data(), take(count * sizeof(T)), count * sizeof(T));
         return v;
@@ -121,7 +129,7 @@ inline Document decode(const void* data, size_t bytes) {
     if (c.u32() != 0x52495950u) throw BuildError("not a pyrite project IR blob");
     if (c.u32() != 1u) throw BuildError("unsupported project IR version");
     static const int arity[] = {4, 3, 2, 3, 3, 2, 1, 0, 0, 0};
-    d.nodes.resize(c.u32());
+    d.nodes.resize(c.count(4));
     for (auto& n : d.nodes) {
         n.kind = c.u32();
         if (n.kind > N_MONO_TEXTURE) throw BuildError("unknown expression node in IR");
@@ -129,7 +137,7 @@ inline Document decode(const void* data, size_t bytes) {
         if (n.kind >= N_SPECTRUM) n.resource = c.u32();
         for (int i = 0; i < arity[n.kind]; ++i) n.arg[i] = c.ex();
     }
-    d.surfaces.resize(c.u32());
+    d.surfaces.resize(c.count(4));
     for (auto& s : d.surfaces) {
         s.kind = c.u32();
         switch (s.kind) {
@@ -142,23 +150,23 @@ inline Document decode(const void* data, size_t bytes) {
             default: throw BuildError("unknown surface material node in IR");
         }
     }
-    d.spectra.resize(c.u32());
+    d.spectra.resize(c.count(8));
     for (auto& s : d.spectra) {
         uint32_t kind = c.u32();
         if (kind == 0) { s.lo = c.f32(); s.hi = c.f32(); s.values = c.block<float>(c.u32()); }
         else if (kind == 1) { s.curve = true; s.values = c.block<float>((size_t)c.u32() * 2); }
         else throw BuildError("unknown spectrum kind in IR");
     }
-    d.color_textures.resize(c.u32());
+    d.color_textures.resize(c.count(8));
     for (auto& t : d.color_textures) { t.width = c.u32(); t.height = c.u32(); t.channels = 4; t.texels = c.block<float>((size_t)t.width * t.height * 4); }
-    d.mono_textures.resize(c.u32());
+    d.mono_textures.resize(c.count(8));
     for (auto& t : d.mono_textures) { t.width = c.u32(); t.height = c.u32(); t.channels = 1; t.texels = c.block<float>((size_t)t.width * t.height); }
-    d.meshes.resize(c.u32());
+    d.meshes.resize(c.count(16));
     for (auto& m : d.meshes) {
         m.positions = c.block<float>((size_t)c.u32() * 3);
         m.uvs = c.block<float>((size_t)c.u32() * 2);
         m.normals = c.block<float>((size_t)c.u32() * 3);
-        m.objects.resize(c.u32());
+        m.objects.resize(c.count(8));
         for (auto& o : m.objects) { o.name = c.text(); o.corners = c.block<int32_t>((size_t)c.u32() * 9); }
     }
     d.burns_lo = c.f32(); d.burns_hi = c.f32(); d.burns = c.block<float>((size_t)c.u32() * 3);
@@ -173,7 +181,7 @@ inline Document decode(const void* data, size_t bytes) {
     d.camera_transform = c.look_at();
     d.fov = c.ex(); d.focus_distance = c.maybe_ex(); d.aperture = c.maybe_ex();
     d.sky = c.maybe_ex();
-    d.objects.resize(c.u32());
+    d.objects.resize(c.count(4));
     for (auto& o : d.objects) {
         o.kind = c.u32();
         switch (o.kind) {
@@ -192,7 +200,7 @@ inline Document decode(const void* data, size_t bytes) {
                 break;
             case OBJ_MESH: {
                 o.mesh = c.u32();
-                uint32_t n = c.u32();
+                uint32_t n = (uint32_t)c.count(8);
                 for (uint32_t i = 0; i < n; ++i) { std::string name = c.text(); o.mesh_materials.emplace_back(name, c.material()); }
                 o.mesh_scale = c.maybe_ex();
                 o.has_transform = c.u32() != 0;

@@ -322,25 +322,28 @@ Ex make_clamp(Document& doc, Ex v, Ex lo, Ex hi) {
 
 // Material::from_project (materials/mod.rs:33-46) + SurfaceMaterial::from_project (:89-228)
 uint32_t bake_material(Document& doc, BakedScene& out, const ir::MaterialUse& use) {
-    struct Work { uint32_t surface; bool weighted; Ex weight; };
-    std::vector<Work> todo{{use.surface, false, Ex()}};
+    // `depth` guards against a cyclic mix / add graph in a hand-made IR blob (the Lua loader cannot produce one);
+    // the worklist is depth-first, so a cycle reaches the limit after ~1024 steps instead of growing for ever
+    struct Work { uint32_t surface; bool weighted; Ex weight; uint32_t depth; };
+    std::vector<Work> todo{{use.surface, false, Ex(), 0u}};
     std::vector<ComponentRec> all, glowing;
     Folder fold{doc};
     while (!todo.empty()) {
         Work w = todo.back();
         todo.pop_back();
         if (w.surface >= doc.surfaces.size()) throw BuildError("surface material id out of range");
+        if (w.depth > 1024) throw BuildError("surface material graph is cyclic");
         const ir::SurfaceNode sn = doc.surfaces[w.surface];
         if (sn.kind == ir::S_MIX) {  // `amount` weights lhs (materials/mod.rs:176-195)
             Ex amount = make_clamp(doc, sn.amount, Ex::constant(0.0), Ex::constant(1.0));
             Ex lhs_weight = w.weighted ? make_product(doc, w.weight, amount) : amount;
-            todo.push_back({sn.lhs, true, lhs_weight});
-            todo.push_back({sn.rhs, true, make_difference(doc, Ex::constant(1.0), lhs_weight)});
+            todo.push_back({sn.lhs, true, lhs_weight, w.depth + 1});
+            todo.push_back({sn.rhs, true, make_difference(doc, Ex::constant(1.0), lhs_weight), w.depth + 1});
             continue;
         }
         if (sn.kind == ir::S_ADD) {
-            todo.push_back({sn.lhs, w.weighted, w.weight});
-            todo.push_back({sn.rhs, w.weighted, w.weight});
+            todo.push_back({sn.lhs, w.weighted, w.weight, w.depth + 1});
+            todo.push_back({sn.rhs, w.weighted, w.weight, w.depth + 1});
             continue;
         }
         ComponentRec c;

@@ -305,6 +305,34 @@ def fractals(width=3840, height=2160, spp=512, bounces=8, light_samples=4, spect
     }
 
 
+def fractal_variants(width=512, height=256, spp=64, bounces=4, light_samples=2, spectrum_samples=6):
+    """The estimator variants no shipped scene uses: quaternion Julia `regular` and `bicomplex` (distance_estimators.rs:78-107),
+    a Mandelbulb with `constant` (the Julia-bulb branch, distance_estimators.rs:16-19), a `bounds.sphere` volume, and an
+    `image.filter` expression next to `image.white` (main.rs:197-238)."""
+    glossy = {"surface": mix(material.mirror(color=1), material.diffuse(color=0.8), fresnel(1.5))}
+    matte = {"surface": material.diffuse(color=spectrum(format="curve", points=[(400, 0.2), (520, 0.9), (700, 0.4)]))}
+    return {
+        "image": {"width": width, "height": height, "white": blackbody(5000),
+                  "filter": spectrum(format="curve", points=[(370, 0.9), (480, 1.0), (600, 0.6), (790, 0.35)])},
+        "renderer": renderer.simple(pixel_samples=spp, spectrum_samples=spectrum_samples, tile_size=32, bounces=bounces,
+                                    light_samples=light_samples),
+        "camera": camera.perspective(fov=38, transform=transform.look_at(**{"from": vector(0.0, -8.5, 2.4), "to": vector(0.0, 0, 1.2),
+                                                                              "up": vector(z=1)})),
+        "world": {"sky": light_source.d65 * 0.2, "objects": [
+            shape.ray_marched(shape=ray_marched.quaternion_julia(iterations=16, threshold=4, constant=vector(-0.291, -0.399, 0.339, 0.437),
+                                                                 slice_plane=0.1, variant=quaternion_julia.regular),
+                              bounds=bounds.box(min=vector(-4.4, -1.4, 0), max=vector(-1.6, 1.4, 2.8)), material=glossy),
+            shape.ray_marched(shape=ray_marched.quaternion_julia(iterations=12, threshold=4, constant=vector(-0.4, 0.45, 0.1, 0.2),
+                                                                 slice_plane=0, variant=quaternion_julia.bicomplex),
+                              bounds=bounds.sphere(position=vector(0, 0, 1.3), radius=1.3), material=matte),
+            shape.ray_marched(shape=ray_marched.mandelbulb(iterations=12, threshold=4, power=6, constant=vector(0.35, -0.45, 0.3)),
+                              bounds=bounds.box(min=vector(1.7, -1.2, 0), max=vector(4.1, 1.2, 2.4)), material=glossy),
+            shape.plane(origin=vector(), normal=vector(z=1), material={"surface": material.diffuse(color=0.5)}),
+            shape.sphere(position=vector(-1, -4, 6), radius=1.0, material={"surface": material.emissive(color=light_source.d65 * 14)}),
+        ]},
+    }
+
+
 def bdpt_cornell_dragon(width=3840, height=2160, spp=1024, bounces=6, light_bounces=6, light_samples=1, mesh=None, dragon_scale=0.22):
     """BASELINE config C5: textured Cornell box (tiles floor, colour-checker back wall) + dragon stand-in, bidirectional."""
     mats = _cornell_materials()
@@ -328,4 +356,5 @@ def bdpt_cornell_dragon(width=3840, height=2160, spp=1024, bounces=6, light_boun
 SCENES = {
     "cornell": cornell, "dragon": dragon, "diamonds": diamonds, "spheres": spheres, "rgb_emission": rgb_emission,
     "textures": textures, "snowflake": snowflake_mesh_scene, "fractals": fractals, "bdpt_cornell_dragon": bdpt_cornell_dragon,
+    "fractal_variants": fractal_variants,
 }

@@ -45,6 +45,8 @@ def small_scene_kwargs():
         "rgb_emission": dict(width=64, height=48, spp=4),
         "snowflake": dict(width=64, height=48, spp=4),
         "fractals": dict(width=48, height=32, spp=2),
+        # Julia regular / bicomplex, Mandelbulb with constant, bounds.sphere, image.filter
+        "fractal_variants": dict(width=48, height=24, spp=2),
         "dragon": dict(width=64, height=48, spp=4, mesh=scenes.dragon_mesh(300, 24)),
         # limits: portrait film (the vertical AspectRatio branch, film.rs:203-246), maximum spectrum / light samples
         "edge_portrait": dict(_scene="cornell", width=40, height=72, spp=4, spectrum_samples=16, light_samples=8, bounces=2),
@@ -59,7 +61,8 @@ def small_scene_kwargs():
     }
 
 
-SCENE_NAMES = ["cornell", "spheres", "diamonds", "textures", "rgb_emission", "snowflake", "fractals", "dragon", "edge_portrait", "lua_orbs"]
+SCENE_NAMES = ["cornell", "spheres", "diamonds", "textures", "rgb_emission", "snowflake", "fractals", "fractal_variants", "dragon", "edge_portrait", "lua_orbs"]
+MARCHED_SCENES = ["fractals", "fractal_variants", "lua_orbs"]  # sphere-traced shapes: tolerance-level parity on the device
 BIDIR_NAMES = ["bd_cornell", "bd_cornell_fractal", "bd_glass_dragon", "bd_diamonds", "bd_spheres", "bd_c5"]
 MESH_SCENES = ["cornell", "diamonds", "textures", "snowflake", "dragon", "spheres", "rgb_emission"]
 

@@ -92,6 +92,46 @@ def test_builder_errors():
         Emu(scene_ir("cornell")[:-8], (64, 64, 64))
 
 
+def test_corrupt_ir_is_rejected_before_allocating():
+    """A count field larger than the blob must fail as `truncated` before any table is allocated, and a cyclic mix / add
+    surface graph (only a hand-made blob can hold one) must fail instead of looping."""
+    import struct
+
+    from emu_lib import Emu, EmuError
+
+    base = {"image": {"width": 8, "height": 8}, "renderer": P.renderer.simple(pixel_samples=1),
+            "camera": P.camera.perspective(fov=40, transform=P.transform.look_at(**{"from": P.vector(0, 0, 5), "to": P.vector(0, 0, 0)}))}
+    surface = P.mix(P.material.mirror(color=1), P.material.diffuse(color=0.5), 0.25)
+    ir = bytearray(P.serialize_project(dict(base, world={"sky": 1.0, "objects": [P.shape.sphere(position=P.vector(), radius=1, material={"surface": surface})]})))
+    Emu(bytes(ir), (8, 8, 64))  # sane as written
+    huge = bytearray(ir)
+    huge[8:12] = struct.pack("<I", 0xFFFFFFFF)  # expression-node count
+    with pytest.raises(EmuError, match="truncated"):
+        Emu(bytes(huge), (8, 8, 64))
+    # walk the surface table (kind, then: emissive/diffuse/mirror = one 12-byte expression; mix = lhs, rhs, expression)
+    n_nodes, = struct.unpack_from("<I", ir, 8)
+    at = 12
+    arity = [4, 3, 2, 3, 3, 2, 1, 0, 0, 0]  # vector rgb binary mix clamp fresnel blackbody spectrum color_texture mono_texture
+    for _ in range(n_nodes):
+        kind, = struct.unpack_from("<I", ir, at)
+        at += 4 + (4 if kind == 2 else 0) + (4 if kind >= 7 else 0) + 12 * arity[kind]
+    n_surfaces, = struct.unpack_from("<I", ir, at)
+    at, patched = at + 4, False
+    for index in range(n_surfaces):
+        kind, = struct.unpack_from("<I", ir, at)
+        if kind in (0, 1, 2):
+            at += 4 + 12
+        elif kind == 4:
+            struct.pack_into("<I", ir, at + 4, index)  # lhs = the mix node itself
+            patched = True
+            at += 4 + 8 + 12
+        else:
+            raise AssertionError(f"unexpected surface kind {kind}")
+    assert patched
+    with pytest.raises(EmuError, match="cyclic"):
+        Emu(bytes(ir), (8, 8, 64))
+
+
 def test_empty_and_degenerate_scenes():
     from emu_lib import Emu
     from oracle_lib import Oracle
