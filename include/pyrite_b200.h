@@ -158,6 +158,14 @@ pyr_status pyr_film_develop(pyr_ctx* ctx, float step_size, float* xyz_out, uint8
 pyr_status pyr_camera_sample(pyr_ctx* ctx, uint64_t seed, uint32_t tile, uint64_t sample, float* position_out, pyr_ray* ray_out,
                              float* wavelengths_out, uint32_t* hero_out);
 
+/* Diagnostic seam (tools/first_divergence.py): ONE `render_tile` iteration of the camera-to-light integrator
+ * (simple.rs:87-139) for path sample (tile, sample), run depth-first by one GPU thread with the same stage functions the
+ * wavefront kernels use, with per-bounce records of `trace` (tracer.rs:221-343).  records_out: max_bounces x 20 words
+ * {kind, prim_id, t, u, v, incident[3], position[3], normal[3], out[3], visibility rays cast, Xorshift `w` after the
+ * bounce, 1 if a surface bounce was pushed}; exposed_out: 16 x (brightness, wavelength) of which n_exposed are valid. */
+pyr_status pyr_debug_path(pyr_ctx* ctx, uint64_t seed, uint32_t tile, uint64_t sample, uint32_t max_bounces, uint32_t* records_out,
+                          uint32_t* n_bounces_out, float* exposed_out, uint32_t* n_exposed_out, float* position_out);
+
 pyr_status pyr_counters_get(pyr_ctx* ctx, pyr_counters* out, int32_t reset);
 
 /* Library / device identification for reports: "pyrite_b200 <version>; sm_100a; <device name>; <SMs> SMs". */

@@ -42,6 +42,7 @@ struct pyro_render_opts {
 };
 
 const char* pyro_last_error() { return g_error.c_str(); }
+int pyro_libm_mode() { return LIBM_MODE; }  // 0 = glibc float functions (the reference), 1 = double, rounded once (the device's expression)
 
 int pyro_load(const void* ir, size_t bytes, void** out) {
     try {
@@ -238,6 +239,37 @@ int pyro_film_develop(void* handle, float step_size, float* xyz_out, uint8_t* sr
         std::vector<std::thread> pool;
         for (int t = 0; t < threads; ++t) pool.emplace_back(work, t);
         for (auto& t : pool) t.join();
+        return 0;
+    } catch (const std::exception& e) {
+        g_error = e.what();
+        return 1;
+    }
+}
+
+// tools/first_divergence.py: one path sample of the camera-to-light integrator with per-bounce records.
+// records: max_bounces x 20 words {kind, prim_id, t, u, v, incident[3], position[3], normal[3], out[3], n_direct, rng_w, pad};
+// exposed: up to 16 x (brightness, wavelength); position2: film position.  The layout equals pyr_debug_path's.
+int pyro_debug_path(void* handle, uint64_t seed, int eager_emissive_draw, uint32_t tile_index, uint64_t sample, uint32_t max_bounces,
+                    uint32_t* records, uint32_t* n_bounces, float* exposed, uint32_t* n_exposed, float* position2) {
+    Handle* h = (Handle*)handle;
+    try {
+        const Project& P = h->world->P;
+        std::vector<Tile> tiles = make_tiles(P.width, P.height, h->R.tile_size);
+        const Tile* tile = nullptr;
+        for (auto& t : tiles) if (t.index == tile_index) tile = &t;
+        if (!tile) throw std::runtime_error("tile index out of range");
+        RenderOptions opt;
+        opt.seed = seed; opt.eager_emissive_draw = eager_emissive_draw != 0;
+        std::vector<DebugBounce> bounces;
+        std::vector<Sample> samples;
+        Vec2 pos;
+        debug_path_simple(*h->world, h->camera, h->R, *h->film, opt, *tile, sample, bounces, pos, samples);
+        static_assert(sizeof(DebugBounce) == 20 * 4, "20 words per record");
+        *n_bounces = (uint32_t)bounces.size();
+        for (size_t b = 0; b < bounces.size() && b < max_bounces; ++b) memcpy(records + 20 * b, &bounces[b], sizeof(DebugBounce));
+        *n_exposed = (uint32_t)samples.size();
+        for (size_t k = 0; k < samples.size() && k < 16; ++k) { exposed[2 * k] = samples[k].brightness; exposed[2 * k + 1] = samples[k].wavelength; }
+        position2[0] = pos.x; position2[1] = pos.y;
         return 0;
     } catch (const std::exception& e) {
         g_error = e.what();

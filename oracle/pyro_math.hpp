@@ -22,6 +22,29 @@ constexpr float PI = 3.14159265358979323846f;
 constexpr float FRAC_1_PI = 0.318309886183790671537767526745028724f;
 constexpr float INF = std::numeric_limits<float>::infinity();
 
+// The reference's f32::sin / cos / acos / atan2 / exp / powf are glibc's float functions (Rust's std calls the platform
+// libm).  That is the default here.  -DPYRO_LIBM_DOUBLE builds the variant liboracle_dbl.so in which the SHADING-side calls
+// (not the distance estimators) evaluate in double and round once - the very expression the device code uses (core.cuh
+// m_sin ...), so that "GPU vs oracle" differences caused by last-bit libm differences can be told apart from real ones:
+// tests/test_gpu_parity.py compares the GPU with both variants and tools/first_divergence.py prints the first differing value.
+#ifdef PYRO_LIBM_DOUBLE
+inline float m_sin(float x) { return (float)std::sin((double)x); }
+inline float m_cos(float x) { return (float)std::cos((double)x); }
+inline float m_acos(float x) { return (float)std::acos((double)x); }
+inline float m_atan2(float y, float x) { return (float)std::atan2((double)y, (double)x); }
+inline float m_exp(float x) { return (float)std::exp((double)x); }
+inline float m_pow(float x, float y) { return (float)std::pow((double)x, (double)y); }
+constexpr int LIBM_MODE = 1;
+#else
+inline float m_sin(float x) { return sinf(x); }
+inline float m_cos(float x) { return cosf(x); }
+inline float m_acos(float x) { return acosf(x); }
+inline float m_atan2(float y, float x) { return atan2f(y, x); }
+inline float m_exp(float x) { return expf(x); }
+inline float m_pow(float x, float y) { return powf(x, y); }
+constexpr int LIBM_MODE = 0;
+#endif
+
 // f32::min / f32::max (IEEE minNum/maxNum: a NaN operand yields the other one).
 inline float fmin_(float a, float b) { return fminf(a, b); }
 inline float fmax_(float a, float b) { return fmaxf(a, b); }
@@ -133,11 +156,11 @@ inline Mat3 operator*(const Mat3& l, const Mat3& r) {
 }
 // Matrix3::from_angle_x / from_angle_y (shapes/mod.rs:357-358)
 inline Mat3 mat3_from_angle_x(float theta) {
-    float s = sinf(theta), c = cosf(theta);
+    float s = m_sin(theta), c = m_cos(theta);
     return Mat3::from_cols({1, 0, 0}, {0, c, s}, {0, -s, c});
 }
 inline Mat3 mat3_from_angle_y(float theta) {
-    float s = sinf(theta), c = cosf(theta);
+    float s = m_sin(theta), c = m_cos(theta);
     return Mat3::from_cols({c, 0, -s}, {0, 1, 0}, {s, 0, c});
 }
 // Quaternion::from(Matrix3) - Shoemake, as in cgmath 0.17 (world.rs:100,357-367; shapes/mod.rs:546,580)

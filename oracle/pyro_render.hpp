@@ -133,11 +133,21 @@ struct RenderCounters {
     std::atomic<uint64_t> rays{0}, nodes{0}, leaves{0}, path_samples{0}, de_evals{0}, de_iters{0};
 };
 
+// What tools/first_divergence.py compares per bounce of one path sample (filled by `trace` when TraceCtx::debug is set).
+struct DebugBounce {
+    uint32_t kind = 0, prim_id = 0xFFFFFFFFu;   // closest hit of the incoming ray (K_MISS: none)
+    float t = 0, u = 0, v = 0;
+    float incident[3] = {0, 0, 0}, position[3] = {0, 0, 0}, normal[3] = {0, 0, 0}, out[3] = {0, 0, 0};
+    uint32_t n_direct = 0;   // direct-light samples drawn at this bounce
+    uint32_t rng_w = 0;      // Xorshift128 `w` after everything this bounce drew
+    uint32_t pad = 0;
+};
 struct TraceCtx {
     const World& W;
     XorShift& rng;
     TraceCounters tc;
     bool eager_emissive_draw = false;  // RNG stream mapping used by the wavefront pipeline
+    std::vector<DebugBounce>* debug = nullptr;
 };
 
 // ---------------------------------------------------------------- BSDF scatter (materials/*.rs)
@@ -301,9 +311,30 @@ inline void trace(std::vector<Bounce>& path, TraceCtx& cx, Ray ray, float wavele
                 bounce.normal = normal;
                 bounce.texture = sd.texture;
                 bounce.probability = sc.probability * component_prob;
+                if (cx.debug) {
+                    DebugBounce db;
+                    const SurfacePoint& sp = isect.surface_point;
+                    db.kind = sp.kind; db.prim_id = sp.kind == K_PLANE ? sp.plane->id : sp.shape->id; db.t = isect.distance; db.u = sp.u; db.v = sp.v;
+                    db.incident[0] = ray.direction.x; db.incident[1] = ray.direction.y; db.incident[2] = ray.direction.z;
+                    db.position[0] = position.x; db.position[1] = position.y; db.position[2] = position.z;
+                    db.normal[0] = normal.x; db.normal[1] = normal.y; db.normal[2] = normal.z;
+                    db.out[0] = sc.out_direction.x; db.out[1] = sc.out_direction.y; db.out[2] = sc.out_direction.z;
+                    db.n_direct = (uint32_t)bounce.direct_light.size(); db.rng_w = cx.rng.w;
+                    cx.debug->push_back(db);
+                }
                 ray = Ray{position, sc.out_direction};
                 path.push_back(std::move(bounce));
             } else {
+                if (cx.debug) {
+                    DebugBounce db;
+                    const SurfacePoint& sp = isect.surface_point;
+                    db.kind = sp.kind; db.prim_id = sp.kind == K_PLANE ? sp.plane->id : sp.shape->id; db.t = isect.distance; db.u = sp.u; db.v = sp.v;
+                    db.incident[0] = ray.direction.x; db.incident[1] = ray.direction.y; db.incident[2] = ray.direction.z;
+                    db.position[0] = position.x; db.position[1] = position.y; db.position[2] = position.z;
+                    db.normal[0] = normal.x; db.normal[1] = normal.y; db.normal[2] = normal.z;
+                    db.rng_w = cx.rng.w;
+                    cx.debug->push_back(db);
+                }
                 if (sample_light) {
                     Bounce bounce;
                     bounce.ty = BT_EMISSION;
@@ -319,6 +350,12 @@ inline void trace(std::vector<Bounce>& path, TraceCtx& cx, Ray ray, float wavele
                 break;
             }
         } else {
+            if (cx.debug) {
+                DebugBounce db;
+                db.incident[0] = ray.direction.x; db.incident[1] = ray.direction.y; db.incident[2] = ray.direction.z;
+                db.rng_w = cx.rng.w;
+                cx.debug->push_back(db);
+            }
             Program color = W.sky;
             if (sample_light) trace_directional(W, ray.direction, color);
             Bounce bounce;
@@ -475,6 +512,35 @@ inline void render_tile_simple(RenderState& st, const Tile& tile) {
     st.counters.path_samples += done;
 }
 
+// One `render_tile` iteration of the camera-to-light integrator (simple.rs:87-139) for path sample (tile, i) on its keyed
+// stream, with the per-bounce records of `trace` and the exposed (brightness, wavelength) pairs: tools/first_divergence.py.
+inline void debug_path_simple(const World& W, const Camera& camera, const RendererParams& R, const Film& film, const RenderOptions& opt,
+                              const Tile& tile, uint64_t i, std::vector<DebugBounce>& bounces, Vec2& position_out, std::vector<Sample>& exposed) {
+    XorShift rng = keyed_rng(opt.seed, tile.index, i);
+    TraceCtx cx{W, rng, {}, opt.eager_emissive_draw, &bounces};
+    std::vector<WSample> additional;
+    std::vector<float> wavelengths;
+    std::vector<Bounce> path;
+    Vec2 position = tile.sample_point(rng);
+    Ray ray = camera.ray_towards(position, rng);
+    film.sample_many_wavelengths(rng, R.spectrum_samples, wavelengths);
+    for (float w : wavelengths) additional.push_back(WSample{Sample{0.0f, w, 1.0f}, 1.0f});
+    size_t pick = rng.gen_range_usize(additional.size());
+    WSample main_sample = additional[pick];
+    additional[pick] = additional.back();
+    additional.pop_back();
+    trace(path, cx, ray, main_sample.s.wavelength, R.bounces, R.light_samples);
+    bool use_additional = true;
+    for (auto& bounce : path) {
+        use_additional = !bounce.dispersed && use_additional;
+        contribute(W, bounce, main_sample, additional.data(), use_additional ? additional.size() : 0);
+    }
+    position_out = position;
+    exposed.push_back(main_sample.s);
+    if (use_additional)
+        for (auto& a : additional) exposed.push_back(a.s);
+}
+
 // Camera::is_visible (cameras.rs:99-158)
 inline bool camera_is_visible(const Camera& cam, Vec3 target, TraceCtx& cx, Vec2& out_pos, Ray& out_ray) {
     Mat4 inv_transform;
@@ -485,7 +551,7 @@ inline bool camera_is_visible(const Camera& cam, Vec3 target, TraceCtx& cx, Vec2
     if (cam.aperture > 0.0f) {
         float sqrt_r = sqrtf(cam.aperture * cx.rng.gen_f32());
         float psi = PI * 2.0f * cx.rng.gen_f32();
-        origin = {sqrt_r * cosf(psi), sqrt_r * sinf(psi), 0.0f};
+        origin = {sqrt_r * m_cos(psi), sqrt_r * m_sin(psi), 0.0f};
     }
     Vec3 world_origin = transform_point(cam.transform, origin);
     Vec3 direction = target - world_origin;
@@ -774,7 +840,7 @@ inline void xyz_to_srgb8(const float xyz[3], uint8_t out[3]) {
         float v = lin[c];
         if (!(v > 0.0f)) v = 0.0f;
         if (v > 1.0f) v = 1.0f;
-        float e = v <= 0.0031308f ? 12.92f * v : 1.055f * powf(v, 1.0f / 2.4f) - 0.055f;
+        float e = v <= 0.0031308f ? 12.92f * v : 1.055f * m_pow(v, 1.0f / 2.4f) - 0.055f;
         float s = e * 255.0f + 0.5f;
         out[c] = (uint8_t)(s < 0.0f ? 0.0f : (s > 255.0f ? 255.0f : s));
     }

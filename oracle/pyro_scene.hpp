@@ -178,7 +178,7 @@ inline float blackbody(float wavelength, float temperature) {
     float a4 = a2 * a2;
     float p5 = 1.0f / (wavelength * a4);
     float power_term = 3.74183e-16f * p5;
-    return power_term / (expf(1.4388e-2f / (wavelength * temperature)) - 1.0f);
+    return power_term / (m_exp(1.4388e-2f / (wavelength * temperature)) - 1.0f);
 }
 // math.rs:98-113
 inline Vec3 ortho(Vec3 v) {
@@ -201,7 +201,7 @@ inline Vec3 sample_cone(XorShift& rng, Vec3 direction, float cos_half) {
     float r1 = PI * 2.0f * rng.gen_f32();
     float r2 = cos_half + (1.0f - cos_half) * rng.gen_f32();
     float oneminus = sqrtf(1.0f - r2 * r2);
-    return (o1 * cosf(r1) * oneminus + o2 * sinf(r1) * oneminus) + direction * r2;
+    return (o1 * m_cos(r1) * oneminus + o2 * m_sin(r1) * oneminus) + direction * r2;
 }
 // math.rs:139-145
 inline float solid_angle(float cos_half) { return cos_half >= 1.0f ? 0.0f : 2.0f * PI * (1.0f - cos_half); }
@@ -210,8 +210,8 @@ inline Vec3 sample_sphere(XorShift& rng) {
     float u = rng.gen_f32();
     float v = rng.gen_f32();
     float theta = 2.0f * PI * u;
-    float phi = acosf(2.0f * v - 1.0f);
-    return {sinf(phi) * cosf(theta), sinf(phi) * sinf(theta), cosf(phi)};
+    float phi = m_acos(2.0f * v - 1.0f);
+    return {m_sin(phi) * m_cos(theta), m_sin(phi) * m_sin(theta), m_cos(phi)};
 }
 // math.rs:155-164
 inline Vec3 sample_hemisphere(XorShift& rng, Vec3 direction) {
@@ -884,8 +884,8 @@ struct Shape {
     SurfaceData surface_data(const SurfacePoint& sp) const {
         if (kind == K_SPHERE) {  // :346-372
             Vec3 normal = normalize(sp.position - position);
-            float latitude = acosf(normal.y);
-            float longitude = atan2f(normal.x, normal.z);
+            float latitude = m_acos(normal.y);
+            float longitude = m_atan2(normal.x, normal.z);
             Mat3 rotation = mat3_from_angle_y(longitude) * mat3_from_angle_x(latitude - PI * 0.5f);
             Vec2 tc{longitude * FRAC_1_PI * 0.5f, 1.0f - (latitude * FRAC_1_PI)};
             return {Normal{normal, quat_from_mat3(rotation)}, Vec2{tc.x / texture_scale.x, tc.y / texture_scale.y}};
@@ -1085,7 +1085,7 @@ struct Camera {
         if (aperture > 0.0f) {
             float sqrt_r = sqrtf(aperture * rng.gen_f32());
             float psi = PI * 2.0f * rng.gen_f32();
-            origin = {sqrt_r * cosf(psi), sqrt_r * sinf(psi), 0.0f};
+            origin = {sqrt_r * m_cos(psi), sqrt_r * m_sin(psi), 0.0f};
             direction = tgt - origin;
         }
         return transform_ray(transform, Ray{origin, normalize(direction)});

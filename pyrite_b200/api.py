@@ -33,7 +33,7 @@ RENDER_TIMING = 2
 EXPORTS = [
     "pyr_init", "pyr_shutdown", "pyr_stream_set", "pyr_last_error", "pyr_project_load", "pyr_project_info_get", "pyr_trace", "pyr_trace_device",
     "pyr_trace_stats", "pyr_bvh_leaf_order", "pyr_render", "pyr_film_expose", "pyr_film_clear", "pyr_film_download", "pyr_film_upload",
-    "pyr_film_device_ptr", "pyr_film_develop", "pyr_camera_sample", "pyr_counters_get", "pyr_version",
+    "pyr_film_device_ptr", "pyr_film_develop", "pyr_camera_sample", "pyr_debug_path", "pyr_counters_get", "pyr_version",
 ]
 
 
@@ -104,6 +104,7 @@ def load_library(path: Optional[Path] = None):
     L.pyr_film_device_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(sz)]
     L.pyr_film_develop.argtypes = [vp, C.c_float, vp, vp]
     L.pyr_camera_sample.argtypes = [vp, C.c_uint64, C.c_uint32, C.c_uint64, vp, vp, vp, vp]
+    L.pyr_debug_path.argtypes = [vp, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, vp, vp, vp, vp, vp]
     L.pyr_counters_get.argtypes = [vp, C.POINTER(Counters), C.c_int32]
     for name in EXPORTS:
         if name not in ("pyr_shutdown", "pyr_last_error", "pyr_version"):
@@ -256,6 +257,16 @@ class Renderer:
         hero = C.c_uint32()
         self._check(self.L.pyr_camera_sample(self.h, seed, tile, sample, _ptr(pos), _ptr(ray), _ptr(wl), C.byref(hero)))
         return pos, ray[0], wl, int(hero.value)
+
+    def debug_path(self, seed: int, tile: int, sample: int, max_bounces: int = 64):
+        """Diagnostic: one path sample of the camera-to-light integrator run depth-first by one GPU thread.
+        Returns (records[n, 20] uint32, exposed[m, 2] float32 (brightness, wavelength), position[2])."""
+        rec = np.zeros((max_bounces, 20), np.uint32)
+        exposed = np.zeros((16, 2), np.float32)
+        pos = np.zeros(2, np.float32)
+        nb, ne = C.c_uint32(), C.c_uint32()
+        self._check(self.L.pyr_debug_path(self.h, seed, tile, sample, max_bounces, _ptr(rec), C.byref(nb), _ptr(exposed), C.byref(ne), _ptr(pos)))
+        return rec[:min(nb.value, max_bounces)], exposed[:ne.value], pos
 
     # -- counters
     def counters(self, reset: bool = False) -> dict:

@@ -636,6 +636,35 @@ pyr_status pyr_camera_sample(pyr_ctx* ctx, uint64_t seed, uint32_t tile, uint64_
     });
 }
 
+pyr_status pyr_debug_path(pyr_ctx* ctx, uint64_t seed, uint32_t tile, uint64_t sample, uint32_t max_bounces, uint32_t* records_out,
+                          uint32_t* n_bounces_out, float* exposed_out, uint32_t* n_exposed_out, float* position_out) {
+    return guarded(ctx, [&] {
+        need_project(ctx);
+        if (tile >= ctx->view.n_tiles) throw ir::BuildError("tile index out of range");
+        if (!records_out || !n_bounces_out || !exposed_out || !n_exposed_out || !position_out) throw ir::BuildError("null output buffer");
+        const size_t words = (size_t)20 * max_bounces + 2 + 2 * MAX_SPECTRUM_SAMPLES + 2;
+        ctx->scratch_a.ensure(words * sizeof(uint32_t));
+        uint32_t* d = ctx->scratch_a.as<uint32_t>();
+        uint32_t* d_counts = d + (size_t)20 * max_bounces;
+        float* d_exposed = reinterpret_cast<float*>(d_counts + 2);
+        float* d_position = d_exposed + 2 * MAX_SPECTRUM_SAMPLES;
+        CU(cudaMemsetAsync(d, 0, words * sizeof(uint32_t), ctx->stream));
+        ctx->scratch_b.ensure(debug_path_scratch_bytes());
+        launch_debug_path(ctx->view, seed, tile, sample, max_bounces, d, d_counts, d_exposed, d_position, ctx->scratch_b.p, ctx->stream);
+        CU(cudaGetLastError());
+        std::vector<uint32_t> host(words);
+        CU(cudaMemcpyAsync(host.data(), d, words * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        memcpy(records_out, host.data(), (size_t)20 * max_bounces * sizeof(uint32_t));
+        const uint32_t* counts = host.data() + (size_t)20 * max_bounces;
+        *n_bounces_out = counts[0];
+        *n_exposed_out = counts[1];
+        memcpy(exposed_out, counts + 2, 2 * MAX_SPECTRUM_SAMPLES * sizeof(float));
+        memcpy(position_out, counts + 2 + 2 * MAX_SPECTRUM_SAMPLES, 2 * sizeof(float));
+        ctx->host_counters.kernel_launches += 1;
+    });
+}
+
 pyr_status pyr_counters_get(pyr_ctx* ctx, pyr_counters* out, int32_t reset) {
     return guarded(ctx, [&] {
         DeviceCounters dc;

@@ -747,6 +747,9 @@ PYR_HD Prim fetch_prim(const Prim* p) {
 struct LocalStack {
     int codes[BVH_STACK];
     float dists[BVH_STACK];
+    float m;  // max(hit distance, entry distance of its leaf's box) of the current closest hit (Traversal::leaf_step)
+    PYR_HD void set_best_m(float v) { m = v; }
+    PYR_HD float best_m() const { return m; }
     PYR_HD void put(int i, int code, float dist) { codes[i] = code; dists[i] = dist; }
     PYR_HD int code(int i) const { return codes[i]; }
     PYR_HD float dist(int i) const { return dists[i]; }
@@ -799,6 +802,7 @@ struct Traversal {
         if (STATS) ++vn;
         if (!slab_test(ld3(sc.root_lo), ld3(sc.root_hi), o, inv, dr) || dr > cull) return;
         cur = sc.root;
+        stack.put(0, cur, dr);  // slot `sp` always holds the entry distance of the box of `cur` (read by leaf_step)
         done = false;
     }
 
@@ -845,8 +849,10 @@ struct Traversal {
         if (code[3] != NODE4_EMPTY) stack.put(sp++, code[3], dist[3]);
         if (code[2] != NODE4_EMPTY) stack.put(sp++, code[2], dist[2]);
         if (code[1] != NODE4_EMPTY) stack.put(sp++, code[1], dist[1]);
-        if (code[0] != NODE4_EMPTY) cur = code[0];
-        else pop(stack);
+        if (code[0] != NODE4_EMPTY) {
+            cur = code[0];
+            if (cur < 0) stack.put(sp, cur, dist[0]);  // a leaf reached without a pop: leave its box's entry distance where a pop would
+        } else pop(stack);
     }
     // one leaf (cur < 0): the primitive test of Shape::ray_intersect and World::intersect's acceptance rule
     template <class Stack>
@@ -869,8 +875,19 @@ struct Traversal {
         if (ok && ht > DIST_EPSILON) {
             if (mode != 0) {
                 if (occludes(mode, ht, limit)) { t = ht; u = hu; v = hv; rank = r; kind = k; done = true; return; }
-            } else if (ht < closest || (ht == closest && kind != KIND_PLANE && r < rank)) {
-                closest = ht; cull = ht * CULL_SLACK; t = ht; u = hu; v = hv; rank = r; kind = k;
+            } else {
+                // The reference folds the leaves in pre-order (= rank order) and takes a leaf only if BOTH its own box's entry
+                // distance and its hit distance lie below the closest hit so far (bvh.rs:213 `d >= closest` skips it otherwise,
+                // world.rs:288-296 strict `<`).  With m = max(hit distance, box entry distance) that is "m < closest": a later leaf
+                // beats an earlier hit only with m below its distance - also when rounding puts a hit a few ulps in FRONT of its own
+                // box (a triangle lying in a face of its box, e.g. coplanar with a plane of the scene).  This walk meets the
+                // candidates in another order, so it applies the same rule pairwise, ordered by rank (planes come before every leaf).
+                const float m_new = fmaxf(ht, stack.dist(sp));
+                bool take;
+                if (kind == KIND_MISS) take = true;
+                else if (kind == KIND_PLANE || rank < r) take = m_new < closest;   // the current hit comes first in the reference's order
+                else take = !(stack.best_m() < ht);                               // the new one comes first: the current one survives only if it would have been taken after it
+                if (take) { closest = ht; cull = ht * CULL_SLACK; stack.set_best_m(m_new); t = ht; u = hu; v = hv; rank = r; kind = k; }
             }
         }
         pop(stack);

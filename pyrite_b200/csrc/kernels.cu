@@ -398,6 +398,10 @@ struct SharedStack {
     __device__ __forceinline__ int2 at(int i) const { return i < SHARED_STACK ? entries[i * TRACE_THREADS] : deep[i - SHARED_STACK]; }
     __device__ __forceinline__ int code(int i) const { return at(i).x; }
     __device__ __forceinline__ float dist(int i) const { return __int_as_float(at(i).y); }
+    // one more row behind the stack: max(hit distance, box entry distance) of the current closest hit (written when a hit is
+    // taken, read only when a later candidate precedes it in the reference's order) - kept out of the registers of the walk
+    __device__ __forceinline__ void set_best_m(float v) { entries[SHARED_STACK * TRACE_THREADS].y = __float_as_int(v); }
+    __device__ __forceinline__ float best_m() const { return __int_as_float(entries[SHARED_STACK * TRACE_THREADS].y); }
 };
 
 // Persistent warps with lane-level refill: a warp reserves 32 ray indices with one atomicAdd and hands
@@ -408,7 +412,7 @@ template <bool STATS, class Emit>
 __device__ __forceinline__ void trace_persistent(const SceneView& sc, const Ray* rays, uint32_t n_main, uint32_t n_shadow, uint32_t shadow_offset,
                                                  uint32_t* cursor, DeviceCounters* counters, bool closest_only, uint32_t refill_min, uint32_t steps,
                                                  Emit& emit) {
-    __shared__ int2 smem_stack[SHARED_STACK * TRACE_THREADS];
+    __shared__ int2 smem_stack[(SHARED_STACK + 1) * TRACE_THREADS];
     SharedStack stack;
     stack.entries = smem_stack + threadIdx.x;
     const uint32_t total = n_main + n_shadow;
@@ -762,6 +766,20 @@ __global__ void k_camera_sample(const SceneView sc, uint64_t seed, uint32_t tile
     out[10 + MAX_SPECTRUM_SAMPLES] = __uint_as_float(pick);
 }
 
+// tools/first_divergence.py: ONE path sample of the camera-to-light integrator run depth-first by a single thread
+// (debug_path_simple in shading.cuh).  A diagnostic seam; nothing on the render path calls it.
+__global__ void k_debug_path(const __grid_constant__ SceneView sc, uint64_t seed, uint32_t tile, uint64_t sample, uint32_t max_bounces, uint32_t* records,
+                             uint32_t* counts, float* exposed, float* position2, Ray* rays, Hit* hits, PendingLight* pend, uint32_t* kinds) {
+    // rays / hits / pend / kinds: global scratch (the stage functions move these records with ld/st.global)
+    PathState ps;
+    bind_spectral(sc, ps);
+    ps.pend = pend;
+    ps.bd = nullptr;
+    ShadeOut out;
+    out.stage_base = sc.vm_regs * WAVE_THREADS;
+    debug_path_simple(sc, seed, tile, sample, max_bounces, records, counts, exposed, position2, rays, hits, kinds, ps, out);
+}
+
 }  // namespace
 
 #include "bdpt_kernels.inl"
@@ -825,6 +843,18 @@ void launch_develop(const SceneView& sc, const float* film, const float* develop
 void launch_camera_sample(const SceneView& sc, uint64_t seed, uint32_t tile, uint64_t sample, float* out, cudaStream_t s) {
     k_camera_sample<<<1, 1, 0, s>>>(sc, seed, tile, sample, out);
 }
+
+void launch_debug_path(const SceneView& sc, uint64_t seed, uint32_t tile, uint64_t sample, uint32_t max_bounces, uint32_t* records, uint32_t* counts,
+                       float* exposed, float* position2, void* scratch, cudaStream_t s) {
+    // scratch: (1 + MAX_LIGHT_SAMPLES) rays, as many hits, MAX_LIGHT_SAMPLES pending lights, 1 + MAX_LIGHT_SAMPLES kinds (32-byte aligned)
+    Ray* rays = (Ray*)scratch;
+    Hit* hits = (Hit*)(rays + 1 + MAX_LIGHT_SAMPLES);
+    PendingLight* pend = (PendingLight*)(hits + 1 + MAX_LIGHT_SAMPLES);
+    uint32_t* kinds = (uint32_t*)(pend + MAX_LIGHT_SAMPLES);
+    cudaFuncSetAttribute(k_debug_path, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wave_smem(sc));
+    k_debug_path<<<1, 1, wave_smem(sc), s>>>(sc, seed, tile, sample, max_bounces, records, counts, exposed, position2, rays, hits, pend, kinds);
+}
+size_t debug_path_scratch_bytes() { return (size_t)(2 * (1 + MAX_LIGHT_SAMPLES) + MAX_LIGHT_SAMPLES) * 32 + (1 + MAX_LIGHT_SAMPLES) * sizeof(uint32_t); }
 
 size_t path_state_bytes() { return sizeof(PathCore); }
 size_t pending_light_bytes() { return sizeof(PendingLight); }

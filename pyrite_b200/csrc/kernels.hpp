@@ -105,6 +105,11 @@ void launch_white_scan(const SceneView& sc, float* develop_params, cudaStream_t 
 void launch_develop(const SceneView& sc, const float* film, const float* develop_params, float step_size, float* xyz, uint8_t* srgb, cudaStream_t s);
 void launch_camera_sample(const SceneView& sc, uint64_t seed, uint32_t tile, uint64_t sample, float* out /* 2 + 8 + 16 + 1 floats */, cudaStream_t s);
 
+void launch_debug_path(const SceneView& sc, uint64_t seed, uint32_t tile, uint64_t sample, uint32_t max_bounces, uint32_t* records /* 20 words each */,
+                       uint32_t* counts /* bounces, exposed */, float* exposed /* 16 x (brightness, wavelength) */, float* position2, void* scratch /* debug_path_scratch_bytes() */,
+                       cudaStream_t s);
+size_t debug_path_scratch_bytes();
+
 size_t path_state_bytes();
 size_t pending_light_bytes();
 size_t bidir_state_bytes();

@@ -661,6 +661,65 @@ PYR_HD void shade_simple(const SceneView& sc, PathState& ps, const Ray* main_ray
 }
 
 
+// ---------------------------------------------------------------- diagnostic: one path sample, depth-first
+// tools/first_divergence.py: one `render_tile` iteration (simple.rs:87-139) for path sample (tile, sample) with the very
+// stage functions the wavefront uses (generate_simple, trace_ray, camera_step), recording per bounce what the oracle's
+// checker records for the same sample - 20 words: kind, prim_id, t, u, v, incident[3], position[3], normal[3], out[3], visibility
+// rays cast, Xorshift `w` after the bounce, 1 if a surface bounce was pushed - and the exposed (brightness, wavelength)
+// pairs.  `rays` / `hits` / `kinds` hold 1 + MAX_LIGHT_SAMPLES records (global memory on the device: camera_step moves
+// them with ld/st.global); `ps` comes with its per-wavelength arrays and pending-light storage bound.
+struct DebugHooks {
+    v3 position, normal;
+    bool surface;
+    PYR_HD void contribute_done(PathState&) {}
+    PYR_HD void pushed_emission(PathState&) {}
+    PYR_HD void pushed_surface(PathState&, bool, v3 p, v3 n, float) { position = p; normal = n; surface = true; }
+};
+PYR_HD void debug_path_simple(const SceneView& sc, uint64_t seed, uint32_t tile, uint64_t sample, uint32_t max_bounces, uint32_t* records, uint32_t* counts,
+                              float* exposed, float* position2, Ray* rays, Hit* hits, uint32_t* kinds, PathState& ps, ShadeOut& out) {
+    generate_simple(sc, seed, tile, sample, ps, out.main);
+    ps.flags |= PS_ALIVE;
+    out.has_main = 1; out.n_shadow = 0; out.alive = 1;
+    position2[0] = ps.pos[0]; position2[1] = ps.pos[1];
+    PathCounters pc;
+    pc.de_evals = 0; pc.de_iters = 0;
+    uint32_t n_bounces = 0;
+    bool more = true;
+    while (more) {
+        const bool had_main = out.has_main != 0;
+        if (had_main) { Hit h; trace_ray<false>(sc, out.main, h, nullptr); rays[0] = out.main; hits[0] = h; }
+        for (uint32_t j = 0; j < out.n_shadow; ++j) {
+            const Ray r = out.get_shadow(j);
+            Hit h;
+            trace_ray<false>(sc, r, h, nullptr);
+            rays[1 + j] = r; hits[1 + j] = h; kinds[1 + j] = h.kind;
+        }
+        DebugHooks hooks;
+        hooks.surface = false;
+        hooks.position = mk3(0, 0, 0); hooks.normal = mk3(0, 0, 0);
+        more = camera_step(sc, ps, rays, hits, rays + 1, kinds + 1, out, pc, hooks);
+        if (had_main) {
+            if (n_bounces < max_bounces) {
+                uint32_t* r = records + 20 * n_bounces;
+                const Hit h = hits[0];
+                r[0] = h.kind;
+                r[1] = h.kind == KIND_MISS ? 0xFFFFFFFFu : (h.kind == KIND_PLANE ? h.rank : prim_object(sc.prims[h.rank]));
+                r[2] = f_bits(h.kind == KIND_MISS ? 0.0f : h.t); r[3] = f_bits(h.kind == KIND_MISS ? 0.0f : h.u); r[4] = f_bits(h.kind == KIND_MISS ? 0.0f : h.v);
+                r[5] = f_bits(rays[0].d[0]); r[6] = f_bits(rays[0].d[1]); r[7] = f_bits(rays[0].d[2]);
+                r[8] = f_bits(hooks.position.x); r[9] = f_bits(hooks.position.y); r[10] = f_bits(hooks.position.z);
+                r[11] = f_bits(hooks.normal.x); r[12] = f_bits(hooks.normal.y); r[13] = f_bits(hooks.normal.z);
+                const bool next = out.has_main != 0;
+                r[14] = f_bits(next ? out.main.d[0] : 0.0f); r[15] = f_bits(next ? out.main.d[1] : 0.0f); r[16] = f_bits(next ? out.main.d[2] : 0.0f);
+                r[17] = out.n_shadow; r[18] = ps.rng.w; r[19] = hooks.surface ? 1u : 0u;
+            }
+            ++n_bounces;
+        }
+    }
+    const uint32_t n = (ps.flags & PS_USE_ADDITIONAL) ? sc.renderer.spectrum_samples : 1u;
+    for (uint32_t k = 0; k < n; ++k) { exposed[2 * k] = ps.bright[k]; exposed[2 * k + 1] = ps.wl[k]; }
+    counts[0] = n_bounces; counts[1] = n;
+}
+
 // ---------------------------------------------------------------- develop (main.rs:190-238, 313-418)
 struct DevelopParams { float white_max, d65_max, step_size; uint32_t pad; };
 

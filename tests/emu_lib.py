@@ -49,6 +49,7 @@ def lib():
         L.emu_develop.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
         L.emu_run_program.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         L.emu_camera_sample.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.emu_debug_path.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -121,6 +122,15 @@ class Emu:
         srgb = np.empty((h, w, 3), np.uint8)
         self.L.emu_develop(self.h, step_size, _ptr(xyz), _ptr(srgb))
         return xyz, srgb
+
+    def debug_path(self, seed, tile, sample, max_bounces=64):
+        """One path sample of the camera-to-light integrator, depth-first: (records[n, 20] u32, exposed[m, 2] f32, position[2])."""
+        rec = np.zeros((max_bounces, 20), np.uint32)
+        exposed = np.zeros((16, 2), np.float32)
+        pos = np.zeros(2, np.float32)
+        nb, ne = C.c_uint32(), C.c_uint32()
+        self.L.emu_debug_path(self.h, seed, tile, sample, max_bounces, _ptr(rec), C.byref(nb), _ptr(exposed), C.byref(ne), _ptr(pos))
+        return rec[:min(nb.value, max_bounces)], exposed[:ne.value], pos
 
     def camera_sample(self, seed, tile, sample, spectrum_samples):
         pos = np.zeros(2, np.float32)

@@ -145,6 +145,26 @@ int emu_render(void* h, uint64_t seed, uint32_t spp_override, uint32_t offset, u
         return 1;
     }
 }
+// tools/first_divergence.py --backend emu: the product's depth-first diagnostic (shading.cuh debug_path_simple) on the CPU
+void emu_debug_path(void* h, uint64_t seed, uint32_t tile, uint64_t sample, uint32_t max_bounces, uint32_t* records, uint32_t* n_bounces,
+                    float* exposed, uint32_t* n_exposed, float* position2) {
+    Emu* e = (Emu*)h;
+    std::vector<Ray> rays(1 + MAX_LIGHT_SAMPLES);
+    std::vector<Hit> hits(rays.size());
+    std::vector<uint32_t> kinds(rays.size());
+    std::vector<PendingLight> pend(MAX_LIGHT_SAMPLES);
+    std::vector<float> spectral(3 * MAX_SPECTRUM_SAMPLES);
+    PathState ps;
+    ps.wl.base = spectral.data(); ps.bright.base = spectral.data() + MAX_SPECTRUM_SAMPLES; ps.refl.base = spectral.data() + 2 * MAX_SPECTRUM_SAMPLES;
+    ps.pend = pend.data();
+    ps.bd = nullptr;
+    ShadeOut out;
+    out.stage_base = 0;
+    uint32_t counts[2] = {0, 0};
+    debug_path_simple(e->view, seed, tile, sample, max_bounces, records, counts, exposed, position2, rays.data(), hits.data(), kinds.data(), ps, out);
+    *n_bounces = counts[0]; *n_exposed = counts[1];
+}
+
 uint64_t emu_rays(void* h) { return ((Emu*)h)->rays; }
 void emu_film(void* h, float* out) { Emu* e = (Emu*)h; memcpy(out, e->film.data(), e->film.size() * sizeof(float)); }
 void emu_set_film(void* h, const float* in) { Emu* e = (Emu*)h; memcpy(e->film.data(), in, e->film.size() * sizeof(float)); }

@@ -40,22 +40,29 @@ class RenderOpts(C.Structure):
                 ("reset_film", C.c_int32)]
 
 
-def build(force: bool = False) -> Path:
+# variants: "glibc" = the reference's arithmetic (parity tests); "double" = shading-side libm in double, rounded once, like
+# the device code (attribution of film differences); "native" = -O3 -march=native -flto, built on the box that runs it
+# (bench.py's CPU baseline legs only: the reference's own release profile)
+VARIANTS = {"glibc": "liboracle.so", "double": "liboracle_dbl.so", "native": "liboracle_native.so"}
+
+
+def build(force: bool = False, variant: str = "glibc") -> Path:
+    target = ORACLE_DIR / VARIANTS[variant]
     srcs = list(ORACLE_DIR.glob("*.hpp")) + list(ORACLE_DIR.glob("*.cpp")) + [ORACLE_DIR / "Makefile"]
-    stale = not LIB_PATH.exists() or any(s.stat().st_mtime > LIB_PATH.stat().st_mtime for s in srcs)
+    stale = not target.exists() or any(s.stat().st_mtime > target.stat().st_mtime for s in srcs)
     if force or stale:
-        subprocess.run(["make", "-C", str(ORACLE_DIR), "-B" if force else "-s"], check=True, capture_output=True)
-    return LIB_PATH
+        subprocess.run(["make", "-C", str(ORACLE_DIR), target.name] + (["-B"] if force else ["-s"]), check=True, capture_output=True)
+    return target
 
 
-_lib = None
+_libs = {}
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        build()
-        L = C.CDLL(str(LIB_PATH))
+def lib(variant: str = "glibc"):
+    if variant not in _libs:
+        L = C.CDLL(str(build(variant=variant)))
+        L.pyro_libm_mode.restype = C.c_int
+        assert L.pyro_libm_mode() == (1 if variant == "double" else 0)
         L.pyro_last_error.restype = C.c_char_p
         L.pyro_last_render_seconds.restype = C.c_double
         L.pyro_last_render_seconds.argtypes = [C.c_void_p]
@@ -72,8 +79,9 @@ def lib():
         L.pyro_film_develop.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_int]
         L.pyro_bvh_leaf_order.argtypes = [C.c_void_p, C.c_void_p]
         L.pyro_camera_sample.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-        _lib = L
-    return _lib
+        L.pyro_debug_path.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _libs[variant] = L
+    return _libs[variant]
 
 
 class OracleError(RuntimeError):
@@ -87,8 +95,8 @@ def _ptr(a: np.ndarray):
 class Oracle:
     """One loaded project (the equivalent of the reference after `parse_project`, main.rs:111-134)."""
 
-    def __init__(self, ir: bytes):
-        self.L = lib()
+    def __init__(self, ir: bytes, variant: str = "glibc"):
+        self.L = lib(variant)
         self.h = C.c_void_p()
         buf = (C.c_char * len(ir)).from_buffer_copy(ir)
         if self.L.pyro_load(buf, len(ir), C.byref(self.h)) != 0:
@@ -157,6 +165,15 @@ class Oracle:
         srgb = np.empty((i.height, i.width, 3), dtype=np.uint8)
         self._check(self.L.pyro_film_develop(self.h, step_size, _ptr(xyz), _ptr(srgb), threads or self.threads))
         return xyz, srgb
+
+    def debug_path(self, seed, tile, sample, max_bounces=64, eager_emissive_draw=True):
+        """One `render_tile` iteration of simple.rs with per-bounce records: (records[n, 20] u32, exposed[m, 2] f32, position[2])."""
+        rec = np.zeros((max_bounces, 20), np.uint32)
+        exposed = np.zeros((16, 2), np.float32)
+        pos = np.zeros(2, np.float32)
+        nb, ne = C.c_uint32(), C.c_uint32()
+        self._check(self.L.pyro_debug_path(self.h, seed, int(eager_emissive_draw), tile, sample, max_bounces, _ptr(rec), C.byref(nb), _ptr(exposed), C.byref(ne), _ptr(pos)))
+        return rec[:min(nb.value, max_bounces)], exposed[:ne.value], pos
 
     def bvh_leaf_order(self) -> np.ndarray:
         out = np.empty(self.info.n_objects, dtype=np.uint32)
