@@ -147,6 +147,21 @@ pyr_status pyr_film_upload(pyr_ctx* ctx, const float* acc_weight_in);
 /* Device address and byte size of the film, for the one NCCL reduction of the multi-GPU path. */
 pyr_status pyr_film_device_ptr(pyr_ctx* ctx, void** d_ptr, size_t* bytes);
 
+/* Multi-GPU (no counterpart in the reference, which renders on the host's threads, renderer/mod.rs:77-111): one process
+ * and one context per GPU, rank r of n renders path samples r, r+n, ... of every tile (pyr_render_params.sample_offset /
+ * sample_stride) and the films are summed once, over NCCL, before developing on the root - the film is additive, a bin's
+ * value is the ratio of its two sums (film.rs:132-185).  The library owns the communicator; the host only has to carry the
+ * 128-byte id from rank 0 to the other ranks (a file, a socket, MPI, torch.distributed ...).
+ *   pyr_comm_unique_id  rank 0: a fresh id (ncclGetUniqueId)
+ *   pyr_comm_init       every rank, collectively (ncclCommInitRank on the context's device)
+ *   pyr_film_reduce     every rank, collectively: film := sum over ranks, on `root` (root < 0: on every rank)
+ * NCCL (libnccl.so.2) is bound when the first of these is called; without it they fail with PYR_ERR_STATE. */
+#define PYR_COMM_ID_BYTES 128
+pyr_status pyr_comm_unique_id(uint8_t* id_out /* PYR_COMM_ID_BYTES */);
+pyr_status pyr_comm_init(pyr_ctx* ctx, int32_t n_ranks, int32_t rank, const uint8_t* id /* PYR_COMM_ID_BYTES */);
+pyr_status pyr_film_reduce(pyr_ctx* ctx, int32_t root);
+pyr_status pyr_comm_destroy(pyr_ctx* ctx);
+
 /* The develop loop (main.rs:313-327: developed_pixels -> spectrum_to_xyz(step) -> x3.444 ->
  * LinSrgb::from_color -> into_encoding).  xyz_out[W*H*3] f32 and/or srgb_out[W*H*3] u8, either
  * may be NULL.  step_size 2.0 is the final image, 30.0 the preview (main.rs:274-279). */

@@ -8,6 +8,7 @@
 //   BVH                     spatial/bvh.rs
 //   world, lamps, camera    world.rs, lamp.rs, cameras.rs
 #pragma once
+#include <cstdlib>
 #include <algorithm>
 #include <array>
 #include <functional>
@@ -1241,6 +1242,10 @@ inline std::unique_ptr<World> world_from_project(Project project) {
                 Vec3 origin = ConstEval{P}.vec3(o.origin);
                 pl.n = normal;
                 pl.d = dot(origin, normal);
+                // SURVEY.md §9 Q1 is an inference (collision 0.20.1 is not vendored): `d = p.n` with `t = -(d + o.n)/(dir.n)` puts the
+                // surface through -origin.  PYRO_Q1_LITERAL=1 builds the other reading (surface through +origin) so that
+                // tools/reference_images.py can show which one the reference's own renders agree with.  Never set in parity tests.
+                if (const char* q1 = getenv("PYRO_Q1_LITERAL")) if (q1[0] == '1') pl.d = -pl.d;
                 pl.normal = Normal{normal, quat_from_mat3(Mat3::from_cols(binormal, tangent, normal))};
                 pl.material = (uint32_t)W->materials.size() - 1;
                 pl.id = (uint32_t)W->planes.size();

@@ -33,7 +33,7 @@ RENDER_TIMING = 2
 EXPORTS = [
     "pyr_init", "pyr_shutdown", "pyr_stream_set", "pyr_last_error", "pyr_project_load", "pyr_project_info_get", "pyr_trace", "pyr_trace_device",
     "pyr_trace_stats", "pyr_bvh_leaf_order", "pyr_render", "pyr_film_expose", "pyr_film_clear", "pyr_film_download", "pyr_film_upload",
-    "pyr_film_device_ptr", "pyr_film_develop", "pyr_camera_sample", "pyr_debug_path", "pyr_counters_get", "pyr_version",
+    "pyr_film_device_ptr", "pyr_comm_unique_id", "pyr_comm_init", "pyr_film_reduce", "pyr_comm_destroy", "pyr_film_develop", "pyr_camera_sample", "pyr_debug_path", "pyr_counters_get", "pyr_version",
 ]
 
 
@@ -103,6 +103,10 @@ def load_library(path: Optional[Path] = None):
     L.pyr_film_upload.argtypes = [vp, vp]
     L.pyr_film_device_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(sz)]
     L.pyr_film_develop.argtypes = [vp, C.c_float, vp, vp]
+    L.pyr_comm_unique_id.argtypes = [vp]
+    L.pyr_comm_init.argtypes = [vp, C.c_int32, C.c_int32, vp]
+    L.pyr_film_reduce.argtypes = [vp, C.c_int32]
+    L.pyr_comm_destroy.argtypes = [vp]
     L.pyr_camera_sample.argtypes = [vp, C.c_uint64, C.c_uint32, C.c_uint64, vp, vp, vp, vp]
     L.pyr_debug_path.argtypes = [vp, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, vp, vp, vp, vp, vp]
     L.pyr_counters_get.argtypes = [vp, C.POINTER(Counters), C.c_int32]
@@ -232,6 +236,29 @@ class Renderer:
         self._check(self.L.pyr_film_device_ptr(self.h, C.byref(ptr), C.byref(nbytes)))
         assert nbytes.value == int(np.prod(self.film_shape)) * 4
         return DeviceFilm(ptr.value, self.film_shape)
+
+    # -- multi-GPU: the library-owned NCCL communicator and the one film reduction
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """Rank 0: a fresh communicator id (128 bytes) to hand to every rank's `comm_init`."""
+        L = load_library()
+        buf = (C.c_uint8 * 128)()
+        status = L.pyr_comm_unique_id(buf)
+        if status != 0:
+            raise PyriteError(status, L.pyr_last_error(None).decode())
+        return bytes(buf)
+
+    def comm_init(self, n_ranks: int, rank: int, comm_id: bytes):
+        assert len(comm_id) == 128
+        buf = (C.c_uint8 * 128).from_buffer_copy(comm_id)
+        self._check(self.L.pyr_comm_init(self.h, n_ranks, rank, buf))
+
+    def film_reduce(self, root: int = 0):
+        """Collective: film := sum of the ranks' films on `root` (root < 0: everywhere)."""
+        self._check(self.L.pyr_film_reduce(self.h, root))
+
+    def comm_destroy(self):
+        self._check(self.L.pyr_comm_destroy(self.h))
 
     def develop(self, step_size: float = 2.0, want_xyz: bool = True, want_srgb: bool = True, out_xyz=None, out_srgb=None):
         """Film -> (XYZ f32, sRGB u8) images on the host.  `out_xyz` / `out_srgb`: caller-owned C-contiguous arrays of the

@@ -2,6 +2,8 @@
 // wavefront driver loop and the film / trace / camera seams.  No CPU fallback exists: every entry
 // point that computes launches kernels on the context's CUDA device.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include <cstdio>
 #include <cstring>
@@ -29,6 +31,46 @@ struct CudaError : std::runtime_error {
 
 std::string g_init_error;
 struct StateError : std::runtime_error { using std::runtime_error::runtime_error; };
+
+// NCCL is bound at the first pyr_comm_* call, not at load time: a single-GPU host needs no NCCL at all, and a host that
+// already carries one (PyTorch bundles its own libnccl.so.2) must not get a second copy - dlopen by soname returns the
+// one that is loaded.  Only the stable core API is used (present in every NCCL 2.x).
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    ncclResult_t (*GetVersion)(int*) = nullptr;
+};
+NcclApi& nccl() {
+    static NcclApi api = [] {
+        NcclApi a;
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+            a.handle = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+            if (a.handle) break;
+        }
+        if (!a.handle) return a;
+        a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(a.handle, "ncclGetUniqueId");
+        a.CommInitRank = (decltype(a.CommInitRank))dlsym(a.handle, "ncclCommInitRank");
+        a.CommDestroy = (decltype(a.CommDestroy))dlsym(a.handle, "ncclCommDestroy");
+        a.Reduce = (decltype(a.Reduce))dlsym(a.handle, "ncclReduce");
+        a.AllReduce = (decltype(a.AllReduce))dlsym(a.handle, "ncclAllReduce");
+        a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.handle, "ncclGetErrorString");
+        a.GetVersion = (decltype(a.GetVersion))dlsym(a.handle, "ncclGetVersion");
+        return a;
+    }();
+    if (!api.handle || !api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.Reduce || !api.AllReduce || !api.GetErrorString)
+        throw StateError("NCCL is not available (libnccl.so.2 could not be loaded): the multi-GPU film reduction needs it");
+    return api;
+}
+#define NC(call)                                                                                              \
+    do {                                                                                                      \
+        ncclResult_t r_ = (call);                                                                             \
+        if (r_ != ncclSuccess) throw CudaError(std::string(#call) + ": " + nccl().GetErrorString(r_));     \
+    } while (0)
 
 struct DeviceBuffer {
     void* p = nullptr;
@@ -73,6 +115,8 @@ struct pyr_ctx {
     bool develop_params_valid = false;
     pyr_counters host_counters{};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    ncclComm_t comm = nullptr;   // pyr_comm_init
+    int comm_ranks = 0, comm_rank = 0;
     unsigned long long* pinned = nullptr;  // [0] ray counts, [1] next sample, [2] live-slot count
 
     size_t film_floats() const { return (size_t)view.film.width * view.film.height * view.film.bins * 2; }
@@ -253,6 +297,7 @@ void pyr_shutdown(pyr_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm) { try { nccl().CommDestroy(ctx->comm); } catch (...) {} ctx->comm = nullptr; }
     DeviceBuffer* all[] = {&ctx->nodes, &ctx->prims, &ctx->tri_shade, &ctx->tri_frames, &ctx->planes, &ctx->marched, &ctx->materials,
                            &ctx->components, &ctx->programs, &ctx->code, &ctx->spectra, &ctx->spectrum_data, &ctx->textures, &ctx->texels,
                            &ctx->lamps, &ctx->tiles, &ctx->burns, &ctx->xyz, &ctx->d65, &ctx->film, &ctx->develop_params, &ctx->counters,
@@ -596,6 +641,58 @@ pyr_status pyr_film_device_ptr(pyr_ctx* ctx, void** d_ptr, size_t* bytes) {
         CU(cudaStreamSynchronize(ctx->stream));
         if (d_ptr) *d_ptr = ctx->film.p;
         if (bytes) *bytes = ctx->film_floats() * sizeof(float);
+    });
+}
+
+// ---- the one collective of the path: summing the films of the ranks (NCCL over NVLink)
+pyr_status pyr_comm_unique_id(uint8_t* id_out) {
+    if (!id_out) return fail(nullptr, PYR_ERR_INVALID, "null id buffer");
+    try {
+        static_assert(sizeof(ncclUniqueId) == PYR_COMM_ID_BYTES, "ncclUniqueId is 128 bytes");
+        ncclUniqueId id;
+        NC(nccl().GetUniqueId(&id));
+        memcpy(id_out, &id, sizeof(id));
+        return PYR_OK;
+    } catch (const StateError& e) {
+        return fail(nullptr, PYR_ERR_STATE, e.what());
+    } catch (const std::exception& e) {
+        return fail(nullptr, PYR_ERR_CUDA, e.what());
+    }
+}
+
+pyr_status pyr_comm_init(pyr_ctx* ctx, int32_t n_ranks, int32_t rank, const uint8_t* id) {
+    return guarded(ctx, [&] {
+        if (!id) throw ir::BuildError("null communicator id");
+        if (n_ranks < 1 || rank < 0 || rank >= n_ranks) throw ir::BuildError("bad rank / rank count");
+        if (ctx->comm) { NC(nccl().CommDestroy(ctx->comm)); ctx->comm = nullptr; }
+        ncclUniqueId uid;
+        memcpy(&uid, id, sizeof(uid));
+        NC(nccl().CommInitRank(&ctx->comm, n_ranks, uid, rank));
+        ctx->comm_ranks = n_ranks;
+        ctx->comm_rank = rank;
+    });
+}
+
+pyr_status pyr_comm_destroy(pyr_ctx* ctx) {
+    return guarded(ctx, [&] {
+        if (!ctx->comm) return;
+        CU(cudaStreamSynchronize(ctx->stream));
+        NC(nccl().CommDestroy(ctx->comm));
+        ctx->comm = nullptr;
+        ctx->comm_ranks = 0;
+    });
+}
+
+pyr_status pyr_film_reduce(pyr_ctx* ctx, int32_t root) {
+    return guarded(ctx, [&] {
+        need_project(ctx);
+        if (!ctx->comm) throw StateError("pyr_comm_init has not been called on this context");
+        if (root >= ctx->comm_ranks) throw ir::BuildError("root rank out of range");
+        // (accumulator, weight) pairs are summed BEFORE developing: a bin's value is the ratio of the two sums (film.rs:132-143)
+        float* film = ctx->film.as<float>();
+        if (root < 0) NC(nccl().AllReduce(film, film, ctx->film_floats(), ncclFloat32, ncclSum, ctx->comm, ctx->stream));
+        else NC(nccl().Reduce(film, film, ctx->film_floats(), ncclFloat32, ncclSum, root, ctx->comm, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
     });
 }
 

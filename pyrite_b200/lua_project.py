@@ -207,12 +207,35 @@ def _to_python(value, seen: Dict[int, Any], as_expr_hint: bool = False):
     return node
 
 
-def load_project(path, output=print) -> tuple:
-    """Evaluate `path` (a pyrite project.lua) and return (project_table, project_dir)."""
+def _install_host_functions(L: Interpreter):
+    """What the Rust side registers before it runs its DSL library (project/tables.rs:14-18): `assign_id` only."""
+    ids = {"next": 0}
+
+    def assign_id(t):
+        ids["next"] += 1
+        t.set("_id", ids["next"])
+
+    L.G.set("assign_id", lambda t: assign_id(t))
+
+
+def load_project(path, output=print, dsl_library=None) -> tuple:
+    """Evaluate `path` (a pyrite project.lua) and return (project_table, project_dir).
+
+    `dsl_library`: path of a Lua DSL library to run verbatim before the project file instead of the native DSL
+    (pyrite's own `src/project/lib.lua`, as `load_project` does, project/mod.rs:43-60) - used by the differential test
+    that checks the native DSL against it."""
     path = Path(path)
     project_dir = path.resolve().parent
     L = Interpreter(search_dirs=[project_dir], output=output)
-    _install_dsl(L)
+    try:
+        if dsl_library is None:
+            _install_dsl(L)
+        else:
+            _install_host_functions(L)
+            L.current_chunk = Path(dsl_library).name
+            L.run(Path(dsl_library).read_text(), Path(dsl_library).name)
+    except LuaError as e:
+        raise ProjectLoadError(f"error while running the DSL library: {e}") from e
     L.current_chunk = path.name
     try:
         result = L.run(path.read_text(), path.name)
@@ -228,9 +251,9 @@ def load_project(path, output=print) -> tuple:
     return table, project_dir
 
 
-def load_project_ir(path, output=print) -> bytes:
+def load_project_ir(path, output=print, dsl_library=None) -> bytes:
     """project.lua -> project IR blob for pyr_project_load."""
-    table, project_dir = load_project(path, output)
+    table, project_dir = load_project(path, output, dsl_library)
     try:
         return P.serialize_project(table, base_dir=project_dir)
     except P.ProjectError as e:

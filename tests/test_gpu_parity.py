@@ -5,17 +5,57 @@ Bars (BASELINE.json north_star / SURVEY.md §8d):
     distances within 1e-5 relative (triangles, spheres, planes: in practice bit-exact, the kernels
     are compiled without FMA contraction);
   * films on identical per-path RNG streams: mean luminance (CIE Y) within 1e-3 relative and
-    per-pixel RMSE(Y)/mean(Y) <= 1e-2 for mesh scenes.  Scenes whose shading calls libm
-    transcendentals per hit (normal-mapped / sphere-UV textures, sphere-traced fractals) differ from
-    glibc by ULPs on the device, which flips rare visibility / march-termination events; their bars
-    are: textures mean <= 1e-2 and <= 5 % of the pixels off by more than 5 % of the mean; fractals
-    mean <= 1e-2 and RMSE <= 1.5 x the RMSE between two independent-seed oracle renders.
+    per-pixel RMSE(Y)/mean(Y) <= 1e-2.  The device evaluates the shading-side transcendentals
+    (sin / cos / acos / atan2 / exp / pow) in double and rounds once, glibc's float functions differ
+    from that in the last bit for a few per cent of the arguments, and a last-bit difference in a
+    sampled direction decorrelates the rest of that path.  Every film is therefore compared with BOTH
+    oracle variants (oracle/pyro_math.hpp): against the double-rounded one the §8d bars hold as
+    stated; against the glibc one (the reference's arithmetic) the RMSE may reach what the two
+    oracle variants differ by between themselves, measured in the same test - i.e. the allowance is
+    the oracle's own sensitivity to libm's last bit, not a free parameter.  tools/first_divergence.py
+    shows the first differing value path by path;
+  * sphere-traced shapes (CUDA's float powf / acosf / ... inside the distance estimators, no double
+    variant exists): mean <= 1e-2 and RMSE <= 1.5 x the RMSE between two independent-seed oracle renders.
+Every observed number is also written to gpurun_out/parity_gpu.json (copied to profiles/parity_r2.json).
 """
+import json
+from pathlib import Path
+
 import numpy as np
 import pytest
 from conftest import BIDIR_NAMES, MARCHED_SCENES, SCENE_NAMES, scene_ir
 
 pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+RECORD = {}
+
+
+@pytest.fixture(scope="module", autouse=True)
+def parity_record():
+    yield RECORD
+    out = ROOT / "gpurun_out"
+    out.mkdir(exist_ok=True)
+    (out / "parity_gpu.json").write_text(json.dumps(RECORD, indent=1, sort_keys=True) + "\n")
+
+
+def film_triplet(name, xg, xo, xd):
+    """GPU vs oracle (glibc libm), GPU vs oracle (double-rounded libm), and the two oracle variants against each other."""
+    g = dict(zip(("mean_rel", "rmse_rel", "off5pct"), luminance_stats(xo, xg)))
+    d = dict(zip(("mean_rel", "rmse_rel", "off5pct"), luminance_stats(xd, xg)))
+    f = dict(zip(("mean_rel", "rmse_rel", "off5pct"), luminance_stats(xo, xd)))
+    RECORD.setdefault("films", {})[name] = {"gpu_vs_oracle_glibc": g, "gpu_vs_oracle_double": d, "oracle_glibc_vs_oracle_double": f}
+    print(f"{name}: GPU vs oracle[double libm] mean {d['mean_rel']:.2e} rmse {d['rmse_rel']:.2e} off {d['off5pct']:.2%} | "
+          f"GPU vs oracle[glibc] mean {g['mean_rel']:.2e} rmse {g['rmse_rel']:.2e} off {g['off5pct']:.2%} | "
+          f"oracle[glibc] vs oracle[double] rmse {f['rmse_rel']:.2e}")
+    return g, d, f
+
+
+def assert_film_bars(name, g, d, f):
+    # Against the oracle that rounds libm like the device does the films agree to float-accumulation level (observed on a B200:
+    # RMSE/mean <= 6e-7 on all 15 exact scenes), far inside the SURVEY.md §8d bars (mean 1e-3, RMSE 1e-2)
+    assert d["mean_rel"] <= 1e-5 and d["rmse_rel"] <= 1e-4, (name, d)
+    # against the reference's glibc arithmetic: no further than the oracle itself moves when only libm's last bit changes
+    assert g["mean_rel"] <= max(1e-3, 2.0 * f["mean_rel"]) and g["rmse_rel"] <= max(1e-2, 1.5 * f["rmse_rel"]), (name, g, f)
 
 EXACT_SCENES = ["cornell", "spheres", "diamonds", "textures", "rgb_emission", "snowflake", "dragon", "edge_portrait"]
 
@@ -94,6 +134,8 @@ def luminance_stats(xo, xg):
 
 @pytest.mark.parametrize("name", SCENE_NAMES)
 def test_films_on_identical_streams(name, gpu_renderer_factory, oracle_factory):
+    from oracle_lib import Oracle
+
     spp = 8 if name in MARCHED_SCENES else 16
     r, o = gpu_renderer_factory(name), oracle_factory(name)
     r.render(seed=5, spp=spp)
@@ -104,6 +146,15 @@ def test_films_on_identical_streams(name, gpu_renderer_factory, oracle_factory):
     xg, sg = r.develop()
     xo, so = o.develop()
     dmean, rmse, off = luminance_stats(xo, xg)
+    if name not in MARCHED_SCENES:
+        od = Oracle(scene_ir(name), "double")
+        od.render(seed=5, spp=spp)
+        g, d, f = film_triplet(name, xg, xo, od.develop()[0])
+        assert_film_bars(name, g, d, f)
+        assert np.mean(np.abs(sg.astype(int) - so.astype(int)) > 1) <= 0.01 + 2.0 * f["off5pct"] + (0.02 if f["rmse_rel"] > 1e-3 else 0.0)
+        c = r.counters()
+        assert c["path_samples"] > 0 and c["rays"] > 0 and c["kernel_launches"] > 0
+        return
     print(f"{name}: mean-Y rel err {dmean:.2e}, RMSE/mean {rmse:.2e}, pixels off by >5% {off:.2%}")
     if name in MARCHED_SCENES:
         # the ray-marched normal is a difference of nearly equal distance estimates (shapes/mod.rs:387-405), so device-vs-glibc
@@ -112,12 +163,8 @@ def test_films_on_identical_streams(name, gpu_renderer_factory, oracle_factory):
         xo2, _ = o.develop()
         _, floor, _ = luminance_stats(xo, xo2)
         print(f"{name}: oracle-vs-oracle noise floor RMSE/mean {floor:.2e}")
+        RECORD.setdefault("films", {})[name] = {"gpu_vs_oracle_glibc": {"mean_rel": dmean, "rmse_rel": rmse, "off5pct": off}, "oracle_independent_seed_rmse_rel": floor}
         assert dmean <= max(1e-2, 2.0 * floor / np.sqrt(xo.shape[0] * xo.shape[1])) and rmse <= 1.5 * floor
-    elif name == "textures":
-        assert dmean <= 1e-2 and off <= 0.05
-    else:
-        assert dmean <= 1e-3 and rmse <= 1e-2
-        assert np.mean(np.abs(sg.astype(int) - so.astype(int)) > 1) <= 0.01
     c = r.counters()
     assert c["path_samples"] > 0 and c["rays"] > 0 and c["kernel_launches"] > 0
 
@@ -125,6 +172,8 @@ def test_films_on_identical_streams(name, gpu_renderer_factory, oracle_factory):
 @pytest.mark.parametrize("name", BIDIR_NAMES)
 def test_bidirectional_films_on_identical_streams(name, gpu_renderer_factory, oracle_factory):
     """renderer/bidirectional.rs through the wavefront (lamp subpath, camera subpath, connections, light tracing)."""
+    from oracle_lib import Oracle
+
     r, o = gpu_renderer_factory(name), oracle_factory(name)
     spp = 8
     r.counters(reset=True)
@@ -135,18 +184,18 @@ def test_bidirectional_films_on_identical_streams(name, gpu_renderer_factory, or
     xo, so = o.develop()
     dmean, rmse, off = luminance_stats(xo, xg)
     rays_g, rays_o = r.counters()["rays"], o.counters()["rays"]
-    print(f"{name}: mean-Y rel err {dmean:.2e}, RMSE/mean {rmse:.2e}, pixels off by >5% {off:.2%}, rays gpu {rays_g} oracle {rays_o}")
+    print(f"{name}: rays gpu {rays_g} oracle {rays_o}")
     assert abs(rays_g - rays_o) <= 2e-3 * rays_o
     if name == "bd_cornell_fractal":
         o.render(seed=6, spp=spp)
         _, floor, _ = luminance_stats(xo, o.develop()[0])
+        RECORD.setdefault("films", {})[name] = {"gpu_vs_oracle_glibc": {"mean_rel": dmean, "rmse_rel": rmse, "off5pct": off}, "oracle_independent_seed_rmse_rel": floor}
         assert dmean <= 1e-2 and rmse <= 1.5 * floor
-    elif name in ("bd_c5", "bd_spheres"):   # textured / sphere-UV scenes: libm ULPs flip rare events (see module docstring)
-        assert dmean <= 1e-2 and off <= 0.05
-    elif name == "bd_glass_dragon":      # 12 dispersive refractions amplify any last-bit difference in a sampled direction
-        assert dmean <= 2e-3 and off <= 0.10
-    else:
-        assert dmean <= 1e-3 and rmse <= 2e-2
+        return
+    od = Oracle(scene_ir(name), "double")
+    od.render(seed=5, spp=spp)
+    g, d, f = film_triplet(name, xg, xo, od.develop()[0])
+    assert_film_bars(name, g, d, f)
 
 
 def test_sample_pass_sharding_is_additive(gpu_renderer_factory):
@@ -437,8 +486,8 @@ def test_cli_renders_a_project_lua(tmp_path):
 
     root = Path(__file__).resolve().parent.parent
     out = tmp_path / "render.png"
-    res = subprocess.run([sys.executable, "-m", "pyrite_b200", str(root / "tests" / "golden" / "scenes" / "orbs.lua"), "--seed", "1", "--out", str(out)],
-                         cwd=root, capture_output=True, text=True, timeout=300)
+    res = subprocess.run([sys.executable, "-m", "pyrite_b200", str(root / "tests" / "golden" / "scenes" / "orbs.lua"), "--seed", "1", "--out", str(out),
+                          "--spp", "32", "--no-preview"], cwd=root, capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stderr
     assert "Project loading" in res.stdout and "Rendering" in res.stdout and "Total" in res.stdout
     im = np.asarray(Image.open(out))
@@ -453,3 +502,110 @@ def test_cli_renders_a_project_lua(tmp_path):
     assert im2.shape == im.shape and abs(float(im2.mean()) - float(im.mean())) < 0.15 * float(im.mean())
     bad = subprocess.run([sys.executable, "-m", "pyrite_b200", str(tmp_path / "missing.lua")], cwd=root, capture_output=True, text=True, timeout=120)
     assert bad.returncode == 1 and "error while loading project file" in bad.stderr
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json configs C2-C5 at their real parameters (resolution, S, B, L, mesh size), a 4-spp fraction of the job on
+# identical per-path streams, GPU vs the oracle on the host cores.  (C1 at its full 64 spp: test_c1_full_config_film.)
+def _full_config_project(config):
+    from pyrite_b200 import scenes
+
+    if config == "C2":   # Stanford-dragon stand-in, 871,200 triangles, 1920x1080, simple, S=10 B=8 L=4
+        return scenes.dragon()
+    if config == "C3":   # diamonds.lua as shipped (dispersion, S=1, B=256, thin lens) at 1920x1080
+        return scenes.diamonds(width=1920, height=1080)
+    if config == "C4":   # Mandelbulb + cubic quaternion Julia, 3840x2160
+        return scenes.fractals()
+    if config == "C5":   # textured Cornell box + dragon stand-in, bidirectional, 3840x2160
+        return scenes.bdpt_cornell_dragon()
+    raise KeyError(config)
+
+
+@pytest.mark.parametrize("config", ["C2", "C3", "C4", "C5"])
+def test_full_config_films(config):
+    from oracle_lib import Oracle
+
+    from pyrite_b200 import api, project, scenes
+
+    spp = 4
+    ir = project.serialize_project(_full_config_project(config))
+    o = Oracle(ir)
+    with api.Renderer(0) as r:
+        r.load(ir)
+        info = r.info
+        secs_gpu = r.render(seed=77, spp=spp)
+        cg = r.counters()
+        xg, sg = r.develop()
+    o.counters(reset=True)
+    secs_cpu = o.render(seed=77, spp=spp)
+    co = o.counters()
+    xo, so = o.develop()
+    entry = {"resolution": [int(info.width), int(info.height)], "spp": spp, "objects": int(info.n_objects), "gpu_seconds": secs_gpu, "oracle_seconds": secs_cpu,
+             "oracle_threads": o.threads, "rays_gpu": cg["rays"], "rays_oracle": co["rays"]}
+    assert cg["path_samples"] == co["path_samples"] == info.width * info.height * spp
+    if config == "C4":
+        # sphere tracing: tolerance-level parity, measured against the oracle's own independent-seed noise at the same spp
+        # (per-pixel noise does not depend on the resolution, so the floor comes from a quarter-resolution pair)
+        dmean, rmse, off = luminance_stats(xo, xg)
+        small = Oracle(project.serialize_project(scenes.fractals(width=960, height=540)))
+        small.render(seed=77, spp=spp)
+        xa = small.develop()[0]
+        small.render(seed=78, spp=spp)
+        _, floor, _ = luminance_stats(xa, small.develop()[0])
+        entry.update({"gpu_vs_oracle_glibc": {"mean_rel": dmean, "rmse_rel": rmse, "off5pct": off}, "oracle_independent_seed_rmse_rel": floor})
+        RECORD.setdefault("full_configs", {})[config] = entry
+        print(f"{config}: {entry}")
+        assert abs(cg["rays"] - co["rays"]) <= 5e-3 * co["rays"]
+        assert dmean <= 1e-2 and rmse <= 1.5 * floor
+        return
+    od = Oracle(ir, "double")
+    od.render(seed=77, spp=spp)
+    g, d, f = film_triplet(config, xg, xo, od.develop()[0])
+    entry.update({"gpu_vs_oracle_glibc": g, "gpu_vs_oracle_double": d, "oracle_glibc_vs_oracle_double": f})
+    RECORD.setdefault("full_configs", {})[config] = entry
+    print(f"{config}: {entry}")
+    assert abs(cg["rays"] - co["rays"]) <= 2e-3 * co["rays"]
+    assert_film_bars(config, g, d, f)
+
+
+@pytest.mark.parametrize("name", ["spheres", "diamonds", "colors", "cornell", "snowflake"])
+def test_reference_example_images(name):
+    """SURVEY.md §8(c) pin (3): the reference's own unmodified project files (fixtures made by tools/reference_images.py), rendered at
+    their own spp, against the example images the reference ships - framing and structure only (see the tool's docstring for why
+    radiometry cannot be pinned by those images)."""
+    import sys
+
+    sys.path.insert(0, str(ROOT / "tools"))
+    import reference_images as ri
+
+    stats = ri.compare(name, ri.render(name, "gpu", 0))
+    RECORD.setdefault("reference_example_images", {})[name] = stats
+    print(f"{name}: {stats}")
+    bars = {"spheres": (0.98, None), "diamonds": (0.90, 0.5), "colors": (0.95, None), "cornell": (0.75, 0.6), "snowflake": (None, None)}[name]
+    if bars[0] is not None:
+        assert stats["pearson_log_luminance"] >= bars[0]
+        assert stats["pearson_log_luminance"] > stats["pearson_if_mirrored"]   # a mirrored camera convention (SURVEY.md §9 Q16) fits worse
+    if bars[1] is not None:
+        assert stats["pearson_if_mirrored"] <= bars[1]
+
+
+@pytest.mark.parametrize("name", ["textures", "spheres", "dragon", "cornell"])
+def test_first_divergence_on_the_gpu(name):
+    """tools/first_divergence.py, GPU vs both oracle variants: against the double-rounded libm nothing may differ before the
+    exposed brightness (float-level), against glibc's libm the first difference must be an ulp-level value, never a hit id."""
+    import sys
+
+    sys.path.insert(0, str(ROOT / "tools"))
+    import first_divergence
+
+    n = 4000
+    rep_d = first_divergence.run(name, "gpu", "double", n, 5, 2)
+    rep_g = first_divergence.run(name, "gpu", "glibc", n, 5, 2)
+    RECORD.setdefault("first_divergence", {})[name] = {"vs_oracle_double": rep_d, "vs_oracle_glibc": rep_g}
+    print(f"{name}: vs double-rounded libm {rep_d['diverged']} of {n} paths differ {rep_d['first_differing_field']}; "
+          f"vs glibc {rep_g['diverged']} of {n} {rep_g['first_differing_field']} max ulps {rep_g['max_ulps_at_first_difference']}")
+    structural = [k for k in rep_d["first_differing_field"] if k.split("@")[0] in ("kind", "prim_id", "rng_w", "path_length", "exposed_count")]
+    assert not structural, rep_d
+    assert rep_d["diverged_fraction"] <= 0.02, rep_d
+    first_is_id = sum(v for k, v in rep_g["first_differing_field"].items() if k.split("@")[0] in ("kind", "prim_id"))
+    assert first_is_id <= 0.002 * n, rep_g

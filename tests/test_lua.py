@@ -197,3 +197,55 @@ def test_every_reference_project_file_evaluates():
         except project.ProjectError as e:
             # dragon.obj and textures/fabric/* are absent from the reference (.MISSING_LARGE_BLOBS)
             assert "dragon.obj" in str(e) or "fabric" in str(e), f"{f}: {e}"
+
+
+# ---------------------------------------------------------------------------------------------
+# Differential test of the native DSL against pyrite's own DSL library, run verbatim.
+REFERENCE_LIB = Path("/root/reference/pyrite/src/project/lib.lua")
+REFERENCE_PROJECTS = ["colors/colors.lua", "cornell/cornell.lua", "diamonds/diamonds.lua", "dragon/dragon.lua", "rgb_emission/rgb_emission.lua",
+                      "rgb_reflection/rgb_reflection.lua", "snowflake/snowflake.lua", "spheres/spheres.lua", "textures/textures.lua"]
+
+
+def _canonical(value, seen):
+    """Project table -> nested tuples; every node is numbered at its first visit so that shared nodes (table identity is what
+    `typed_nodes` interns on, project/tables.rs:14-18) must be shared in the same places."""
+    if isinstance(value, dict):
+        if id(value) in seen:
+            return ("ref", seen[id(value)])
+        seen[id(value)] = len(seen)
+        return (type(value).__name__, seen[id(value)], tuple((k, _canonical(value[k], seen)) for k in sorted(value)))
+    if isinstance(value, list):
+        return ("list", tuple(_canonical(v, seen) for v in value))
+    if isinstance(value, float) and value == int(value):
+        return float(value)
+    return value
+
+
+@pytest.mark.skipif(not REFERENCE_LIB.exists(), reason="the reference tree is only present in the build container")
+@pytest.mark.parametrize("rel", REFERENCE_PROJECTS + ["<orbs>"])
+def test_native_dsl_matches_the_reference_lib_lua(rel):
+    """pyrite's `src/project/lib.lua` runs VERBATIM in pyrite_b200.lua (the host only registers `assign_id`, as
+    project/tables.rs:14-18 does) and every project the reference ships evaluates to the same table - same fields, same
+    values, same sharing of nodes - as through the native DSL of lua_project._install_dsl; where the assets exist the
+    serialised project IR is byte-identical too."""
+    path = SCENES / "orbs.lua" if rel == "<orbs>" else REFERENCE / rel
+    native, _ = lua_project.load_project(path)
+    verbatim, _ = lua_project.load_project(path, dsl_library=REFERENCE_LIB)
+    assert _canonical(native, {}) == _canonical(verbatim, {})
+    if rel not in ("dragon/dragon.lua", "textures/textures.lua"):  # dragon.obj and fabric/*.jpg are absent from the reference itself
+        assert lua_project.load_project_ir(path) == lua_project.load_project_ir(path, dsl_library=REFERENCE_LIB)
+
+
+@pytest.mark.parametrize("name", ["spheres", "diamonds", "colors", "snowflake", "cornell"])
+def test_reference_scene_fixtures(name):
+    """tests/golden/reference_scenes/*.ir.gz (made by tools/reference_images.py --make-fixtures from the unmodified reference
+    projects) travel to the GPU box; here they must still be what the loader produces, and the oracle must accept them."""
+    import gzip
+
+    from oracle_lib import Oracle
+
+    blob = gzip.decompress((SCENES.parent / "reference_scenes" / f"{name}.ir.gz").read_bytes())
+    if REFERENCE.exists():
+        assert blob == lua_project.load_project_ir(REFERENCE / name / f"{name}.lua")
+    o = Oracle(blob)
+    assert o.info.width == 512 and o.info.n_objects > 0

@@ -136,3 +136,24 @@ def test_errors_mirror_the_reference():
 
 def test_hit_dtype_sizes():
     assert RAY_DTYPE.itemsize == 32 and HIT_DTYPE.itemsize == 20
+
+
+def test_eager_emissive_draw_is_distribution_neutral():
+    """The wavefront draws a shape lamp's emissive-component index before the visibility result, the reference
+    draws it only for unblocked samples (tracer.rs:381-400).  Same distribution, different stream: the oracle in the
+    reference's order and in the product's order must agree in mean luminance within the noise of independent renders."""
+    from conftest import scene_ir
+    from oracle_lib import Oracle
+
+    o = Oracle(scene_ir("spheres", width=32, height=24))   # one emissive sphere is the lamp
+    means = {}
+    for eager in (True, False):
+        ys = []
+        for seed in range(12):
+            o.render(seed=100 + seed, spp=64, eager_emissive_draw=eager, threads=4)
+            y = o.develop()[0][..., 1]
+            ys.append(float(np.minimum(y, 5 * y.mean()).mean()))
+        means[eager] = (np.mean(ys), np.std(ys) / np.sqrt(len(ys)))
+    diff = abs(means[True][0] - means[False][0])
+    sigma = float(np.hypot(means[True][1], means[False][1]))
+    assert diff <= 4 * sigma and diff <= 5e-3 * means[False][0], (means, diff, sigma)
