@@ -41,7 +41,7 @@ class RenderOpts(C.Structure):
 
 
 # variants: "glibc" = the reference's arithmetic (parity tests); "double" = shading-side libm in double, rounded once, like
-# the device code (attribution of film differences); "native" = -O3 -march=native -flto, built on the box that runs it
+# the device code (attribution of film differences); "native" = -O3 -march=native, built on the box that runs it
 # (bench.py's CPU baseline legs only: the reference's own release profile)
 VARIANTS = {"glibc": "liboracle.so", "double": "liboracle_dbl.so", "native": "liboracle_native.so"}
 
