@@ -335,7 +335,10 @@ def fixed_job(config: str, total_spp: int, small: bool, world: int, rank: int, l
                                      "accumulators_close": bool(np.allclose(together[..., 0], alone[..., 0], rtol=2e-4, atol=1e-5))}
         barrier(world)
     if rank == 0 and xyz is not None:
-        out["mean_luminance"] = float(xyz[..., 1].mean())
+        # a sample whose lamp-vertex BRDF is 0 exposes 0/0 (the reference's `brdf_in = x / x`, bidirectional.rs:365-372): such bins stay NaN there too
+        finite = np.isfinite(xyz[..., 1])
+        out["mean_luminance"] = float(xyz[..., 1][finite].mean()) if finite.any() else None
+        out["non_finite_pixels"] = int((~finite).sum())
     r.close()
     return out
 

@@ -107,7 +107,7 @@ struct pyr_ctx {
     DeviceBuffer nodes, prims, tri_shade, tri_frames, planes, marched, materials, components, programs, code, spectra, spectrum_data,
         textures, texels, lamps, tiles, burns, xyz, d65;
     DeviceBuffer film, develop_params, counters, scalars, tile_first;
-    DeviceBuffer paths, pend, bidir, rays[2], hits, shadow_kinds, march_queue[2], march_key, light_vertices, cam_vertices, bin_count, bin_first, bin_fill, bin_keys, bin_list, live_list;
+    DeviceBuffer paths, pend, bidir, rays[2], hits, shadow_kinds, march_queue[2], march_key, light_vertices, cam_vertices, bin_count, bin_first, bin_fill, bin_keys, bin_list, live_list, died_list;
     uint32_t shadow_per_path = 1;
     uint32_t march_capacity[2] = {0, 0};
     DeviceBuffer scratch_a, scratch_b;
@@ -120,11 +120,12 @@ struct pyr_ctx {
     unsigned long long* pinned = nullptr;  // [0] ray counts, [1] next sample, [2] live-slot count
 
     size_t film_floats() const { return (size_t)view.film.width * view.film.height * view.film.bins * 2; }
-    // scalars: [0..1] counts A {path rays, visibility rays}, [2..3] counts B, [4] trace cursor, [6..7] next_sample (u64), [8..9] march counts, [10..11] march cursors, [12..13] live-slot counts
+    // scalars: [0..1] counts A {path rays, visibility rays}, [2..3] counts B, [4] trace cursor, [6..7] next_sample (u64), [8..9] march counts, [10..11] march cursors, [12..13] live-slot counts, [14] died-slot count
     uint32_t* count(int i) const { return scalars.as<uint32_t>() + 2 * i; }
     uint32_t* cursor() const { return scalars.as<uint32_t>() + 4; }
     uint32_t* march_count() const { return scalars.as<uint32_t>() + 8; }
     uint32_t* live_count(int i) const { return scalars.as<uint32_t>() + 12 + i; }
+    uint32_t* died_count() const { return scalars.as<uint32_t>() + 14; }
     unsigned long long* next_sample() const { return (unsigned long long*)(scalars.as<uint32_t>() + 6); }
 };
 
@@ -200,6 +201,7 @@ void ensure_pool(pyr_ctx* ctx, uint32_t pool) {
     ctx->bin_keys.ensure((size_t)pool * sizeof(uint16_t));
     ctx->bin_list.ensure((size_t)pool * sizeof(uint32_t));
     ctx->live_list.ensure((size_t)pool * sizeof(uint32_t));
+    ctx->died_list.ensure(bidir ? (size_t)pool * sizeof(uint32_t) : 16);
     if (bidir) ctx->bidir.ensure((size_t)pool * bidir_state_bytes());
     ctx->rays[0].ensure(ray_cap * sizeof(Ray));
     ctx->rays[1].ensure(ray_cap * sizeof(Ray));
@@ -229,7 +231,7 @@ size_t pool_bytes_per_path(const pyr_ctx* ctx) {
     const RendererRec& R = ctx->view.renderer;
     const bool bidir = R.algorithm == 1;
     const size_t shadow = bidir ? (size_t)bdpt_stage_rays() : std::max<uint32_t>(R.light_samples, 1);
-    size_t b = path_state_bytes() + MAX_LIGHT_SAMPLES * pending_light_bytes() + 2 * sizeof(uint32_t) + sizeof(uint16_t) +
+    size_t b = path_state_bytes() + MAX_LIGHT_SAMPLES * pending_light_bytes() + (bidir ? 3 : 2) * sizeof(uint32_t) + sizeof(uint16_t) +
                (1 + shadow) * 2 * sizeof(Ray) + sizeof(Hit) + shadow * sizeof(uint32_t);
     if (ctx->view.n_marched) b += (1 + shadow) * (size_t)ctx->view.n_marched * sizeof(uint2) + sizeof(unsigned long long);
     if (bidir) b += bidir_state_bytes() + (size_t)(R.light_bounces + 1) * light_vertex_bytes() + (size_t)std::max<uint32_t>(R.bounces, 1) * cam_vertex_bytes();
@@ -301,7 +303,7 @@ void pyr_shutdown(pyr_ctx* ctx) {
     DeviceBuffer* all[] = {&ctx->nodes, &ctx->prims, &ctx->tri_shade, &ctx->tri_frames, &ctx->planes, &ctx->marched, &ctx->materials,
                            &ctx->components, &ctx->programs, &ctx->code, &ctx->spectra, &ctx->spectrum_data, &ctx->textures, &ctx->texels,
                            &ctx->lamps, &ctx->tiles, &ctx->burns, &ctx->xyz, &ctx->d65, &ctx->film, &ctx->develop_params, &ctx->counters,
-                           &ctx->scalars, &ctx->tile_first, &ctx->paths, &ctx->pend, &ctx->bidir, &ctx->bin_count, &ctx->bin_first, &ctx->bin_fill, &ctx->bin_keys, &ctx->bin_list, &ctx->live_list, &ctx->rays[0], &ctx->rays[1], &ctx->hits, &ctx->shadow_kinds, &ctx->march_queue[0], &ctx->march_queue[1], &ctx->march_key, &ctx->light_vertices, &ctx->cam_vertices,
+                           &ctx->scalars, &ctx->tile_first, &ctx->paths, &ctx->pend, &ctx->bidir, &ctx->bin_count, &ctx->bin_first, &ctx->bin_fill, &ctx->bin_keys, &ctx->bin_list, &ctx->live_list, &ctx->died_list, &ctx->rays[0], &ctx->rays[1], &ctx->hits, &ctx->shadow_kinds, &ctx->march_queue[0], &ctx->march_queue[1], &ctx->march_key, &ctx->light_vertices, &ctx->cam_vertices,
                            &ctx->scratch_a, &ctx->scratch_b};
     for (DeviceBuffer* b : all) b->release();
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -522,10 +524,12 @@ pyr_status pyr_render(pyr_ctx* ctx, const pyr_render_params* params, pyr_progres
                 a.live_list = ctx->live_list.as<uint32_t>();
                 a.live_count_in = ctx->live_count(cur);
                 a.live_count_out = ctx->live_count(nxt);
+                a.died_list = ctx->died_list.as<uint32_t>();
+                a.died_count = ctx->died_count();
                 a.bin_first = ctx->bin_first.as<uint32_t>();
                 a.bin_list = ctx->bin_list.as<uint32_t>();
                 launch_bin(a, bins, cluster_shift, R.algorithm == 1, s);
-                if (R.algorithm == 0) launch_wave_simple(ctx->view, a, s); else launch_wave_bidirectional(ctx->view, a, s);
+                if (R.algorithm == 0) launch_wave_simple(ctx->view, a, s); else launch_wave_bidirectional(ctx->view, a, ctx->sm_count, s);
                 if (timing) CU(cudaEventRecord(ctx->timing_events[3 * b + 1], s));
                 TraceArgs t{};
                 t.rays = ctx->rays[nxt].as<Ray>();
@@ -548,7 +552,7 @@ pyr_status pyr_render(pyr_ctx* ctx, const pyr_render_params* params, pyr_progres
                 if (timing) CU(cudaEventRecord(ctx->timing_events[3 * b + 2], s));
                 cur = nxt;
                 ++iterations;
-                launches += 5;
+                launches += R.algorithm == 0 ? 5 : 4 + wave_bidirectional_launches();
             }
             CU(cudaGetLastError());
             CU(cudaMemcpyAsync(&ctx->pinned[0], ctx->count(cur), 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));

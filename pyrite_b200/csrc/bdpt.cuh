@@ -65,11 +65,23 @@ struct alignas(32) CamVertex : CamVertexHead {
     float refl[MAX_SPECTRUM_SAMPLES];
 };
 
+// What one step asks to be traced next.  The visibility rays are not materialised per thread on the device (16 x 32 B of
+// thread-local memory): a step only COUNTS them (`n_shadow`, `shadow_kind`), the kernel reserves queue space for the block and
+// then writes them straight into the queue (write_staged), re-deriving them from the stored vertices.  On the host (CPU
+// emulation) they land in `shadow`.
+enum : uint32_t { SH_NONE = 0, SH_NEE = 1, SH_CONNECT = 2, SH_SPLAT = 3 };
 struct BidirOut {
-    uint32_t alive, has_main, n_shadow, pad;
+    uint32_t alive, has_main, n_shadow, shadow_kind;
     Ray main;
+#if !defined(__CUDA_ARCH__)
     Ray shadow[BDPT_STAGE];
+#endif
 };
+#if defined(__CUDA_ARCH__)
+#define PYR_STAGE_RAYS(out) static_cast<Ray*>(nullptr)
+#else
+#define PYR_STAGE_RAYS(out) (out).shadow
+#endif
 
 struct BidirCtx {
     LightVertex* lv;   // this path's lamp vertices
@@ -207,9 +219,12 @@ PYR_HD void finish_lamp_path(const SceneView& sc, PathState& ps, LightVertex* lv
     }
 }
 
-// Stage the visibility rays of connect_paths for camera vertex `conn_cam`, lamp vertices from `conn_light`.
-// Returns the number staged and leaves the next lamp index in ps.bd->conn_next.
-PYR_HD uint32_t stage_connections(const PathState& ps, const BidirCtx& cx, uint32_t from_light, Ray* rays, uint32_t* lamp_index, uint32_t& next) {
+// The connections of connect_paths (bidirectional.rs:310-398) for camera vertex `conn_cam`, lamp vertices from `from_light`, at
+// most BDPT_STAGE per iteration: f(j, i, geometry of lamp vertex i, unit direction, distance) is called for the j-th one.
+// Returns their number; `next` = the first lamp index that was not looked at.  The same walk stages the rays (count only, or
+// writing them), and evaluates them one iteration later, so nothing has to be remembered per ray.
+template <class F>
+PYR_HD uint32_t for_each_connection(const PathState& ps, const BidirCtx& cx, uint32_t from_light, uint32_t& next, F&& f) {
     const CamVertex& c = cx.cv[ps.bd->conn_cam];
     const v3 from = ld3(c.position), cn = ld3(c.normal);
     uint32_t n = 0, i = from_light;
@@ -225,30 +240,35 @@ PYR_HD uint32_t stage_connections(const PathState& ps, const BidirCtx& cx, uint3
         v3 dir = direction / distance;
         if (dot(cn, dir) <= 0.0f) continue;
         if (dot(v.normal, -dir) <= 0.0f) continue;
-        if (rays) rays[n] = make_ray(from, dir, 2, distance - DIST_EPSILON);  // blocked <=> a hit closer than distance - eps
-        if (lamp_index) lamp_index[n] = i;
+        f(n, i, v, from, dir, distance, sq_distance);
         ++n;
     }
     next = i;
     return n;
+}
+PYR_HD uint32_t stage_connections(const PathState& ps, const BidirCtx& cx, uint32_t from_light, Ray* rays, uint32_t& next) {
+    return for_each_connection(ps, cx, from_light, next, [&](uint32_t j, uint32_t, const VertexGeometry&, v3 from, v3 dir, float distance, float) {
+        if (rays) rays[j] = make_ray(from, dir, 2, distance - DIST_EPSILON);  // blocked <=> a hit closer than distance - eps
+    });
 }
 
 // Advance the connect phase until some rays are staged or every camera vertex is done.
 PYR_HD bool advance_connect(PathState& ps, const BidirCtx& cx, BidirOut& out) {
     while (ps.bd->conn_cam < ps.bd->n_cam_stored) {
         uint32_t next;
-        uint32_t n = stage_connections(ps, cx, ps.bd->conn_light, out.shadow, nullptr, next);
-        if (n) { ps.bd->conn_next = next; out.n_shadow = n; out.alive = 1; return true; }
+        uint32_t n = stage_connections(ps, cx, ps.bd->conn_light, PYR_STAGE_RAYS(out), next);
+        if (n) { ps.bd->conn_next = next; out.n_shadow = n; out.shadow_kind = SH_CONNECT; out.alive = 1; return true; }
         ps.bd->conn_cam += 1;
         ps.bd->conn_light = 0;
     }
     return false;
 }
 
-// Camera::is_visible up to the visibility ray, for lamp vertices from `conn_light` (cameras.rs:99-142).
-// `rng` advances exactly as the reference's does; `origins` receives the lens sample per staged ray.
-PYR_HD uint32_t stage_visibility(const SceneView& sc, const PathState& ps, const BidirCtx& cx, Rng& rng, uint32_t from_light, Ray* rays,
-                                 uint32_t* lamp_index, v3* lens, uint32_t& next) {
+// Camera::is_visible up to the visibility ray, for the diffuse lamp vertices from `from_light` (cameras.rs:99-142): f(j, i,
+// position of lamp vertex i, lens sample, world-space lens point, unit direction, distance).  `rng` advances exactly as the
+// reference's does (one lens sample per candidate vertex).
+template <class F>
+PYR_HD uint32_t for_each_splat(const SceneView& sc, const PathState& ps, const BidirCtx& cx, Rng& rng, uint32_t from_light, uint32_t& next, F&& f) {
     uint32_t n = 0, i = from_light;
     if (!sc.camera.inv_ok) { next = ps.bd->n_light; return 0; }
     const uint32_t n_light = ps.bd->n_light;
@@ -264,24 +284,35 @@ PYR_HD uint32_t stage_visibility(const SceneView& sc, const PathState& ps, const
         const v3 world_origin = transform_point(sc.camera.m, origin);
         const v3 direction = target - world_origin;
         const float distance = length(direction);
-        if (rays) rays[n] = make_ray(world_origin, direction / distance, 2, distance - DIST_EPSILON);
-        if (lamp_index) lamp_index[n] = i;
-        if (lens) lens[n] = origin;
+        f(n, i, target, local_target, origin, world_origin, direction / distance, distance);
         ++n;
     }
     next = i;
     return n;
+}
+PYR_HD uint32_t stage_visibility(const SceneView& sc, const PathState& ps, const BidirCtx& cx, Rng& rng, uint32_t from_light, Ray* rays, uint32_t& next) {
+    return for_each_splat(sc, ps, cx, rng, from_light, next, [&](uint32_t j, uint32_t, v3, v3, v3, v3 world_origin, v3 dir, float distance) {
+        if (rays) rays[j] = make_ray(world_origin, dir, 2, distance - DIST_EPSILON);
+    });
 }
 
 PYR_HD bool advance_splat(const SceneView& sc, PathState& ps, const BidirCtx& cx, BidirOut& out) {
     while (ps.bd->conn_light < ps.bd->n_light) {
         ps.bd->rng_saved = ps.rng;
         uint32_t next;
-        uint32_t n = stage_visibility(sc, ps, cx, ps.rng, ps.bd->conn_light, out.shadow, nullptr, nullptr, next);
-        if (n) { ps.bd->conn_next = next; out.n_shadow = n; out.alive = 1; return true; }
+        uint32_t n = stage_visibility(sc, ps, cx, ps.rng, ps.bd->conn_light, PYR_STAGE_RAYS(out), next);
+        if (n) { ps.bd->conn_next = next; out.n_shadow = n; out.shadow_kind = SH_SPLAT; out.alive = 1; return true; }
         ps.bd->conn_light = next;
     }
     return false;
+}
+
+// The staged visibility rays of a connect / splat step, written where the kernel reserved room for them (`dst`, in the ray
+// queue): the same walk as the counting pass (the lens samples replay from the saved RNG state).
+PYR_HD void write_staged(const SceneView& sc, const PathState& ps, const BidirCtx& cx, uint32_t shadow_kind, Ray* dst) {
+    uint32_t next;
+    if (shadow_kind == SH_CONNECT) stage_connections(ps, cx, ps.bd->conn_light, dst, next);
+    else if (shadow_kind == SH_SPLAT) { Rng replay = ps.bd->rng_saved; stage_visibility(sc, ps, cx, replay, ps.bd->conn_light, dst, next); }
 }
 
 // After the camera path has ended: expose it, then start connecting (or splatting, or finish).
@@ -321,7 +352,7 @@ PYR_HD void generate_bidirectional(const SceneView& sc, uint64_t seed, uint32_t 
     ps.flags = 0;
     ps.bd->n_light = 0; ps.bd->n_cam = 0; ps.bd->n_cam_stored = 0; ps.bd->lamp_bounces = 0; ps.bd->conn_cam = 0; ps.bd->conn_light = 0; ps.bd->conn_next = 0;
     ps.bd->cam_store_pending = 0; ps.light_events = 0; ps.n_pending = 0; ps.bounce = 0;
-    out.alive = 0; out.has_main = 0; out.n_shadow = 0;
+    out.alive = 0; out.has_main = 0; out.n_shadow = 0; out.shadow_kind = SH_NONE;
 
     // World::pick_lamp + Lamp::sample_ray
     const uint32_t lamp_index = (uint32_t)rng.gen_range_usize(sc.n_lamps);
@@ -441,111 +472,124 @@ PYR_HD bool lamp_step(const SceneView& sc, PathState& ps, const BidirCtx& cx, co
     return false;
 }
 
+// ---- one wavefront step per phase.  The kernels run one specialised kernel per phase over the slots sorted by phase (each with
+// the registers ITS phase needs); shade_bidirectional below dispatches for the CPU emulation.
+// PH_LAMP: one iteration of the lamp subpath; when it ends: fix-up, colours, and the camera subpath starts.
+PYR_HD void shade_bd_lamp(const SceneView& sc, PathState& ps, const BidirCtx& cx, const Ray* main_ray, const Hit* main_hit, BidirOut& out, PathCounters& pc) {
+    out.alive = 0; out.has_main = 0; out.n_shadow = 0; out.shadow_kind = SH_NONE;
+    if (lamp_step(sc, ps, cx, load_record_stream(main_ray), load_record(main_hit), out, pc)) return;
+    finish_lamp_path(sc, ps, cx.lv);
+    ps.light_events = 0;
+    begin_camera(ps, out);
+}
+// PH_CAMERA: one iteration of the camera subpath (the camera-to-light integrator's step with the vertex hooks); `so` carries its
+// next-event visibility rays (SH_NEE).  When the path ends: expose, then connections, then light tracing.
 template <class Add>
-PYR_HD void shade_bidirectional(const SceneView& sc, PathState& ps, const BidirCtx& cx, const Ray* main_ray, const Hit* main_hit,
-                                const Ray* shadow_rays, const uint32_t* shadow_kinds, BidirOut& out, Add& add, PathCounters& pc) {
-    out.alive = 0; out.has_main = 0; out.n_shadow = 0;
-    const uint32_t S = sc.renderer.spectrum_samples;
-    if (ps.bd->phase == PH_LAMP) {
-        if (lamp_step(sc, ps, cx, load_record_stream(main_ray), load_record(main_hit), out, pc)) return;
-        finish_lamp_path(sc, ps, cx.lv);
-        ps.light_events = 0;
-        begin_camera(ps, out);
+PYR_HD void shade_bd_camera(const SceneView& sc, PathState& ps, const BidirCtx& cx, const Ray* main_ray, const Hit* main_hit, const Ray* shadow_rays,
+                            const uint32_t* shadow_kinds, ShadeOut& so, BidirOut& out, Add& add, PathCounters& pc) {
+    out.alive = 0; out.has_main = 0; out.n_shadow = 0; out.shadow_kind = SH_NONE;
+    CameraHooks hooks{cx, sc.renderer.spectrum_samples};
+    const bool more = camera_step(sc, ps, main_ray, main_hit, shadow_rays, shadow_kinds, so, pc, hooks);
+    if (more) {
+        out.alive = 1; out.has_main = so.has_main; out.main = so.main; out.n_shadow = so.n_shadow; out.shadow_kind = so.n_shadow ? SH_NEE : SH_NONE;
         return;
     }
-    if (ps.bd->phase == PH_CAMERA) {
-        ShadeOut so;
-        so.stage_base = sc.vm_regs * 128u;
-        CameraHooks hooks{cx, sc.renderer.spectrum_samples};
-        const bool more = camera_step(sc, ps, main_ray, main_hit, shadow_rays, shadow_kinds, so, pc, hooks);
-        if (more) {
-            out.alive = 1; out.has_main = so.has_main; out.main = so.main; out.n_shadow = so.n_shadow;
-            for (uint32_t j = 0; j < so.n_shadow; ++j) out.shadow[j] = so.get_shadow(j);
+    end_camera_path(sc, ps, cx, out, add);
+}
+// PH_CONNECT: evaluate the connections whose visibility rays were just traced (bidirectional.rs:310-398), stage the next ones
+template <class Add>
+PYR_HD void shade_bd_connect(const SceneView& sc, PathState& ps, const BidirCtx& cx, const uint32_t* shadow_kinds, BidirOut& out, Add& add) {
+    out.alive = 0; out.has_main = 0; out.n_shadow = 0; out.shadow_kind = SH_NONE;
+    const uint32_t S = sc.renderer.spectrum_samples;
+    const SpecArray bright = cx.bright, refl = cx.refl;
+    const CamVertex& stored = cx.cv[ps.bd->conn_cam];
+    const CamVertexHead c = stored;
+    const float weight = 1.0f / (float)(ps.bd->n_cam * ps.bd->n_light);  // bidirectional.rs:217-218
+    uint32_t next;
+    for_each_connection(ps, cx, ps.bd->conn_light, next, [&](uint32_t j, uint32_t i, const VertexGeometry&, v3, v3 dir, float, float sq_distance) {
+        if (shadow_kinds[j] != KIND_MISS) return;
+        const LightVertexHead v = load_head(cx.lv + i);
+        const v3 cn = ld3(c.normal);
+        float cos_out = fabsf(dot(cn, dir));
+        float cos_in = fabsf(dot(ld3(v.normal), -dir));
+        float brdf_out = (2.0f * fabsf(dot(dir, cn))) / c.brdf;
+        float scale = cos_in * cos_out * brdf_out / (2.0f * PYR_PI * sq_distance);
+        float brdf_in = vertex_brdf(v) / vertex_brdf(v);
+        {
+            static_assert(MAX_SPECTRUM_SAMPLES == 16, "two chunks per array");
+            Vec8 b[2], r[2];
+            b[0] = ld256(stored.bright); r[0] = ld256(stored.refl);
+            if (S > 8) { b[1] = ld256(stored.bright + 8); r[1] = ld256(stored.refl + 8); }
+#pragma unroll
+            for (uint32_t k = 0; k < MAX_SPECTRUM_SAMPLES; ++k)
+                if (k < S) { bright[k] = b[k >> 3].v[k & 7]; refl[k] = r[k >> 3].v[k & 7] * scale; }
+        }
+        bool use_additional = c.use_additional != 0;
+        fold_lamp_tail(sc, cx.lv, i, ps.bd->n_light, use_additional, bright, refl, brdf_in);
+        film_expose(sc.film, ps.pos[0], ps.pos[1], bright[0], ps.wl[0], weight, add);
+        if (use_additional)
+            for (uint32_t k = 1; k < S; ++k) film_expose(sc.film, ps.pos[0], ps.pos[1], bright[k], ps.wl[k], weight, add);
+    });
+    ps.bd->conn_light = ps.bd->conn_next;
+    if (ps.bd->conn_light >= ps.bd->n_light) { ps.bd->conn_cam += 1; ps.bd->conn_light = 0; }
+    if (advance_connect(ps, cx, out)) return;
+    ps.bd->phase = PH_SPLAT;
+    ps.bd->conn_light = 0;
+    if (advance_splat(sc, ps, cx, out)) return;
+    out.alive = 0;
+}
+// PH_SPLAT: evaluate the light-traced samples whose visibility rays were just traced (bidirectional.rs:253-306)
+template <class Add>
+PYR_HD void shade_bd_splat(const SceneView& sc, PathState& ps, const BidirCtx& cx, const uint32_t* shadow_kinds, BidirOut& out, Add& add) {
+    out.alive = 0; out.has_main = 0; out.n_shadow = 0; out.shadow_kind = SH_NONE;
+    const uint32_t S = sc.renderer.spectrum_samples;
+    const SpecArray bright = cx.bright, refl = cx.refl;
+    Rng replay = ps.bd->rng_saved;
+    const float weight = 1.0f / (float)ps.bd->n_light;
+    uint32_t next;
+    for_each_splat(sc, ps, cx, replay, ps.bd->conn_light, next, [&](uint32_t j, uint32_t i, v3 target, v3 local_target, v3 origin, v3 world_origin, v3, float) {
+        if (shadow_kinds[j] != KIND_MISS) return;
+        const LightVertexHead v = load_head(cx.lv + i);
+        local_target.z += sc.camera.focus_distance;
+        const float dist = local_target.z;
+        local_target = local_target - (origin * dist) / sc.camera.focus_distance;
+        local_target.z -= sc.camera.focus_distance;
+        const v3 view_plane_target = (-local_target) / local_target.z;
+        const float px = view_plane_target.x * sc.camera.view_plane, py = (-view_plane_target.y) * sc.camera.view_plane;
+        if (!(px > -1.0f && px < 1.0f && py > -1.0f && py < 1.0f)) return;
+        const float sq_distance = length2(world_origin - target);
+        const float scale = 1.0f / sq_distance;
+        const float brdf_in = vertex_brdf(v) / vertex_brdf(v);
+        for (uint32_t k = 0; k < S; ++k) { bright[k] = 0.0f; refl[k] = scale; }
+        bool use_additional = true;
+        fold_lamp_tail(sc, cx.lv, i, ps.bd->n_light, use_additional, bright, refl, brdf_in);
+        film_expose(sc.film, px, py, bright[0], ps.wl[0], weight, add);
+        if (use_additional)
+            for (uint32_t k = 1; k < S; ++k) film_expose(sc.film, px, py, bright[k], ps.wl[k], weight, add);
+    });
+    ps.bd->conn_light = ps.bd->conn_next;
+    if (advance_splat(sc, ps, cx, out)) return;
+    out.alive = 0;
+}
+
+#if !defined(__CUDA_ARCH__)
+// The CPU emulation's dispatcher (tests/host_emu.cpp): one step of whatever phase the sample is in.
+template <class Add>
+inline void shade_bidirectional(const SceneView& sc, PathState& ps, const BidirCtx& cx, const Ray* main_ray, const Hit* main_hit,
+                                const Ray* shadow_rays, const uint32_t* shadow_kinds, BidirOut& out, Add& add, PathCounters& pc) {
+    switch (ps.bd->phase) {
+        case PH_LAMP: shade_bd_lamp(sc, ps, cx, main_ray, main_hit, out, pc); return;
+        case PH_CAMERA: {
+            ShadeOut so;
+            so.stage_base = 0;
+            shade_bd_camera(sc, ps, cx, main_ray, main_hit, shadow_rays, shadow_kinds, so, out, add, pc);
+            if (out.shadow_kind == SH_NEE) for (uint32_t j = 0; j < out.n_shadow; ++j) out.shadow[j] = so.get_shadow(j);
             return;
         }
-        end_camera_path(sc, ps, cx, out, add);
-        return;
-    }
-    uint32_t lamp_index[BDPT_STAGE];
-    const SpecArray bright = cx.bright, refl = cx.refl;
-    if (ps.bd->phase == PH_CONNECT) {  // evaluate the connections whose visibility rays were just traced
-        uint32_t next;
-        const uint32_t n = stage_connections(ps, cx, ps.bd->conn_light, nullptr, lamp_index, next);
-        const CamVertex& stored = cx.cv[ps.bd->conn_cam];
-        const CamVertexHead c = stored;
-        const v3 from = ld3(c.position), cn = ld3(c.normal);
-        const float weight = 1.0f / (float)(ps.bd->n_cam * ps.bd->n_light);  // bidirectional.rs:217-218
-        for (uint32_t j = 0; j < n; ++j) {
-            if (shadow_kinds[j] != KIND_MISS) continue;
-            const LightVertexHead v = load_head(cx.lv + lamp_index[j]);
-            v3 direction = ld3(v.position) - from;
-            float sq_distance = length2(direction);
-            float distance = sqrtf(sq_distance);
-            v3 dir = direction / distance;
-            float cos_out = fabsf(dot(cn, dir));
-            float cos_in = fabsf(dot(ld3(v.normal), -dir));
-            float brdf_out = (2.0f * fabsf(dot(dir, cn))) / c.brdf;
-            float scale = cos_in * cos_out * brdf_out / (2.0f * PYR_PI * sq_distance);
-            float brdf_in = vertex_brdf(v) / vertex_brdf(v);
-            {
-                static_assert(MAX_SPECTRUM_SAMPLES == 16, "two chunks per array");
-                Vec8 b[2], r[2];
-                b[0] = ld256(stored.bright); r[0] = ld256(stored.refl);
-                if (S > 8) { b[1] = ld256(stored.bright + 8); r[1] = ld256(stored.refl + 8); }
-#pragma unroll
-                for (uint32_t k = 0; k < MAX_SPECTRUM_SAMPLES; ++k)
-                    if (k < S) { bright[k] = b[k >> 3].v[k & 7]; refl[k] = r[k >> 3].v[k & 7] * scale; }
-            }
-            bool use_additional = c.use_additional != 0;
-            fold_lamp_tail(sc, cx.lv, lamp_index[j], ps.bd->n_light, use_additional, bright, refl, brdf_in);
-            film_expose(sc.film, ps.pos[0], ps.pos[1], bright[0], ps.wl[0], weight, add);
-            if (use_additional)
-                for (uint32_t k = 1; k < S; ++k) film_expose(sc.film, ps.pos[0], ps.pos[1], bright[k], ps.wl[k], weight, add);
-        }
-        ps.bd->conn_light = ps.bd->conn_next;
-        if (ps.bd->conn_light >= ps.bd->n_light) { ps.bd->conn_cam += 1; ps.bd->conn_light = 0; }
-        if (advance_connect(ps, cx, out)) return;
-        ps.bd->phase = PH_SPLAT;
-        ps.bd->conn_light = 0;
-        if (advance_splat(sc, ps, cx, out)) return;
-        out.alive = 0;
-        return;
-    }
-    // PH_SPLAT: evaluate the light-traced samples (bidirectional.rs:253-306)
-    {
-        v3 lens[BDPT_STAGE];
-        Rng replay = ps.bd->rng_saved;
-        uint32_t next;
-        const uint32_t n = stage_visibility(sc, ps, cx, replay, ps.bd->conn_light, nullptr, lamp_index, lens, next);
-        const float weight = 1.0f / (float)ps.bd->n_light;
-        for (uint32_t j = 0; j < n; ++j) {
-            if (shadow_kinds[j] != KIND_MISS) continue;
-            const LightVertexHead v = load_head(cx.lv + lamp_index[j]);
-            const v3 target = ld3(v.position);
-            v3 local_target = transform_point(sc.camera.inv, target);
-            const v3 origin = lens[j];
-            local_target.z += sc.camera.focus_distance;
-            const float dist = local_target.z;
-            local_target = local_target - (origin * dist) / sc.camera.focus_distance;
-            local_target.z -= sc.camera.focus_distance;
-            const v3 view_plane_target = (-local_target) / local_target.z;
-            const float px = view_plane_target.x * sc.camera.view_plane, py = (-view_plane_target.y) * sc.camera.view_plane;
-            if (!(px > -1.0f && px < 1.0f && py > -1.0f && py < 1.0f)) continue;
-            const v3 world_origin = ld3(load_record_stream(shadow_rays + j).o);
-            const float sq_distance = length2(world_origin - target);
-            const float scale = 1.0f / sq_distance;
-            const float brdf_in = vertex_brdf(v) / vertex_brdf(v);
-            for (uint32_t k = 0; k < S; ++k) { bright[k] = 0.0f; refl[k] = scale; }
-            bool use_additional = true;
-            fold_lamp_tail(sc, cx.lv, lamp_index[j], ps.bd->n_light, use_additional, bright, refl, brdf_in);
-            film_expose(sc.film, px, py, bright[0], ps.wl[0], weight, add);
-            if (use_additional)
-                for (uint32_t k = 1; k < S; ++k) film_expose(sc.film, px, py, bright[k], ps.wl[k], weight, add);
-        }
-        ps.bd->conn_light = ps.bd->conn_next;
-        if (advance_splat(sc, ps, cx, out)) return;
-        out.alive = 0;
+        case PH_CONNECT: shade_bd_connect(sc, ps, cx, shadow_kinds, out, add); return;
+        default: shade_bd_splat(sc, ps, cx, shadow_kinds, out, add); return;
     }
 }
+#endif
 
 }  // namespace pyr

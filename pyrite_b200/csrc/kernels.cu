@@ -14,6 +14,7 @@
 //   k_develop       stage 6 tail: spectral film -> CIE XYZ -> sRGB
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdlib>
 
 #include "kernels.hpp"
@@ -223,9 +224,10 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_keys(const PathCore* paths,
         if (c) atomicAdd(&bin_count[k], c);
     }
 }
-__global__ void __launch_bounds__(1024) k_bin_scan(uint32_t* bin_count, uint32_t* bin_first, uint32_t* bin_fill, uint32_t* queue_counts, uint32_t* live_count_out) {
-    // also clears what the shade pass of this iteration counts into: its ray-queue counters and its live-slot count
-    if (threadIdx.x == 0) { queue_counts[0] = 0; queue_counts[1] = 0; *live_count_out = 0; }
+__global__ void __launch_bounds__(1024) k_bin_scan(uint32_t* bin_count, uint32_t* bin_first, uint32_t* bin_fill, uint32_t* queue_counts, uint32_t* live_count_out,
+                                                   uint32_t* died_count) {
+    // also clears what the shade pass of this iteration counts into: its ray-queue counters, its live-slot count and its died-slot count
+    if (threadIdx.x == 0) { queue_counts[0] = 0; queue_counts[1] = 0; *live_count_out = 0; *died_count = 0; }
     constexpr int PER = (NUM_KEYS + 1023) / 1024;
     __shared__ uint32_t s_warp[32];
     uint32_t c[PER], sum = 0;
@@ -792,7 +794,7 @@ void launch_bin(const WaveArgs& a, const BinBuffers& b, uint32_t cluster_shift, 
     cudaFuncSetAttribute(k_bin_keys, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NUM_KEYS * sizeof(uint32_t)));
     k_bin_keys<<<blocks, BIN_THREADS, NUM_KEYS * sizeof(uint32_t), s>>>(a.paths, bidirectional ? a.bidir : nullptr, a.pool, a.hits_in, a.shadow_kinds_in, cluster_shift, b.count, b.keys,
                                               a.live_list, a.live_count_in);
-    k_bin_scan<<<1, 1024, 0, s>>>(b.count, b.first, b.fill, a.count_out, a.live_count_out);
+    k_bin_scan<<<1, 1024, 0, s>>>(b.count, b.first, b.fill, a.count_out, a.live_count_out, a.died_count);
     cudaFuncSetAttribute(k_bin_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * NUM_KEYS * sizeof(uint32_t)));
     k_bin_scatter<<<blocks, BIN_THREADS, 2 * NUM_KEYS * sizeof(uint32_t), s>>>(a.pool, b.keys, b.first, b.fill, b.list, a.live_list, a.live_count_in);
 }

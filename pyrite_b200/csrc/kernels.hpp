@@ -53,6 +53,9 @@ struct WaveArgs {
     uint32_t* live_list;
     const uint32_t* live_count_in;
     uint32_t* live_count_out;
+    // bidirectional: slots whose sample ended in this iteration's phase kernels (the GEN kernel restarts them in the same iteration)
+    uint32_t* died_list;
+    uint32_t* died_count;
 };
 #ifndef PYR_BIN_CLUSTERS
 #define PYR_BIN_CLUSTERS 16
@@ -93,7 +96,8 @@ TraceTuning trace_tuning();
 // the wavefront
 void launch_pool_reset(PathCore* paths, uint32_t pool, uint32_t* live_list, uint32_t* live_count, cudaStream_t s);
 void launch_wave_simple(const SceneView& sc, const WaveArgs& a, cudaStream_t s);
-void launch_wave_bidirectional(const SceneView& sc, const WaveArgs& a, cudaStream_t s);
+void launch_wave_bidirectional(const SceneView& sc, const WaveArgs& a, int sm_count, cudaStream_t s);
+int wave_bidirectional_launches();
 void launch_trace(const SceneView& sc, const TraceArgs& a, int grid_blocks, cudaStream_t s);
 void launch_march(const SceneView& sc, const TraceArgs& a, int grid_blocks, cudaStream_t s);
 
