@@ -79,6 +79,8 @@ typedef struct pyr_render_params {
     uint32_t reset_film;    /* non-zero: clear the film first; zero: keep accumulating (film is additive) */
     uint32_t pool_paths;    /* paths in flight; 0 = library default */
     uint32_t flags;         /* PYR_RENDER_* */
+    uint32_t tile_filter;   /* 0 = every tile; t + 1 = only tile t (diagnostics: replaying the samples of one tile) */
+    uint32_t reserved;      /* must be 0 */
 } pyr_render_params;
 #define PYR_RENDER_STATS 1u  /* also count visited BVH nodes / tested leaves (slower) */
 #define PYR_RENDER_TIMING 2u /* bracket every trace / shade launch with CUDA events (pyr_counters.*_seconds) */

@@ -180,6 +180,26 @@ int pyro_render(void* handle, const pyro_render_opts* o) {
     }
 }
 
+// Exactly ONE path sample (tile, sample) of the project's integrator into the film, on its keyed stream: replays a sample the
+// product flagged (tools/find_nonfinite.py).
+int pyro_render_sample(void* handle, uint64_t seed, uint32_t tile, uint32_t sample, int reset_film) {
+    Handle* h = (Handle*)handle;
+    try {
+        const Project& P = h->world->P;
+        if (reset_film) h->film = std::make_unique<Film>(P.width, P.height, h->R.spectrum_bins, h->R.span_lo, h->R.span_hi);
+        RenderOptions opt;
+        opt.seed = seed; opt.rng_mode = 1; opt.eager_emissive_draw = true;
+        opt.spp_override = 0xFFFFFFFFu;   // `sample` < area * spp for any sample index
+        opt.sample_offset = sample; opt.sample_stride = 1; opt.sample_limit = 1; opt.threads = 1; opt.cas_attempts = 0; opt.only_tile = tile;
+        RenderState st{*h->world, h->camera, h->R, *h->film, opt, h->counters};
+        render(st);
+        return 0;
+    } catch (const std::exception& e) {
+        g_error = e.what();
+        return 1;
+    }
+}
+
 double pyro_last_render_seconds(void* handle) { return ((Handle*)handle)->last_render_seconds; }
 
 int pyro_counters(void* handle, pyro_counters_t* c, int reset) {

@@ -463,6 +463,8 @@ struct RenderOptions {
     uint32_t sample_stride = 1;    // samples i = offset, offset+stride, ... (< area*spp)
     int threads = 0;               // 0 = renderer.threads
     int cas_attempts = 5;
+    int64_t only_tile = -1;        // >= 0: render this tile only (tools/find_nonfinite.py replays single path samples)
+    uint64_t sample_limit = 0;     // > 0: at most this many samples per tile
 };
 
 struct RenderState {
@@ -486,6 +488,7 @@ inline void render_tile_simple(RenderState& st, const Tile& tile) {
     TraceCtx cx{st.W, rng, {}, st.opt.eager_emissive_draw};
     uint64_t done = 0;
     for (uint64_t i = st.opt.sample_offset; i < iterations; i += st.opt.sample_stride) {
+        if (st.opt.sample_limit && done >= st.opt.sample_limit) break;
         if (st.opt.rng_mode == 1) rng = keyed_rng(st.opt.seed, tile.index, i);
         additional.clear(); path.clear(); wavelengths.clear();
         Vec2 position = tile.sample_point(rng);
@@ -625,6 +628,7 @@ inline void render_tile_bidirectional(RenderState& st, const Tile& tile) {
     TraceCtx cx{W, rng, {}, st.opt.eager_emissive_draw};
     uint64_t done = 0;
     for (uint64_t it = st.opt.sample_offset; it < iterations; it += st.opt.sample_stride) {
+        if (st.opt.sample_limit && done >= st.opt.sample_limit) break;
         if (st.opt.rng_mode == 1) rng = keyed_rng(st.opt.seed, tile.index, it);
         lamp_path.clear(); camera_path.clear(); additional.clear(); wavelengths.clear();
         Vec2 position = tile.sample_point(rng);
@@ -736,6 +740,7 @@ inline void render(RenderState& st) {
             for (;;) {
                 size_t i = next.fetch_add(1);
                 if (i >= tiles.size()) break;
+                if (st.opt.only_tile >= 0 && (int64_t)tiles[i].index != st.opt.only_tile) continue;
                 if (st.R.algorithm == 0) render_tile_simple(st, tiles[i]);
                 else if (st.R.algorithm == 1) render_tile_bidirectional(st, tiles[i]);
                 else throw std::runtime_error("photon mapping is out of scope (SURVEY.md §2 row 21)");

@@ -54,7 +54,7 @@ class ProjectInfo(C.Structure):
 
 class RenderParams(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("spp_override", C.c_uint32), ("sample_offset", C.c_uint32), ("sample_stride", C.c_uint32),
-                ("reset_film", C.c_uint32), ("pool_paths", C.c_uint32), ("flags", C.c_uint32)]
+                ("reset_film", C.c_uint32), ("pool_paths", C.c_uint32), ("flags", C.c_uint32), ("tile_filter", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class Counters(C.Structure):
@@ -202,9 +202,10 @@ class Renderer:
 
     # -- Renderer::render
     def render(self, seed: int = 0, spp: int = 0, sample_offset: int = 0, sample_stride: int = 1, reset_film: bool = True,
-               pool_paths: int = 0, stats: bool = False, timing: bool = False, progress=None) -> float:
-        """Runs the wavefront pipeline into the film; returns the device seconds it took."""
-        p = RenderParams(seed, spp, sample_offset, sample_stride, int(reset_film), pool_paths, (RENDER_STATS if stats else 0) | (RENDER_TIMING if timing else 0))
+               pool_paths: int = 0, stats: bool = False, timing: bool = False, progress=None, only_tile=None) -> float:
+        """Runs the wavefront pipeline into the film; returns the device seconds it took.  `only_tile`: render one tile only (diagnostics)."""
+        p = RenderParams(seed, spp, sample_offset, sample_stride, int(reset_film), pool_paths, (RENDER_STATS if stats else 0) | (RENDER_TIMING if timing else 0),
+                         0 if only_tile is None else only_tile + 1, 0)
         if progress is None:
             cb = PROGRESS_CB()
         else:

@@ -443,6 +443,7 @@ pyr_status pyr_render(pyr_ctx* ctx, const pyr_render_params* params, pyr_progres
         const uint32_t spp = p.spp_override ? p.spp_override : R.pixel_samples;
         const uint32_t stride = p.sample_stride ? p.sample_stride : 1u;
         const uint32_t offset = p.sample_offset;
+        if (p.tile_filter > ctx->scene.tiles.size()) throw ir::BuildError("tile_filter out of range");
         if (ctx->view.n_lamps == 0) {
             // World::pick_lamp panics on an empty lamp list (`gen_range(0..0)`, world.rs:301-305); the reference reaches it
             // from trace_direct at the first diffuse bounce (even with light_samples = 0) and from every bidirectional sample
@@ -458,6 +459,7 @@ pyr_status pyr_render(pyr_ctx* ctx, const pyr_render_params* params, pyr_progres
         for (size_t t = 0; t < ctx->scene.tiles.size(); ++t) {
             unsigned long long iterations = (unsigned long long)ctx->scene.tiles[t].width * ctx->scene.tiles[t].height * spp;
             unsigned long long mine = offset < iterations ? (iterations - offset + stride - 1) / stride : 0;
+            if (p.tile_filter && p.tile_filter != t + 1) mine = 0;
             first[t + 1] = first[t] + mine;
         }
         const unsigned long long total = first.back();

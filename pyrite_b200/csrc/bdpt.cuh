@@ -42,14 +42,22 @@ struct alignas(32) LightVertexHead {   // 96 B: what a thread keeps in registers
     uint32_t pad[6];
 };
 struct alignas(32) LightVertex : LightVertexHead {
-    float color[MAX_SPECTRUM_SAMPLES];  // color(wl[k]), filled by finish_lamp_path; read in place (never copied to a thread)
+    // The fold of `contribute` over lamp_path[i..] as seen by a connection that STARTS at this vertex, per wavelength:
+    // connect_paths (bidirectional.rs:373-389) and light tracing (:276-292) re-fold that tail for every connection, always
+    // with the same colours, and the fold is linear in the reflectance it starts from -
+    //     brightness_out[k] = brightness_in[k] + reflectance_in[k] * fold[k]
+    // - so finish_lamp_path evaluates every vertex' colour program once at the path's wavelengths and stores the tail folds
+    // (one backward pass); a connection is then ONE 64-byte load instead of a walk over the tail.
+    float fold[MAX_SPECTRUM_SAMPLES];
 };
+constexpr uint32_t VT_TAIL_DISPERSED = 0x100u;  // in `type` after finish_lamp_path: some vertex of lamp_path[i..] is dispersive
 // position, type and normal of a lamp vertex: one 32-byte load
-struct VertexGeometry { v3 position; uint32_t type; v3 normal; };
+struct VertexGeometry { v3 position; uint32_t type; bool tail_dispersed; v3 normal; };
 PYR_HD VertexGeometry vertex_geometry(const Vec8& q) {
     VertexGeometry g;
     g.position = mk3(q.v[0], q.v[1], q.v[2]);
-    g.type = f_bits(q.v[3]);
+    g.type = f_bits(q.v[3]) & 0xffu;
+    g.tail_dispersed = (f_bits(q.v[3]) & VT_TAIL_DISPERSED) != 0;
     g.normal = mk3(q.v[4], q.v[5], q.v[6]);
     return g;
 }
@@ -110,37 +118,6 @@ PYR_HD void store_head(LightVertex* p, const LightVertexHead& h) {
     __builtin_memcpy(&c, reinterpret_cast<const char*>(&h) + 64, 32);
     st256(p, a); st256(reinterpret_cast<Vec8*>(p) + 1, b); st256(reinterpret_cast<Vec8*>(p) + 2, c);
 }
-// `contribute` (renderer/algorithm.rs:14-100) of a lamp-subpath bounce on a detached sample state
-PYR_HD void contribute_vertex(const LightVertexHead& v, const float* color, uint32_t n, SpecArray bright, SpecArray refl) {
-    // the colours come in with two 32-byte loads issued together, not one dependent 4-byte load per wavelength
-    static_assert(MAX_SPECTRUM_SAMPLES == 16, "two chunks");
-    Vec8 c[2];
-    c[0] = ld256(color);
-    if (n > 8) c[1] = ld256(color + 8);
-    if (v.type == VT_EMISSION) {
-#pragma unroll
-        for (uint32_t k = 0; k < MAX_SPECTRUM_SAMPLES; ++k)
-            if (k < n) bright[k] += c[k >> 3].v[k & 7] * v.probability * refl[k];
-    } else {
-        const float brdf = vertex_brdf(v);
-#pragma unroll
-        for (uint32_t k = 0; k < MAX_SPECTRUM_SAMPLES; ++k)
-            if (k < n) { refl[k] *= c[k >> 3].v[k & 7] * v.probability; refl[k] *= brdf; }
-    }
-}
-// the fold over lamp_path[first..] shared by connect_paths (:373-389) and light tracing (:276-292)
-PYR_HD void fold_lamp_tail(const SceneView& sc, const LightVertex* lv, uint32_t first, uint32_t n_light, bool& use_additional,
-                           SpecArray bright, SpecArray refl, float brdf_in) {
-    const uint32_t S = sc.renderer.spectrum_samples;
-    for (uint32_t k = first; k < n_light; ++k) {
-        const LightVertexHead v = load_head(lv + k);
-        use_additional = !v.dispersed && use_additional;
-        const uint32_t n = use_additional ? S : 1u;
-        contribute_vertex(v, lv[k].color, n, bright, refl);
-        if (k == first) for (uint32_t j = 0; j < n; ++j) refl[j] *= brdf_in;
-    }
-}
-
 // Camera::ray_towards inputs for the lens sample of Camera::is_visible (cameras.rs:122-131)
 PYR_HD v3 lens_origin(const CameraRec& cam, Rng& rng) {
     if (cam.aperture > 0.0f) {
@@ -191,8 +168,19 @@ PYR_HD void begin_camera(PathState& ps, BidirOut& out) {
 }
 
 // The end of the lamp subpath: utils::pairs fix-up (skips the last pair, utils.rs:5-13), drop a trailing
-// emission vertex, reverse (bidirectional.rs:187-202).
-PYR_HD void finish_lamp_path(const SceneView& sc, PathState& ps, LightVertex* lv) {
+// emission vertex, reverse (bidirectional.rs:187-202); then the tail folds (see LightVertex::fold).
+//
+// `contribute` (renderer/algorithm.rs:14-100) on a tail lamp_path[i..], started with (brightness b, reflectance r):
+//     emission vertex k:  b += (c_k p_k) r                      other vertex k:  r *= c_k p_k;  r *= brdf_k
+//     and after the FIRST vertex of the tail:  r *= brdf_in  (= brdf_i / brdf_i, the reference's quirk, :365-372)
+// With T_i = the fold of lamp_path[i..] without that first-vertex factor (T_n = 0):
+//     emission:  T_i = c_i p_i + T_{i+1}                          fold_i = c_i p_i + brdf_in_i T_{i+1}
+//     other:     T_i = ((c_i p_i) brdf_i) T_{i+1}                 fold_i = (((c_i p_i) brdf_i) brdf_in_i) T_{i+1}
+// (same products as the reference, associated from the tail end instead of from the connection: float rounding differs
+// in the last bits only, far inside the film tolerance).  Additional wavelengths are exposed only if no vertex of the
+// tail is dispersive (`use_additional`), which the VT_TAIL_DISPERSED bit records.
+PYR_HD void finish_lamp_path(const SceneView& sc, PathState& ps, const BidirCtx& cx) {
+    LightVertex* lv = cx.lv;
     uint32_t n = ps.bd->n_light;
     if (n >= 2)
         for (uint32_t pos = 0; pos + 2 < n; ++pos) {
@@ -202,20 +190,38 @@ PYR_HD void finish_lamp_path(const SceneView& sc, PathState& ps, LightVertex* lv
             if (from.type == VT_DIFFUSE) { from.out[0] = from.incident[0]; from.out[1] = from.incident[1]; from.out[2] = from.incident[2]; }
         }
     if (n > 1 && lv[n - 1].type == VT_EMISSION) n -= 1;
-    for (uint32_t i = 0; i < n / 2; ++i) {  // the colours are not evaluated yet: only the heads move
+    for (uint32_t i = 0; i < n / 2; ++i) {  // only the heads move
         const LightVertexHead a = load_head(lv + i), b = load_head(lv + n - 1 - i);
         store_head(lv + i, b);
         store_head(lv + n - 1 - i, a);
     }
     ps.bd->n_light = n;
-    // evaluate every vertex' colour once at the path's wavelengths (with the incident vectors as fixed up above)
     PYR_REGFILE(R);
-    for (uint32_t i = 0; i < n; ++i) {
+    const uint32_t S = sc.renderer.spectrum_samples;
+    const SpecArray T = cx.bright, c = cx.refl;  // the detached per-wavelength scratch arrays (unused until the connect phase)
+    for (uint32_t k = 0; k < S; ++k) T[k] = 0.0f;
+    bool tail_dispersed = false;
+    for (uint32_t i = n; i-- > 0;) {
         const LightVertexHead v = load_head(lv + i);
         VmInputs in;
         in.wavelength = 0.0f; in.incident = ld3(v.incident); in.normal = ld3(v.normal); in.tex[0] = v.tex[0]; in.tex[1] = v.tex[1];
-        float* const color = lv[i].color;
-        eval_spectral_each(sc, v.color_program, in, ps.wl, sc.renderer.spectrum_samples, R, [&](uint32_t k, float c) { color[k] = c; });
+        eval_spectral_each(sc, v.color_program, in, ps.wl, S, R, [&](uint32_t k, float value) { c[k] = value; });
+        const float brdf = vertex_brdf(v), brdf_in = brdf / brdf;
+        tail_dispersed = tail_dispersed || v.dispersed != 0;
+        Vec8 out[2];
+#pragma unroll
+        for (uint32_t k = 0; k < MAX_SPECTRUM_SAMPLES; ++k) {
+            float fold = 0.0f;
+            if (k < S) {
+                const float cp = c[k] * v.probability, rest = T[k];
+                if (v.type == VT_EMISSION) { fold = cp + brdf_in * rest; T[k] = cp + rest; }
+                else { fold = ((cp * brdf) * brdf_in) * rest; T[k] = (cp * brdf) * rest; }
+            }
+            out[k >> 3].v[k & 7] = fold;
+        }
+        st256(lv[i].fold, out[0]);
+        if (S > 8) st256(lv[i].fold + 8, out[1]);
+        if (tail_dispersed) lv[i].type = v.type | VT_TAIL_DISPERSED;
     }
 }
 
@@ -265,7 +271,7 @@ PYR_HD bool advance_connect(PathState& ps, const BidirCtx& cx, BidirOut& out) {
 }
 
 // Camera::is_visible up to the visibility ray, for the diffuse lamp vertices from `from_light` (cameras.rs:99-142): f(j, i,
-// position of lamp vertex i, lens sample, world-space lens point, unit direction, distance).  `rng` advances exactly as the
+// geometry of lamp vertex i, its camera-space position, lens sample, world-space lens point, unit direction, distance).  `rng` advances exactly as the
 // reference's does (one lens sample per candidate vertex).
 template <class F>
 PYR_HD uint32_t for_each_splat(const SceneView& sc, const PathState& ps, const BidirCtx& cx, Rng& rng, uint32_t from_light, uint32_t& next, F&& f) {
@@ -284,14 +290,14 @@ PYR_HD uint32_t for_each_splat(const SceneView& sc, const PathState& ps, const B
         const v3 world_origin = transform_point(sc.camera.m, origin);
         const v3 direction = target - world_origin;
         const float distance = length(direction);
-        f(n, i, target, local_target, origin, world_origin, direction / distance, distance);
+        f(n, i, v, local_target, origin, world_origin, direction / distance, distance);
         ++n;
     }
     next = i;
     return n;
 }
 PYR_HD uint32_t stage_visibility(const SceneView& sc, const PathState& ps, const BidirCtx& cx, Rng& rng, uint32_t from_light, Ray* rays, uint32_t& next) {
-    return for_each_splat(sc, ps, cx, rng, from_light, next, [&](uint32_t j, uint32_t, v3, v3, v3, v3 world_origin, v3 dir, float distance) {
+    return for_each_splat(sc, ps, cx, rng, from_light, next, [&](uint32_t j, uint32_t, const VertexGeometry&, v3, v3, v3 world_origin, v3 dir, float distance) {
         if (rays) rays[j] = make_ray(world_origin, dir, 2, distance - DIST_EPSILON);
     });
 }
@@ -406,7 +412,7 @@ PYR_HD void generate_bidirectional(const SceneView& sc, uint64_t seed, uint32_t 
     store_head(cx.lv, first);
     ps.bd->n_light = 1;
     if (sc.renderer.light_bounces == 0) {
-        finish_lamp_path(sc, ps, cx.lv);
+        finish_lamp_path(sc, ps, cx);
         begin_camera(ps, out);
         return;
     }
@@ -478,7 +484,7 @@ PYR_HD bool lamp_step(const SceneView& sc, PathState& ps, const BidirCtx& cx, co
 PYR_HD void shade_bd_lamp(const SceneView& sc, PathState& ps, const BidirCtx& cx, const Ray* main_ray, const Hit* main_hit, BidirOut& out, PathCounters& pc) {
     out.alive = 0; out.has_main = 0; out.n_shadow = 0; out.shadow_kind = SH_NONE;
     if (lamp_step(sc, ps, cx, load_record_stream(main_ray), load_record(main_hit), out, pc)) return;
-    finish_lamp_path(sc, ps, cx.lv);
+    finish_lamp_path(sc, ps, cx);
     ps.light_events = 0;
     begin_camera(ps, out);
 }
@@ -501,34 +507,40 @@ template <class Add>
 PYR_HD void shade_bd_connect(const SceneView& sc, PathState& ps, const BidirCtx& cx, const uint32_t* shadow_kinds, BidirOut& out, Add& add) {
     out.alive = 0; out.has_main = 0; out.n_shadow = 0; out.shadow_kind = SH_NONE;
     const uint32_t S = sc.renderer.spectrum_samples;
-    const SpecArray bright = cx.bright, refl = cx.refl;
     const CamVertex& stored = cx.cv[ps.bd->conn_cam];
     const CamVertexHead c = stored;
+    const v3 cn = ld3(c.normal);
     const float weight = 1.0f / (float)(ps.bd->n_cam * ps.bd->n_light);  // bidirectional.rs:217-218
+    // the sample state right after this camera vertex' `contribute`: fetched once per step (not once per connection) into the
+    // detached per-wavelength arrays
+    const SpecArray bright = cx.bright, refl = cx.refl;
+    {
+        static_assert(MAX_SPECTRUM_SAMPLES == 16, "two chunks per array");
+        Vec8 b[2], r[2];
+        b[0] = ld256(stored.bright); r[0] = ld256(stored.refl);
+        if (S > 8) { b[1] = ld256(stored.bright + 8); r[1] = ld256(stored.refl + 8); }
+#pragma unroll
+        for (uint32_t k = 0; k < MAX_SPECTRUM_SAMPLES; ++k)
+            if (k < S) { bright[k] = b[k >> 3].v[k & 7]; refl[k] = r[k >> 3].v[k & 7]; }
+    }
     uint32_t next;
-    for_each_connection(ps, cx, ps.bd->conn_light, next, [&](uint32_t j, uint32_t i, const VertexGeometry&, v3, v3 dir, float, float sq_distance) {
+    for_each_connection(ps, cx, ps.bd->conn_light, next, [&](uint32_t j, uint32_t i, const VertexGeometry& v, v3, v3 dir, float, float sq_distance) {
         if (shadow_kinds[j] != KIND_MISS) return;
-        const LightVertexHead v = load_head(cx.lv + i);
-        const v3 cn = ld3(c.normal);
         float cos_out = fabsf(dot(cn, dir));
-        float cos_in = fabsf(dot(ld3(v.normal), -dir));
+        float cos_in = fabsf(dot(v.normal, -dir));
         float brdf_out = (2.0f * fabsf(dot(dir, cn))) / c.brdf;
         float scale = cos_in * cos_out * brdf_out / (2.0f * PYR_PI * sq_distance);
-        float brdf_in = vertex_brdf(v) / vertex_brdf(v);
-        {
-            static_assert(MAX_SPECTRUM_SAMPLES == 16, "two chunks per array");
-            Vec8 b[2], r[2];
-            b[0] = ld256(stored.bright); r[0] = ld256(stored.refl);
-            if (S > 8) { b[1] = ld256(stored.bright + 8); r[1] = ld256(stored.refl + 8); }
+        Vec8 f[2];
+        f[0] = ld256(cx.lv[i].fold);
+        if (S > 8) f[1] = ld256(cx.lv[i].fold + 8);
+        const bool use_additional = c.use_additional != 0 && !v.tail_dispersed;
+        // brightness + (reflectance * scale) * fold(lamp_path[i..])
+        film_expose(sc.film, ps.pos[0], ps.pos[1], bright[0] + (refl[0] * scale) * f[0].v[0], ps.wl[0], weight, add);
+        if (use_additional) {
 #pragma unroll
-            for (uint32_t k = 0; k < MAX_SPECTRUM_SAMPLES; ++k)
-                if (k < S) { bright[k] = b[k >> 3].v[k & 7]; refl[k] = r[k >> 3].v[k & 7] * scale; }
+            for (uint32_t k = 1; k < MAX_SPECTRUM_SAMPLES; ++k)
+                if (k < S) film_expose(sc.film, ps.pos[0], ps.pos[1], bright[k] + (refl[k] * scale) * f[k >> 3].v[k & 7], ps.wl[k], weight, add);
         }
-        bool use_additional = c.use_additional != 0;
-        fold_lamp_tail(sc, cx.lv, i, ps.bd->n_light, use_additional, bright, refl, brdf_in);
-        film_expose(sc.film, ps.pos[0], ps.pos[1], bright[0], ps.wl[0], weight, add);
-        if (use_additional)
-            for (uint32_t k = 1; k < S; ++k) film_expose(sc.film, ps.pos[0], ps.pos[1], bright[k], ps.wl[k], weight, add);
     });
     ps.bd->conn_light = ps.bd->conn_next;
     if (ps.bd->conn_light >= ps.bd->n_light) { ps.bd->conn_cam += 1; ps.bd->conn_light = 0; }
@@ -543,13 +555,12 @@ template <class Add>
 PYR_HD void shade_bd_splat(const SceneView& sc, PathState& ps, const BidirCtx& cx, const uint32_t* shadow_kinds, BidirOut& out, Add& add) {
     out.alive = 0; out.has_main = 0; out.n_shadow = 0; out.shadow_kind = SH_NONE;
     const uint32_t S = sc.renderer.spectrum_samples;
-    const SpecArray bright = cx.bright, refl = cx.refl;
     Rng replay = ps.bd->rng_saved;
     const float weight = 1.0f / (float)ps.bd->n_light;
     uint32_t next;
-    for_each_splat(sc, ps, cx, replay, ps.bd->conn_light, next, [&](uint32_t j, uint32_t i, v3 target, v3 local_target, v3 origin, v3 world_origin, v3, float) {
+    for_each_splat(sc, ps, cx, replay, ps.bd->conn_light, next, [&](uint32_t j, uint32_t i, const VertexGeometry& v, v3 local_target, v3 origin, v3 world_origin, v3, float) {
         if (shadow_kinds[j] != KIND_MISS) return;
-        const LightVertexHead v = load_head(cx.lv + i);
+        const v3 target = v.position;
         local_target.z += sc.camera.focus_distance;
         const float dist = local_target.z;
         local_target = local_target - (origin * dist) / sc.camera.focus_distance;
@@ -559,13 +570,16 @@ PYR_HD void shade_bd_splat(const SceneView& sc, PathState& ps, const BidirCtx& c
         if (!(px > -1.0f && px < 1.0f && py > -1.0f && py < 1.0f)) return;
         const float sq_distance = length2(world_origin - target);
         const float scale = 1.0f / sq_distance;
-        const float brdf_in = vertex_brdf(v) / vertex_brdf(v);
-        for (uint32_t k = 0; k < S; ++k) { bright[k] = 0.0f; refl[k] = scale; }
-        bool use_additional = true;
-        fold_lamp_tail(sc, cx.lv, i, ps.bd->n_light, use_additional, bright, refl, brdf_in);
-        film_expose(sc.film, px, py, bright[0], ps.wl[0], weight, add);
-        if (use_additional)
-            for (uint32_t k = 1; k < S; ++k) film_expose(sc.film, px, py, bright[k], ps.wl[k], weight, add);
+        Vec8 f[2];
+        f[0] = ld256(cx.lv[i].fold);
+        if (S > 8) f[1] = ld256(cx.lv[i].fold + 8);
+        // brightness 0, reflectance `scale`: the sample is scale * fold(lamp_path[i..])
+        film_expose(sc.film, px, py, scale * f[0].v[0], ps.wl[0], weight, add);
+        if (!v.tail_dispersed) {
+#pragma unroll
+            for (uint32_t k = 1; k < MAX_SPECTRUM_SAMPLES; ++k)
+                if (k < S) film_expose(sc.film, px, py, scale * f[k >> 3].v[k & 7], ps.wl[k], weight, add);
+        }
     });
     ps.bd->conn_light = ps.bd->conn_next;
     if (advance_splat(sc, ps, cx, out)) return;

@@ -71,8 +71,10 @@ template <int PHASE> __device__ __forceinline__ void phase_run(const WaveArgs& a
     hi = __ldg(a.bin_first + S1 * BIN_CLUSTERS);
 }
 
+// resident blocks per SM the compiler plans for: the camera step needs its 168 registers (3 blocks, like k_wave_simple),
+// the other phases fit 128 (4 blocks)
 template <int PHASE>
-__global__ void __launch_bounds__(WAVE_THREADS) k_wave_bd(const __grid_constant__ SceneView sc, const __grid_constant__ WaveArgs a) {
+__global__ void __launch_bounds__(WAVE_THREADS, PHASE == BD_CAMERA ? 3 : 4) k_wave_bd(const __grid_constant__ SceneView sc, const __grid_constant__ WaveArgs a) {
     if (PHASE == BD_LAMP && blockIdx.x == 0 && threadIdx.x == 0) *a.trace_cursor = 0;  // the first kernel after k_bin_*
     uint32_t lo, hi;
     phase_run<PHASE>(a, lo, hi);

@@ -79,6 +79,7 @@ def lib(variant: str = "glibc"):
         L.pyro_film_develop.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_int]
         L.pyro_bvh_leaf_order.argtypes = [C.c_void_p, C.c_void_p]
         L.pyro_camera_sample.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.pyro_render_sample.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int]
         L.pyro_debug_path.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _libs[variant] = L
     return _libs[variant]
@@ -138,6 +139,10 @@ class Oracle:
                        cas_attempts, int(reset_film))
         self._check(self.L.pyro_render(self.h, C.byref(o)))
         return float(self.L.pyro_last_render_seconds(self.h))
+
+    def render_sample(self, seed: int, tile: int, sample: int, reset_film: bool = True):
+        """Exactly one path sample (tile, sample) of the project's integrator into the film."""
+        self._check(self.L.pyro_render_sample(self.h, seed, tile, sample, int(reset_film)))
 
     def counters(self, reset=False) -> dict:
         c = Counters()
