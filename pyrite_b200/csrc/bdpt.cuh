@@ -123,7 +123,9 @@ PYR_HD v3 lens_origin(const CameraRec& cam, Rng& rng) {
     if (cam.aperture > 0.0f) {
         float sqrt_r = sqrtf(cam.aperture * rng.gen_f32());
         float psi = PYR_PI * 2.0f * rng.gen_f32();
-        return mk3(sqrt_r * m_cos(psi), sqrt_r * m_sin(psi), 0.0f);
+        float sn, cs;
+        m_sincos(psi, sn, cs);
+        return mk3(sqrt_r * cs, sqrt_r * sn, 0.0f);
     }
     return mk3(0, 0, 0);
 }
@@ -225,49 +227,56 @@ PYR_HD void finish_lamp_path(const SceneView& sc, PathState& ps, const BidirCtx&
     }
 }
 
-// The connections of connect_paths (bidirectional.rs:310-398) for camera vertex `conn_cam`, lamp vertices from `from_light`, at
-// most BDPT_STAGE per iteration: f(j, i, geometry of lamp vertex i, unit direction, distance) is called for the j-th one.
-// Returns their number; `next` = the first lamp index that was not looked at.  The same walk stages the rays (count only, or
-// writing them), and evaluates them one iteration later, so nothing has to be remembered per ray.
-template <class F>
-PYR_HD uint32_t for_each_connection(const PathState& ps, const BidirCtx& cx, uint32_t from_light, uint32_t& next, F&& f) {
-    const CamVertex& c = cx.cv[ps.bd->conn_cam];
-    const v3 from = ld3(c.position), cn = ld3(c.normal);
-    uint32_t n = 0, i = from_light;
-    const uint32_t n_light = ps.bd->n_light;
-    Vec8 fetched = ld256(cx.lv + (i < n_light ? i : 0u));
-    for (; i < n_light && n < (uint32_t)BDPT_STAGE; ++i) {
-        const VertexGeometry v = vertex_geometry(fetched);
-        if (i + 1 < n_light) fetched = ld256(cx.lv + i + 1);  // the next vertex is on its way while this one is examined
-        if (v.type == VT_SPECULAR) continue;
-        v3 direction = v.position - from;
-        float sq_distance = length2(direction);
-        float distance = sqrtf(sq_distance);
-        v3 dir = direction / distance;
-        if (dot(cn, dir) <= 0.0f) continue;
-        if (dot(v.normal, -dir) <= 0.0f) continue;
-        f(n, i, v, from, dir, distance, sq_distance);
-        ++n;
+// The connections of connect_paths (bidirectional.rs:310-398): (camera vertex, lamp vertex) pairs in the reference's order
+// (camera vertices outermost), walked from the cursor (cam, light) until BDPT_STAGE of them have been found or the pairs
+// are exhausted.  new_cam(index, vertex) is called when the walk enters a camera vertex, f(j, i, geometry of lamp vertex i,
+// origin, unit direction, distance, squared distance) for the j-th connection.  Returns their number and leaves the cursor
+// behind the last pair looked at.  The same walk counts the visibility rays, writes them, and evaluates them one iteration
+// later, so nothing has to be remembered per ray - and one step serves as many camera vertices as fit the batch.
+template <class NewCam, class F>
+PYR_HD uint32_t for_each_connection(const PathState& ps, const BidirCtx& cx, uint32_t& cam, uint32_t& light, NewCam&& new_cam, F&& f) {
+    uint32_t n = 0;
+    const uint32_t n_light = ps.bd->n_light, n_cam = ps.bd->n_cam_stored;
+    while (cam < n_cam && n < (uint32_t)BDPT_STAGE) {
+        const CamVertex& c = cx.cv[cam];
+        const Vec8 head = ld256(&c);   // position, brdf, normal, use_additional
+        const v3 from = mk3(head.v[0], head.v[1], head.v[2]), cn = mk3(head.v[4], head.v[5], head.v[6]);
+        new_cam(cam, c, head);
+        uint32_t i = light;
+        Vec8 fetched = ld256(cx.lv + (i < n_light ? i : 0u));
+        for (; i < n_light && n < (uint32_t)BDPT_STAGE; ++i) {
+            const VertexGeometry v = vertex_geometry(fetched);
+            if (i + 1 < n_light) fetched = ld256(cx.lv + i + 1);  // the next vertex is on its way while this one is examined
+            if (v.type == VT_SPECULAR) continue;
+            v3 direction = v.position - from;
+            float sq_distance = length2(direction);
+            float distance = sqrtf(sq_distance);
+            v3 dir = direction / distance;
+            if (dot(cn, dir) <= 0.0f) continue;
+            if (dot(v.normal, -dir) <= 0.0f) continue;
+            f(n, i, v, from, cn, dir, distance, sq_distance);
+            ++n;
+        }
+        if (i >= n_light) { cam += 1; light = 0; }
+        else { light = i; break; }  // the batch is full: the next one goes on with this camera vertex
     }
-    next = i;
     return n;
 }
-PYR_HD uint32_t stage_connections(const PathState& ps, const BidirCtx& cx, uint32_t from_light, Ray* rays, uint32_t& next) {
-    return for_each_connection(ps, cx, from_light, next, [&](uint32_t j, uint32_t, const VertexGeometry&, v3 from, v3 dir, float distance, float) {
+PYR_HD uint32_t stage_connections(const PathState& ps, const BidirCtx& cx, uint32_t& cam, uint32_t& light, Ray* rays) {
+    return for_each_connection(ps, cx, cam, light, [](uint32_t, const CamVertex&, const Vec8&) {},
+                               [&](uint32_t j, uint32_t, const VertexGeometry&, v3 from, v3, v3 dir, float distance, float) {
         if (rays) rays[j] = make_ray(from, dir, 2, distance - DIST_EPSILON);  // blocked <=> a hit closer than distance - eps
     });
 }
 
-// Advance the connect phase until some rays are staged or every camera vertex is done.
+// Stage the next batch of connections from the cursor (conn_cam, conn_light); false when every pair is done.
 PYR_HD bool advance_connect(PathState& ps, const BidirCtx& cx, BidirOut& out) {
-    while (ps.bd->conn_cam < ps.bd->n_cam_stored) {
-        uint32_t next;
-        uint32_t n = stage_connections(ps, cx, ps.bd->conn_light, PYR_STAGE_RAYS(out), next);
-        if (n) { ps.bd->conn_next = next; out.n_shadow = n; out.shadow_kind = SH_CONNECT; out.alive = 1; return true; }
-        ps.bd->conn_cam += 1;
-        ps.bd->conn_light = 0;
-    }
-    return false;
+    uint32_t cam = ps.bd->conn_cam, light = ps.bd->conn_light;
+    const uint32_t n = stage_connections(ps, cx, cam, light, PYR_STAGE_RAYS(out));
+    if (!n) return false;
+    ps.bd->conn_next_cam = cam; ps.bd->conn_next = light;
+    out.n_shadow = n; out.shadow_kind = SH_CONNECT; out.alive = 1;
+    return true;
 }
 
 // Camera::is_visible up to the visibility ray, for the diffuse lamp vertices from `from_light` (cameras.rs:99-142): f(j, i,
@@ -317,7 +326,7 @@ PYR_HD bool advance_splat(const SceneView& sc, PathState& ps, const BidirCtx& cx
 // queue): the same walk as the counting pass (the lens samples replay from the saved RNG state).
 PYR_HD void write_staged(const SceneView& sc, const PathState& ps, const BidirCtx& cx, uint32_t shadow_kind, Ray* dst) {
     uint32_t next;
-    if (shadow_kind == SH_CONNECT) stage_connections(ps, cx, ps.bd->conn_light, dst, next);
+    if (shadow_kind == SH_CONNECT) { uint32_t cam = ps.bd->conn_cam, light = ps.bd->conn_light; stage_connections(ps, cx, cam, light, dst); }
     else if (shadow_kind == SH_SPLAT) { Rng replay = ps.bd->rng_saved; stage_visibility(sc, ps, cx, replay, ps.bd->conn_light, dst, next); }
 }
 
@@ -356,7 +365,7 @@ PYR_HD void generate_bidirectional(const SceneView& sc, uint64_t seed, uint32_t 
     st3(ps.bd->cam_o, co); st3(ps.bd->cam_d, cd);
     ps.tile = tile;
     ps.flags = 0;
-    ps.bd->n_light = 0; ps.bd->n_cam = 0; ps.bd->n_cam_stored = 0; ps.bd->lamp_bounces = 0; ps.bd->conn_cam = 0; ps.bd->conn_light = 0; ps.bd->conn_next = 0;
+    ps.bd->n_light = 0; ps.bd->n_cam = 0; ps.bd->n_cam_stored = 0; ps.bd->lamp_bounces = 0; ps.bd->conn_cam = 0; ps.bd->conn_light = 0; ps.bd->conn_next = 0; ps.bd->conn_next_cam = 0;
     ps.bd->cam_store_pending = 0; ps.light_events = 0; ps.n_pending = 0; ps.bounce = 0;
     out.alive = 0; out.has_main = 0; out.n_shadow = 0; out.shadow_kind = SH_NONE;
 
@@ -502,48 +511,54 @@ PYR_HD void shade_bd_camera(const SceneView& sc, PathState& ps, const BidirCtx& 
     }
     end_camera_path(sc, ps, cx, out, add);
 }
-// PH_CONNECT: evaluate the connections whose visibility rays were just traced (bidirectional.rs:310-398), stage the next ones
+// PH_CONNECT: evaluate the connections whose visibility rays were just traced (bidirectional.rs:310-398), stage the next ones.
+// Every connection of a path sample is exposed at the sample's film position with the sample's wavelengths and the same
+// weight 1 / (len(camera_path) * len(lamp_path)) (bidirectional.rs:217-218), so the step sums them per wavelength and makes
+// ONE film update per wavelength instead of one per connection (the film is additive: (sum of value * weight, sum of weight)).
 template <class Add>
 PYR_HD void shade_bd_connect(const SceneView& sc, PathState& ps, const BidirCtx& cx, const uint32_t* shadow_kinds, BidirOut& out, Add& add) {
     out.alive = 0; out.has_main = 0; out.n_shadow = 0; out.shadow_kind = SH_NONE;
     const uint32_t S = sc.renderer.spectrum_samples;
-    const CamVertex& stored = cx.cv[ps.bd->conn_cam];
-    const CamVertexHead c = stored;
-    const v3 cn = ld3(c.normal);
-    const float weight = 1.0f / (float)(ps.bd->n_cam * ps.bd->n_light);  // bidirectional.rs:217-218
-    // the sample state right after this camera vertex' `contribute`: fetched once per step (not once per connection) into the
-    // detached per-wavelength arrays
-    const SpecArray bright = cx.bright, refl = cx.refl;
-    {
-        static_assert(MAX_SPECTRUM_SAMPLES == 16, "two chunks per array");
-        Vec8 b[2], r[2];
-        b[0] = ld256(stored.bright); r[0] = ld256(stored.refl);
-        if (S > 8) { b[1] = ld256(stored.bright + 8); r[1] = ld256(stored.refl + 8); }
+    const float weight = 1.0f / (float)(ps.bd->n_cam * ps.bd->n_light);
+    // per-wavelength scratch: the camera vertex' sample state (detached arrays) and the step's sums (the sample's own brightness /
+    // reflectance arrays are dead once the camera path has been exposed)
+    const SpecArray bright = cx.bright, refl = cx.refl, sum = ps.bright, count = ps.refl;
+    for (uint32_t k = 0; k < S; ++k) { sum[k] = 0.0f; count[k] = 0.0f; }
+    float brdf = 1.0f;
+    bool cam_additional = false;
+    uint32_t cam = ps.bd->conn_cam, light = ps.bd->conn_light;
+    for_each_connection(ps, cx, cam, light,
+        [&](uint32_t, const CamVertex& stored, const Vec8& head) {
+            // the sample state right after this camera vertex' `contribute`: fetched once per vertex, not once per connection
+            brdf = head.v[3];
+            cam_additional = f_bits(head.v[7]) != 0;
+            static_assert(MAX_SPECTRUM_SAMPLES == 16, "two chunks per array");
+            Vec8 b[2], r[2];
+            b[0] = ld256(stored.bright); r[0] = ld256(stored.refl);
+            if (S > 8) { b[1] = ld256(stored.bright + 8); r[1] = ld256(stored.refl + 8); }
 #pragma unroll
-        for (uint32_t k = 0; k < MAX_SPECTRUM_SAMPLES; ++k)
-            if (k < S) { bright[k] = b[k >> 3].v[k & 7]; refl[k] = r[k >> 3].v[k & 7]; }
-    }
-    uint32_t next;
-    for_each_connection(ps, cx, ps.bd->conn_light, next, [&](uint32_t j, uint32_t i, const VertexGeometry& v, v3, v3 dir, float, float sq_distance) {
-        if (shadow_kinds[j] != KIND_MISS) return;
-        float cos_out = fabsf(dot(cn, dir));
-        float cos_in = fabsf(dot(v.normal, -dir));
-        float brdf_out = (2.0f * fabsf(dot(dir, cn))) / c.brdf;
-        float scale = cos_in * cos_out * brdf_out / (2.0f * PYR_PI * sq_distance);
-        Vec8 f[2];
-        f[0] = ld256(cx.lv[i].fold);
-        if (S > 8) f[1] = ld256(cx.lv[i].fold + 8);
-        const bool use_additional = c.use_additional != 0 && !v.tail_dispersed;
-        // brightness + (reflectance * scale) * fold(lamp_path[i..])
-        film_expose(sc.film, ps.pos[0], ps.pos[1], bright[0] + (refl[0] * scale) * f[0].v[0], ps.wl[0], weight, add);
-        if (use_additional) {
+            for (uint32_t k = 0; k < MAX_SPECTRUM_SAMPLES; ++k)
+                if (k < S) { bright[k] = b[k >> 3].v[k & 7]; refl[k] = r[k >> 3].v[k & 7]; }
+        },
+        [&](uint32_t j, uint32_t i, const VertexGeometry& v, v3, v3 cn, v3 dir, float, float sq_distance) {
+            if (shadow_kinds[j] != KIND_MISS) return;
+            float cos_out = fabsf(dot(cn, dir));
+            float cos_in = fabsf(dot(v.normal, -dir));
+            float brdf_out = (2.0f * fabsf(dot(dir, cn))) / brdf;
+            float scale = cos_in * cos_out * brdf_out / (2.0f * PYR_PI * sq_distance);
+            Vec8 f[2];
+            f[0] = ld256(cx.lv[i].fold);
+            if (S > 8) f[1] = ld256(cx.lv[i].fold + 8);
+            const uint32_t n = (cam_additional && !v.tail_dispersed) ? S : 1u;
+            // brightness + (reflectance * scale) * fold(lamp_path[i..])
 #pragma unroll
-            for (uint32_t k = 1; k < MAX_SPECTRUM_SAMPLES; ++k)
-                if (k < S) film_expose(sc.film, ps.pos[0], ps.pos[1], bright[k] + (refl[k] * scale) * f[k >> 3].v[k & 7], ps.wl[k], weight, add);
-        }
-    });
+            for (uint32_t k = 0; k < MAX_SPECTRUM_SAMPLES; ++k)
+                if (k < n) { sum[k] += bright[k] + (refl[k] * scale) * f[k >> 3].v[k & 7]; count[k] += 1.0f; }
+        });
+    for (uint32_t k = 0; k < S; ++k)
+        if (count[k] > 0.0f) film_expose_sum(sc.film, ps.pos[0], ps.pos[1], sum[k] * weight, ps.wl[k], count[k] * weight, add);
+    ps.bd->conn_cam = ps.bd->conn_next_cam;
     ps.bd->conn_light = ps.bd->conn_next;
-    if (ps.bd->conn_light >= ps.bd->n_light) { ps.bd->conn_cam += 1; ps.bd->conn_light = 0; }
     if (advance_connect(ps, cx, out)) return;
     ps.bd->phase = PH_SPLAT;
     ps.bd->conn_light = 0;

@@ -31,9 +31,16 @@ __device__ __forceinline__ Vec8 ld256(const void* p) {
                  : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7]) : "l"(p));
     return r;
 }
+#ifndef PYR_STREAM_LD
+#define PYR_STREAM_LD 0
+#endif
 __device__ __forceinline__ Vec8 ld256_stream(const void* p) {
     Vec8 r;
+#if PYR_STREAM_LD == 1   // do not allocate the line in L1 at all: L1 stays with the scene tables and the thread-local lines
+    asm volatile("ld.global.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#else
     asm volatile("ld.global.cs.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#endif
                  : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7]) : "l"(p));
     return r;
 }
@@ -84,6 +91,7 @@ template <class T> PYR_HD void store_record_stream(T* p, const T& r) { st256_str
 #if defined(__CUDA_ARCH__)
 PYR_HD float m_sin(float x) { return (float)sin((double)x); }
 PYR_HD float m_cos(float x) { return (float)cos((double)x); }
+PYR_HD void m_sincos(float x, float& s, float& c) { double ds, dc; sincos((double)x, &ds, &dc); s = (float)ds; c = (float)dc; }  // one range reduction for both
 PYR_HD float m_acos(float x) { return (float)acos((double)x); }
 PYR_HD float m_atan2(float y, float x) { return (float)atan2((double)y, (double)x); }
 PYR_HD float m_exp(float x) { return (float)exp((double)x); }
@@ -91,6 +99,7 @@ PYR_HD float m_pow(float x, float y) { return (float)pow((double)x, (double)y); 
 #else
 PYR_HD float m_sin(float x) { return sinf(x); }
 PYR_HD float m_cos(float x) { return cosf(x); }
+PYR_HD void m_sincos(float x, float& s, float& c) { s = sinf(x); c = cosf(x); }
 PYR_HD float m_acos(float x) { return acosf(x); }
 PYR_HD float m_atan2(float y, float x) { return atan2f(y, x); }
 PYR_HD float m_exp(float x) { return expf(x); }
@@ -300,7 +309,9 @@ PYR_HD v3 sample_cone(Rng& rng, v3 direction, float cos_half) {  // math.rs:125-
     float r1 = PYR_PI * 2.0f * rng.gen_f32();
     float r2 = cos_half + (1.0f - cos_half) * rng.gen_f32();
     float oneminus = sqrtf(1.0f - r2 * r2);
-    return (o1 * m_cos(r1) * oneminus + o2 * m_sin(r1) * oneminus) + direction * r2;
+    float s1, c1;
+    m_sincos(r1, s1, c1);
+    return (o1 * c1 * oneminus + o2 * s1 * oneminus) + direction * r2;
 }
 PYR_HD float solid_angle(float cos_half) { return cos_half >= 1.0f ? 0.0f : 2.0f * PYR_PI * (1.0f - cos_half); }  // math.rs:139-145
 PYR_HD v3 sample_sphere(Rng& rng) {  // math.rs:147-153
@@ -308,7 +319,10 @@ PYR_HD v3 sample_sphere(Rng& rng) {  // math.rs:147-153
     float v = rng.gen_f32();
     float theta = 2.0f * PYR_PI * u;
     float phi = m_acos(2.0f * v - 1.0f);
-    return mk3(m_sin(phi) * m_cos(theta), m_sin(phi) * m_sin(theta), m_cos(phi));
+    float st, ct, sp, cp;
+    m_sincos(theta, st, ct);
+    m_sincos(phi, sp, cp);
+    return mk3(sp * ct, sp * st, cp);
 }
 PYR_HD v3 sample_hemisphere(Rng& rng, v3 direction) {  // math.rs:155-164
     v3 s = sample_sphere(rng);

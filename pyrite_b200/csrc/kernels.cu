@@ -34,7 +34,7 @@ constexpr unsigned FULL = 0xffffffffu;
 // dynamic shared memory, sized by what the scene needs: VM registers (+ visibility-ray staging in the wave kernels)
 inline size_t vm_smem(const SceneView& sc) { return (size_t)sc.vm_regs * WAVE_THREADS * sizeof(float4); }
 inline size_t wave_smem(const SceneView& sc) {
-    return vm_smem(sc) + (size_t)2 * (sc.renderer.light_samples ? sc.renderer.light_samples : 1) * WAVE_THREADS * sizeof(float4) +
+    return vm_smem(sc) + (size_t)stage_quads(sc.renderer.light_samples) * WAVE_THREADS * sizeof(float4) +
            (size_t)4 * sc.renderer.spectrum_samples * WAVE_THREADS * sizeof(float);  // colour cache + wl / bright / refl
 }
 
@@ -88,12 +88,11 @@ __device__ __forceinline__ void locate_sample(const unsigned long long* tile_fir
 // streaming hint (ld/st.global.cs) so that they do not evict the BVH and the thread-local lines from L2.
 __device__ __forceinline__ void store_ray(Ray* dst, const Ray& r) { store_record_stream(dst, r); }
 // Dynamic shared memory of the shade kernels, in float4 units: VM registers [vm_regs][thread]; staged visibility
-// rays [2 * light_samples][thread]; then floats: the fold's colour cache [S][thread] and the path's wl / bright / refl
+// rays [1 + light_samples][thread] (shared origin + one quad per ray); then floats: the fold's colour cache [S][thread] and the path's wl / bright / refl
 // arrays [3 * S][thread].
 __device__ __forceinline__ float* spectral_base(const SceneView& sc) {
 #if defined(__CUDA_ARCH__)
-    const uint32_t L = sc.renderer.light_samples ? sc.renderer.light_samples : 1u;
-    float* floats = reinterpret_cast<float*>(pyr_dyn_smem + (sc.vm_regs + 2u * L) * PYR_BLOCK);
+    float* floats = reinterpret_cast<float*>(pyr_dyn_smem + (sc.vm_regs + stage_quads(sc.renderer.light_samples)) * PYR_BLOCK);
     return floats + sc.renderer.spectrum_samples * PYR_BLOCK + threadIdx.x;
 #else
     return nullptr;

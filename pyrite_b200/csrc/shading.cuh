@@ -39,7 +39,8 @@ struct alignas(32) PathCore : PathHeader {
 struct alignas(32) BidirState {   // 80 B of state, padded to three 32-byte chunks
     uint32_t phase, n_light, n_cam, n_cam_stored, lamp_bounces, conn_cam, conn_light, conn_next;
     float cam_o[3], cam_d[3];
-    uint32_t cam_store_pending, pad2;
+    uint32_t cam_store_pending;
+    uint32_t conn_next_cam;   // connect phase: the camera vertex the next batch starts at (with conn_next = its first lamp vertex)
     Rng rng_saved;
     uint32_t pad3[4];
 };
@@ -61,21 +62,23 @@ struct PathState : PathHeader {
     BidirState* bd;
 };
 
-// What one shade step asks to be traced next.  The visibility rays are staged on chip (dynamic shared
-// memory behind the VM registers, two 16-byte halves per ray, [ray][half][thread]) in the kernels.
+// What one shade step asks to be traced next.  The visibility rays are staged on chip in the kernels (dynamic shared
+// memory behind the VM registers): the light samples of one next-event estimation leave from the same surface point, so
+// the staging area holds that origin once and a (direction, limit) quad per ray - (1 + light_samples) float4 per thread.
+PYR_HD uint32_t stage_quads(uint32_t light_samples) { return 1u + (light_samples ? light_samples : 1u); }
 struct ShadeOut {
     uint32_t alive, has_main, n_shadow, pad;
     Ray main;
 #if defined(__CUDA_ARCH__)
     uint32_t stage_base;  // first float4 of the staging area = vm_regs * PYR_BLOCK
     __device__ __forceinline__ void put_shadow(uint32_t j, const Ray& r) {
-        float4* s = pyr_dyn_smem + stage_base + (2 * j) * PYR_BLOCK + threadIdx.x;
-        s[0] = make_float4(r.o[0], r.o[1], r.o[2], __uint_as_float(r.mode));
-        s[PYR_BLOCK] = make_float4(r.d[0], r.d[1], r.d[2], r.limit);
+        float4* s = pyr_dyn_smem + stage_base + threadIdx.x;
+        if (j == 0) s[0] = make_float4(r.o[0], r.o[1], r.o[2], __uint_as_float(r.mode));  // shared by the rays of this event
+        s[(1 + j) * PYR_BLOCK] = make_float4(r.d[0], r.d[1], r.d[2], r.limit);
     }
     __device__ __forceinline__ Ray get_shadow(uint32_t j) const {
-        const float4* s = pyr_dyn_smem + stage_base + (2 * j) * PYR_BLOCK + threadIdx.x;
-        const float4 a = s[0], b = s[PYR_BLOCK];
+        const float4* s = pyr_dyn_smem + stage_base + threadIdx.x;
+        const float4 a = s[0], b = s[(1 + j) * PYR_BLOCK];
         Ray r;
         r.o[0] = a.x; r.o[1] = a.y; r.o[2] = a.z; r.mode = __float_as_uint(a.w);
         r.d[0] = b.x; r.d[1] = b.y; r.d[2] = b.z; r.limit = b.w;
@@ -112,6 +115,17 @@ PYR_HD void film_expose(const FilmRec& f, float x, float y, float brightness, fl
     add((px + py * (uint64_t)f.width) * f.bins + grain, brightness * weight, weight);
 }
 
+// Several exposures of the same bin at once: `increment` = sum of brightness * weight, `weight` = sum of weights.
+template <class Add>
+PYR_HD void film_expose_sum(const FilmRec& f, float x, float y, float increment, float wavelength, float weight, Add& add) {
+    uint64_t grain = f32_as_usize((wavelength - f.wavelength_start) * f.grains_per_wavelength);
+    uint64_t px, py;
+    if (!film_to_pixel(f, x, y, px, py)) return;
+    if (px >= f.width || py >= f.height) return;
+    if (grain >= f.bins) return;
+    add((px + py * (uint64_t)f.width) * f.bins + grain, increment, weight);
+}
+
 // ---------------------------------------------------------------- camera (cameras.rs:70-97)
 PYR_HD void camera_ray(const CameraRec& cam, float tx, float ty, Rng& rng, v3& origin_out, v3& dir_out) {
     float focus_x = tx / cam.view_plane * cam.focus_distance;
@@ -121,7 +135,9 @@ PYR_HD void camera_ray(const CameraRec& cam, float tx, float ty, Rng& rng, v3& o
     if (cam.aperture > 0.0f) {
         float sqrt_r = sqrtf(cam.aperture * rng.gen_f32());
         float psi = PYR_PI * 2.0f * rng.gen_f32();
-        origin = mk3(sqrt_r * m_cos(psi), sqrt_r * m_sin(psi), 0.0f);
+        float sn, cs;
+        m_sincos(psi, sn, cs);
+        origin = mk3(sqrt_r * cs, sqrt_r * sn, 0.0f);
         direction = target - origin;
     }
     origin_out = transform_point(cam.m, origin);
@@ -202,9 +218,10 @@ PYR_HD void sphere_surface(const Prim& pr, v3 position, bool want_frame, Surface
     s.tex[1] = ty / pr.b.y;
     if (want_frame) {
         // Matrix3::from_angle_y(longitude) * Matrix3::from_angle_x(latitude - pi/2)
-        float sy = m_sin(longitude), cy = m_cos(longitude);
+        float sy, cy, sx, cx;
+        m_sincos(longitude, sy, cy);
         float a = latitude - PYR_PI * 0.5f;
-        float sx = m_sin(a), cx = m_cos(a);
+        m_sincos(a, sx, cx);
         v3 yc0 = mk3(cy, 0, -sy), yc1 = mk3(0, 1, 0), yc2 = mk3(sy, 0, cy);     // columns of Ry
         v3 xc0 = mk3(1, 0, 0), xc1 = mk3(0, cx, sx), xc2 = mk3(0, -sx, cx);     // columns of Rx
         v3 r0 = mk3(yc0.x, yc1.x, yc2.x), r1 = mk3(yc0.y, yc1.y, yc2.y), r2 = mk3(yc0.z, yc1.z, yc2.z);  // rows of Ry
@@ -561,7 +578,7 @@ PYR_HD bool camera_step(const SceneView& sc, PathState& ps, const Ray* main_ray,
         uint32_t cached_n = 0;
 #if defined(__CUDA_ARCH__)
         // [wavelength][thread] floats behind the staged visibility rays
-        float* const c_base = reinterpret_cast<float*>(pyr_dyn_smem + out.stage_base + 2 * max(sc.renderer.light_samples, 1u) * PYR_BLOCK) + threadIdx.x;
+        float* const c_base = reinterpret_cast<float*>(pyr_dyn_smem + out.stage_base + stage_quads(sc.renderer.light_samples) * PYR_BLOCK) + threadIdx.x;
 #define PYR_C(k) c_base[(k) * PYR_BLOCK]
 #else
         float c_local[MAX_SPECTRUM_SAMPLES];
