@@ -8,6 +8,9 @@
 // so a slot is never idle for an iteration.  All of them append to the same ray queue / live list.
 namespace {
 
+#ifndef BD_CONNECT_BLOCKS
+#define BD_CONNECT_BLOCKS 4
+#endif
 enum : int { BD_GEN = 0, BD_LAMP = 1, BD_CAMERA = 2, BD_CONNECT = 3, BD_SPLAT = 4 };
 
 // Queue space for one block: path rays, visibility rays, the live list and the list of slots whose sample just ended.
@@ -74,7 +77,7 @@ template <int PHASE> __device__ __forceinline__ void phase_run(const WaveArgs& a
 // resident blocks per SM the compiler plans for: the camera step needs its 168 registers (3 blocks, like k_wave_simple),
 // the other phases fit 128 (4 blocks)
 template <int PHASE>
-__global__ void __launch_bounds__(WAVE_THREADS, PHASE == BD_CAMERA ? 3 : 4) k_wave_bd(const __grid_constant__ SceneView sc, const __grid_constant__ WaveArgs a) {
+__global__ void __launch_bounds__(WAVE_THREADS, PHASE == BD_CAMERA ? 3 : (PHASE == BD_CONNECT || PHASE == BD_SPLAT) ? BD_CONNECT_BLOCKS : 4) k_wave_bd(const __grid_constant__ SceneView sc, const __grid_constant__ WaveArgs a) {
     if (PHASE == BD_LAMP && blockIdx.x == 0 && threadIdx.x == 0) *a.trace_cursor = 0;  // the first kernel after k_bin_*
     uint32_t lo, hi;
     phase_run<PHASE>(a, lo, hi);
@@ -89,7 +92,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, PHASE == BD_CAMERA ? 3 : 4) k_wa
         uint32_t slot = 0;
         if (valid) slot = (PHASE != BD_GEN || g < n_sorted) ? a.bin_list[lo + g] : a.died_list[g - n_sorted];
         PathState ps;
-        bind_spectral(sc, ps);
+        bind_spectral<PHASE == BD_CONNECT || PHASE == BD_SPLAT>(sc, ps);
         ps.flags = 0;
         BidirState bd;
         ps.bd = &bd;
@@ -149,10 +152,12 @@ __global__ void __launch_bounds__(WAVE_THREADS, PHASE == BD_CAMERA ? 3 : 4) k_wa
 template <int PHASE>
 void launch_bd_phase(const SceneView& sc, const WaveArgs& a, size_t smem, int sm_count, cudaStream_t s) {
     static int per_sm = 0;  // resident blocks per SM of this phase's kernel (registers / shared memory decide)
+    static size_t per_sm_smem = ~(size_t)0;
     cudaFuncSetAttribute(k_wave_bd<PHASE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (per_sm == 0) {
+    if (per_sm == 0 || per_sm_smem != smem) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wave_bd<PHASE>, WAVE_THREADS, smem);
         if (per_sm < 1) per_sm = 1;
+        per_sm_smem = smem;
     }
     const unsigned needed = (a.grid_paths + WAVE_THREADS - 1) / WAVE_THREADS;
     const unsigned grid = std::min<unsigned>(needed, (unsigned)(sm_count * per_sm));
@@ -162,12 +167,14 @@ void launch_bd_phase(const SceneView& sc, const WaveArgs& a, size_t smem, int sm
 }  // namespace
 
 inline size_t bidir_smem(const SceneView& sc) { return wave_smem(sc) + (size_t)2 * sc.renderer.spectrum_samples * WAVE_THREADS * sizeof(float); }
+// connect / splat: wl | bright | refl | detached bright | detached refl, nothing else (bind_spectral<LEAN>)
+inline size_t bidir_lean_smem(const SceneView& sc) { return (size_t)5 * sc.renderer.spectrum_samples * WAVE_THREADS * sizeof(float); }
 void launch_wave_bidirectional(const SceneView& sc, const WaveArgs& a, int sm_count, cudaStream_t s) {
-    const size_t smem = bidir_smem(sc);
+    const size_t smem = bidir_smem(sc), lean = bidir_lean_smem(sc);
     launch_bd_phase<BD_LAMP>(sc, a, smem, sm_count, s);
     launch_bd_phase<BD_CAMERA>(sc, a, smem, sm_count, s);
-    launch_bd_phase<BD_CONNECT>(sc, a, smem, sm_count, s);
-    launch_bd_phase<BD_SPLAT>(sc, a, smem, sm_count, s);
+    launch_bd_phase<BD_CONNECT>(sc, a, lean, sm_count, s);
+    launch_bd_phase<BD_SPLAT>(sc, a, lean, sm_count, s);
     launch_bd_phase<BD_GEN>(sc, a, smem, sm_count, s);
 }
 int wave_bidirectional_launches() { return 5; }

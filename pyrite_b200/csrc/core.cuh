@@ -32,7 +32,7 @@ __device__ __forceinline__ Vec8 ld256(const void* p) {
     return r;
 }
 #ifndef PYR_STREAM_LD
-#define PYR_STREAM_LD 0
+#define PYR_STREAM_LD 1   // A/B on a B200: shade stage -2.2 % on C2, -1 % on C5 against ld.global.cs
 #endif
 __device__ __forceinline__ Vec8 ld256_stream(const void* p) {
     Vec8 r;

@@ -90,16 +90,21 @@ __device__ __forceinline__ void store_ray(Ray* dst, const Ray& r) { store_record
 // Dynamic shared memory of the shade kernels, in float4 units: VM registers [vm_regs][thread]; staged visibility
 // rays [1 + light_samples][thread] (shared origin + one quad per ray); then floats: the fold's colour cache [S][thread] and the path's wl / bright / refl
 // arrays [3 * S][thread].
+// LEAN: the layout of kernels that run no expression program and stage no rays (the bidirectional connect / splat phases):
+// only the per-wavelength arrays, from the start of the dynamic shared memory - less shared memory, more resident blocks.
+template <bool LEAN = false>
 __device__ __forceinline__ float* spectral_base(const SceneView& sc) {
 #if defined(__CUDA_ARCH__)
+    if (LEAN) return reinterpret_cast<float*>(pyr_dyn_smem) + threadIdx.x;
     float* floats = reinterpret_cast<float*>(pyr_dyn_smem + (sc.vm_regs + stage_quads(sc.renderer.light_samples)) * PYR_BLOCK);
     return floats + sc.renderer.spectrum_samples * PYR_BLOCK + threadIdx.x;
 #else
     return nullptr;
 #endif
 }
+template <bool LEAN = false>
 __device__ __forceinline__ void bind_spectral(const SceneView& sc, PathState& ps) {
-    float* base = spectral_base(sc);
+    float* base = spectral_base<LEAN>(sc);
     const uint32_t S = sc.renderer.spectrum_samples;
     ps.wl.base = base;
     ps.bright.base = base + S * WAVE_THREADS;
