@@ -2,6 +2,11 @@
 #include "scene_build.hpp"
 
 #include <algorithm>
+#include <thread>
+#include <string>
+#include <mutex>
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -444,6 +449,23 @@ Box item_box(const Item& it, const BakedScene& out) {  // Bounded for Shape (sha
     return Box::of(V3{a.x - r, a.y - r, a.z - r}, V3{a.x + r, a.y + r, a.z + r});
 }
 
+// fn(from, to) over [0, n) on a few threads (sequentially for small n); the first exception is rethrown as a BuildError
+template <class F> void parallel_ranges(size_t n, F&& fn) {
+    unsigned threads = std::min(std::thread::hardware_concurrency(), 32u);
+    if (const char* e = getenv("PYR_BUILD_THREADS")) threads = (unsigned)atoi(e);
+    if (threads <= 1 || n < 32768) { fn(0, n); return; }
+    std::string error;
+    std::mutex error_mutex;
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < threads; ++t)
+        pool.emplace_back([&, t]() {
+            try { fn(n * t / threads, n * (t + 1) / threads); }
+            catch (const std::exception& e) { std::lock_guard<std::mutex> g(error_mutex); if (error.empty()) error = e.what(); }
+        });
+    for (auto& t : pool) t.join();
+    if (!error.empty()) throw BuildError(error);
+}
+
 // ------------------------------------------------------------------ BVH (spatial/bvh.rs:13-155, 250-275, 318-370)
 struct Hull2 {
     Box all, centres;
@@ -463,10 +485,91 @@ struct TreeBuilder {
     // Builds the subtree over `ids`, emitting leaves in the reference's flattened pre-order, and
     // returns its child code.  The reference's `first` child (visited first) is the subtree of the
     // SECOND item group: the Join pops it from the node stack first (bvh.rs:39-50).
+    //
+    // The tree is a pure function of the item list (every split only looks at its own items), so subtrees are independent:
+    // the top of the tree is expanded here until the pending groups are small (`grain` items), those groups are built by a
+    // pool of threads into private builders, and the pieces are stitched together in depth-first order - the leaf ranks
+    // (the pre-order the tie rule of World::intersect is defined on) come out exactly as from a sequential build.
+    struct Frame { std::vector<uint32_t> ids; Hull2 hull; int32_t parent; int slot; int depth; };
     int32_t run(std::vector<uint32_t> root_ids, Hull2 root_hull) {
-        struct Frame { std::vector<uint32_t> ids; Hull2 hull; int32_t parent; int slot; int depth; };
+        const size_t total = root_ids.size();
+        unsigned threads = std::min(std::thread::hardware_concurrency(), 32u);
+        if (const char* e = getenv("PYR_BUILD_THREADS")) threads = (unsigned)atoi(e);
+        if (threads <= 1 || total < 65536) return run_sequential(Frame{std::move(root_ids), root_hull, -1, 0, 0}, true);
+        // 1. the top of the tree, sequentially; groups of at most `grain` items become tasks (in depth-first order)
+        const size_t grain = std::max<size_t>(total / (threads * 8), 1024);
+        std::vector<Frame> tasks;
         std::vector<Frame> stack;
         stack.push_back(Frame{std::move(root_ids), root_hull, -1, 0, 0});
+        int32_t root_code = 0;
+        bool root_is_task = false;
+        while (!stack.empty()) {
+            Frame f = std::move(stack.back());
+            stack.pop_back();
+            if (f.ids.size() <= grain) {
+                if (f.parent < 0) root_is_task = true;
+                tasks.push_back(std::move(f));
+                continue;
+            }
+            if (f.depth > max_depth) max_depth = f.depth;
+            std::vector<uint32_t> group_a, group_b;
+            Hull2 hull_a{}, hull_b{};
+            split(f.ids, f.hull, group_a, hull_a, group_b, hull_b);
+            const int32_t code = (int32_t)interiors.size();
+            Interior in;
+            in.box[0] = hull_b.all; in.box[1] = hull_a.all;
+            in.child[0] = in.child[1] = 0;
+            interiors.push_back(in);
+            stack.push_back(Frame{std::move(group_a), hull_a, code, 1, f.depth + 1});
+            stack.push_back(Frame{std::move(group_b), hull_b, code, 0, f.depth + 1});
+            if (f.parent < 0) root_code = code; else interiors[f.parent].child[f.slot] = code;
+        }
+        // 2. the tasks, in parallel, each into its own builder (local leaf ranks and interior indices)
+        std::vector<TreeBuilder> parts;
+        parts.reserve(tasks.size());
+        for (size_t i = 0; i < tasks.size(); ++i) parts.push_back(TreeBuilder{items, out, {}, {}});
+        std::vector<int32_t> part_root(tasks.size(), 0);
+        std::atomic<size_t> next{0};
+        std::string error;
+        std::mutex error_mutex;
+        auto worker = [&]() {
+            for (;;) {
+                const size_t i = next.fetch_add(1);
+                if (i >= tasks.size()) return;
+                try {
+                    Frame f = std::move(tasks[i]);
+                    const int32_t parent = f.parent;
+                    const int slot = f.slot;
+                    f.parent = -1;
+                    part_root[i] = parts[i].run_sequential(std::move(f), false);
+                    tasks[i].parent = parent; tasks[i].slot = slot;
+                } catch (const std::exception& e) {
+                    std::lock_guard<std::mutex> g(error_mutex);
+                    if (error.empty()) error = e.what();
+                }
+            }
+        };
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < threads; ++t) pool.emplace_back(worker);
+        for (auto& t : pool) t.join();
+        if (!error.empty()) throw BuildError(error);
+        // 3. stitch in depth-first (task) order: leaf ranks and interior indices shift by what came before
+        for (size_t i = 0; i < tasks.size(); ++i) {
+            TreeBuilder& p = parts[i];
+            const int32_t rank_base = (int32_t)order.size(), interior_base = (int32_t)interiors.size();
+            auto remap = [&](int32_t code) { return code < 0 ? ~(~code + rank_base) : code + interior_base; };
+            order.insert(order.end(), p.order.begin(), p.order.end());
+            for (Interior in : p.interiors) { in.child[0] = remap(in.child[0]); in.child[1] = remap(in.child[1]); interiors.push_back(in); }
+            if (p.max_depth > max_depth) max_depth = p.max_depth;
+            const int32_t code = remap(part_root[i]);
+            if (tasks[i].parent < 0) root_code = code; else interiors[tasks[i].parent].child[tasks[i].slot] = code;
+        }
+        (void)root_is_task;
+        return root_code;
+    }
+    int32_t run_sequential(Frame root, bool) {
+        std::vector<Frame> stack;
+        stack.push_back(std::move(root));
         int32_t root_code = 0;
         while (!stack.empty()) {
             Frame f = std::move(stack.back());
@@ -590,8 +693,23 @@ std::vector<TileRec> make_tiles(uint32_t width, uint32_t height, uint32_t tile_s
     return tiles;
 }
 
+namespace {
+struct BuildTimer {  // PYR_BUILD_TIMING=1: phase times of the scene build on stderr
+    bool on = getenv("PYR_BUILD_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void lap(const char* what) {
+        if (!on) return;
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[scene build] %-28s %.3f s\n", what, std::chrono::duration<double>(now - t).count());
+        t = now;
+    }
+};
+}  // namespace
+
 BakedScene build_scene(const Document& input) {
+    BuildTimer timer;
     Document doc = input;  // material flattening appends expression nodes
+    timer.lap("copy of the document");
     BakedScene out;
     Folder fold{doc};
     SceneView& sv = out.view;
@@ -770,15 +888,20 @@ BakedScene build_scene(const Document& input) {
                     const M4 place = o.has_transform ? placement(o.transform) : M4::identity();
                     const float factor = o.mesh_scale.some ? fold.scalar(o.mesh_scale.ex) : 1.0f;
                     const size_t count = part.corners.size() / 9;
-                    for (size_t t = 0; t < count; ++t) {
-                        Item it = triangle_item(mesh, &part.corners[9 * t], mat);
-                        for (auto& c : it.c) c.p = scale(c.p, factor);                                  // Shape::scale (shapes/mod.rs:290-316)
-                        for (auto& c : it.c) transform_corner_normal(c, place);                          // Shape::transform (:318-344)
-                        for (auto& c : it.c) c.p = xform_point(place, c.p);
-                        it.object_id = (uint32_t)items.size();
-                        if (glows) lamp_seeds.push_back({true, it.object_id, LampRec{}});
-                        items.push_back(it);
-                    }
+                    const size_t first = items.size();
+                    items.resize(first + count);
+                    // every triangle is independent and its place in `items` is known: big meshes are converted by a few threads
+                    parallel_ranges(count, [&](size_t from, size_t to) {
+                        for (size_t t = from; t < to; ++t) {
+                            Item it = triangle_item(mesh, &part.corners[9 * t], mat);
+                            for (auto& c : it.c) c.p = scale(c.p, factor);                                  // Shape::scale (shapes/mod.rs:290-316)
+                            for (auto& c : it.c) transform_corner_normal(c, place);                          // Shape::transform (:318-344)
+                            for (auto& c : it.c) c.p = xform_point(place, c.p);
+                            it.object_id = (uint32_t)(first + t);
+                            items[first + t] = it;
+                        }
+                    });
+                    if (glows) for (size_t t = 0; t < count; ++t) lamp_seeds.push_back({true, (uint32_t)(first + t), LampRec{}});
                 }
                 break;
             }
@@ -797,8 +920,9 @@ BakedScene build_scene(const Document& input) {
         }
     }
     out.n_objects = (uint32_t)items.size();
-    for (auto& it : items) it.box = item_box(it, out);
+    parallel_ranges(items.size(), [&](size_t from, size_t to) { for (size_t i = from; i < to; ++i) items[i].box = item_box(items[i], out); });
 
+    timer.lap("materials, items, boxes");
     // ---- BVH + rank order
     TreeBuilder tb{items, out, {}, {}};
     if (!items.empty()) {
@@ -819,7 +943,9 @@ BakedScene build_scene(const Document& input) {
     out.prims.resize(items.size());
     out.tri_shade.resize(items.size());
     if (any_normal_map) out.tri_frames.resize(items.size());
-    for (uint32_t rank = 0; rank < tb.order.size(); ++rank) {
+    timer.lap("BVH build");
+    parallel_ranges(tb.order.size(), [&](size_t rank_from, size_t rank_to) {
+    for (uint32_t rank = (uint32_t)rank_from; rank < (uint32_t)rank_to; ++rank) {
         const Item& it = items[tb.order[rank]];
         out.rank_of_object[it.object_id] = rank;
         Prim p;
@@ -852,6 +978,7 @@ BakedScene build_scene(const Document& input) {
         out.prims[rank] = p;
         out.tri_shade[rank] = ts;
     }
+    });
     // fold the binary tree into 4-wide nodes: a Node4 per binary node that is the root or a grandchild-level entry
     if (!tb.interiors.empty()) {
         std::vector<int32_t> node4_of(tb.interiors.size(), -1);
@@ -898,6 +1025,7 @@ BakedScene build_scene(const Document& input) {
         }
     }
 
+    timer.lap("primitive records + Node4 fold");
     // ---- lamps, in the order the reference collects them (world.rs:75-83, 250-262)
     for (const auto& seed : lamp_seeds) {
         LampRec l = seed.rec;

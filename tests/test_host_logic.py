@@ -217,3 +217,28 @@ def test_ir_spec_is_sufficient_to_write_a_project_by_hand():
     emu2 = Emu(ours, (8, 16, 64))
     emu2.render(seed=3)
     assert np.array_equal(emu.film(), emu2.film())
+
+
+def test_parallel_scene_build_equals_the_sequential_one(monkeypatch):
+    """Big meshes are converted and their BVH is built by several host threads (scene_build.cpp): subtrees are independent, the
+    pieces are stitched in depth-first order, so the leaf pre-order (the tie rule of World::intersect) and every hit must be
+    exactly those of the one-thread build - and of the oracle."""
+    from emu_lib import Emu
+    from oracle_lib import Oracle
+
+    from pyrite_b200 import scenes
+
+    ir = P.serialize_project(scenes.dragon(width=64, height=48, spp=1, mesh=scenes.dragon_mesh(400, 100)))  # 80,000 triangles: above the threshold
+    monkeypatch.setenv("PYR_BUILD_THREADS", "4")
+    many = Emu(ir, (48, 64, 64))
+    monkeypatch.setenv("PYR_BUILD_THREADS", "1")
+    one = Emu(ir, (48, 64, 64))
+    o = Oracle(ir)
+    assert many.info == one.info
+    assert np.array_equal(many.leaf_order(), one.leaf_order()) and np.array_equal(many.leaf_order(), o.bvh_leaf_order())
+    rays = o.gen_rays(1, 3000, seed=4)
+    a, _ = many.trace(rays)
+    b, _ = one.trace(rays)
+    w, _ = o.trace(rays)
+    for f in ("prim_id", "kind", "t", "u", "v"):
+        assert np.array_equal(a[f], b[f]) and np.array_equal(a[f], w[f])
