@@ -402,6 +402,8 @@ def run_product(args):
 
     for w in range(args.warmup):
         step(w)
+    if world > 1:
+        r.film_reduce(0)   # warm-up of the collective too (NCCL sizes its buffers at the first large reduction)
     r.counters(reset=True)
     sampler = ClockSampler(local)
     if rank == 0:

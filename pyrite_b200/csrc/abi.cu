@@ -93,6 +93,40 @@ template <class T> void upload(DeviceBuffer& b, const std::vector<T>& v, cudaStr
 
 }  // namespace
 
+// One wavefront: a pool of path slots with its queues, sort buffers and counters.  A render drives one lane on the context's
+// stream, or two lanes of half the pool each on two streams of their own: the shade kernels wait on memory latency with few
+// warps per SM and leave most issue slots idle, the traversal kernel is issue-bound - two independent wavefronts let the GPU
+// run the one lane's traversal under the other lane's shading.  Path samples are handed out from ONE counter and every
+// sample owns its RNG stream, so the film does not depend on which lane renders a sample.
+struct Lane {
+    cudaStream_t own_stream = nullptr;  // two-lane renders
+    cudaEvent_t batch_done = nullptr;
+    unsigned long long* pinned = nullptr;  // [0] ray counts, [1] next sample, [2] live-slot count
+    DeviceBuffer paths, pend, bidir, rays[2], hits, shadow_kinds, march_queue[2], march_key, light_vertices, cam_vertices, bin_count, bin_first, bin_fill,
+        bin_keys, bin_list, live_list, died_list, scalars;
+    uint32_t pool = 0;
+    uint32_t march_capacity[2] = {0, 0};
+    // state of the running render
+    cudaStream_t stream = nullptr;
+    int cur = 0;
+    uint32_t grid_paths = 0;
+    bool finished = false;
+    // scalars: [0..1] counts A {path rays, visibility rays}, [2..3] counts B, [4] trace cursor, [8..9] march counts, [10..11] march cursors,
+    // [12..13] live-slot counts, [14] died-slot count
+    uint32_t* count(int i) const { return scalars.as<uint32_t>() + 2 * i; }
+    uint32_t* cursor() const { return scalars.as<uint32_t>() + 4; }
+    uint32_t* march_count() const { return scalars.as<uint32_t>() + 8; }
+    uint32_t* live_count(int i) const { return scalars.as<uint32_t>() + 12 + i; }
+    uint32_t* died_count() const { return scalars.as<uint32_t>() + 14; }
+    void release() {
+        DeviceBuffer* all[] = {&paths, &pend, &bidir, &rays[0], &rays[1], &hits, &shadow_kinds, &march_queue[0], &march_queue[1], &march_key, &light_vertices,
+                               &cam_vertices, &bin_count, &bin_first, &bin_fill, &bin_keys, &bin_list, &live_list, &died_list, &scalars};
+        for (DeviceBuffer* b : all) b->release();
+        pool = 0;
+    }
+};
+constexpr int MAX_LANES = 2;
+
 struct pyr_ctx {
     int device = 0;
     int sm_count = 0;
@@ -107,25 +141,20 @@ struct pyr_ctx {
     DeviceBuffer nodes, prims, tri_shade, tri_frames, planes, marched, materials, components, programs, code, spectra, spectrum_data,
         textures, texels, lamps, tiles, burns, xyz, d65;
     DeviceBuffer film, develop_params, counters, scalars, tile_first;
-    DeviceBuffer paths, pend, bidir, rays[2], hits, shadow_kinds, march_queue[2], march_key, light_vertices, cam_vertices, bin_count, bin_first, bin_fill, bin_keys, bin_list, live_list, died_list;
+    Lane lanes[MAX_LANES];
+    cudaEvent_t ev_fork = nullptr;
     uint32_t shadow_per_path = 1;
-    uint32_t march_capacity[2] = {0, 0};
     DeviceBuffer scratch_a, scratch_b;
-    uint32_t pool = 0;
     bool develop_params_valid = false;
     pyr_counters host_counters{};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     ncclComm_t comm = nullptr;   // pyr_comm_init
     int comm_ranks = 0, comm_rank = 0;
-    unsigned long long* pinned = nullptr;  // [0] ray counts, [1] next sample, [2] live-slot count
+    unsigned long long* pinned = nullptr;  // [3] sphere-tracing overflow counter
 
     size_t film_floats() const { return (size_t)view.film.width * view.film.height * view.film.bins * 2; }
-    // scalars: [0..1] counts A {path rays, visibility rays}, [2..3] counts B, [4] trace cursor, [6..7] next_sample (u64), [8..9] march counts, [10..11] march cursors, [12..13] live-slot counts, [14] died-slot count
-    uint32_t* count(int i) const { return scalars.as<uint32_t>() + 2 * i; }
+    // shared scalars: [4] work cursor of the pyr_trace* seams, [6..7] next_sample (u64): ONE counter hands out the path samples of a render
     uint32_t* cursor() const { return scalars.as<uint32_t>() + 4; }
-    uint32_t* march_count() const { return scalars.as<uint32_t>() + 8; }
-    uint32_t* live_count(int i) const { return scalars.as<uint32_t>() + 12 + i; }
-    uint32_t* died_count() const { return scalars.as<uint32_t>() + 14; }
     unsigned long long* next_sample() const { return (unsigned long long*)(scalars.as<uint32_t>() + 6); }
 };
 
@@ -187,40 +216,41 @@ void marched_per_type(const pyr_ctx* ctx, size_t out[2]) {
     for (const MarchedRec& m : ctx->scene.marched) out[m.estimator ? 1 : 0] += 1;
 }
 
-void ensure_pool(pyr_ctx* ctx, uint32_t pool) {
-    if (pool == ctx->pool && ctx->paths.p) return;
+void ensure_pool(pyr_ctx* ctx, Lane& ln, uint32_t pool) {
+    if (pool == ln.pool && ln.paths.p) return;
     const RendererRec& R = ctx->view.renderer;
     const bool bidir = R.algorithm == 1;
     ctx->shadow_per_path = bidir ? (uint32_t)bdpt_stage_rays() : std::max<uint32_t>(R.light_samples, 1);
     const size_t ray_cap = (size_t)pool * (1 + ctx->shadow_per_path);
-    ctx->paths.ensure((size_t)pool * path_state_bytes());
-    ctx->pend.ensure((size_t)pool * MAX_LIGHT_SAMPLES * pending_light_bytes());
-    ctx->bin_count.ensure(NUM_KEYS * sizeof(uint32_t));
-    ctx->bin_first.ensure((NUM_KEYS + 1) * sizeof(uint32_t));
-    ctx->bin_fill.ensure(NUM_KEYS * sizeof(uint32_t));
-    ctx->bin_keys.ensure((size_t)pool * sizeof(uint16_t));
-    ctx->bin_list.ensure((size_t)pool * sizeof(uint32_t));
-    ctx->live_list.ensure((size_t)pool * sizeof(uint32_t));
-    ctx->died_list.ensure(bidir ? (size_t)pool * sizeof(uint32_t) : 16);
-    if (bidir) ctx->bidir.ensure((size_t)pool * bidir_state_bytes());
-    ctx->rays[0].ensure(ray_cap * sizeof(Ray));
-    ctx->rays[1].ensure(ray_cap * sizeof(Ray));
-    ctx->hits.ensure((size_t)pool * sizeof(Hit));
-    ctx->shadow_kinds.ensure((size_t)pool * ctx->shadow_per_path * sizeof(uint32_t));
+    ln.scalars.ensure(16 * sizeof(uint32_t));
+    ln.paths.ensure((size_t)pool * path_state_bytes());
+    ln.pend.ensure((size_t)pool * MAX_LIGHT_SAMPLES * pending_light_bytes());
+    ln.bin_count.ensure(NUM_KEYS * sizeof(uint32_t));
+    ln.bin_first.ensure((NUM_KEYS + 1) * sizeof(uint32_t));
+    ln.bin_fill.ensure(NUM_KEYS * sizeof(uint32_t));
+    ln.bin_keys.ensure((size_t)pool * sizeof(uint16_t));
+    ln.bin_list.ensure((size_t)pool * sizeof(uint32_t));
+    ln.live_list.ensure((size_t)pool * sizeof(uint32_t));
+    ln.died_list.ensure(bidir ? (size_t)pool * sizeof(uint32_t) : 16);
+    if (bidir) ln.bidir.ensure((size_t)pool * bidir_state_bytes());
+    ln.rays[0].ensure(ray_cap * sizeof(Ray));
+    ln.rays[1].ensure(ray_cap * sizeof(Ray));
+    ln.hits.ensure((size_t)pool * sizeof(Hit));
+    ln.shadow_kinds.ensure((size_t)pool * ctx->shadow_per_path * sizeof(uint32_t));
     if (ctx->view.n_marched) {
         size_t per_type[2];
         marched_per_type(ctx, per_type);
-        ctx->march_queue[0].ensure(ray_cap * per_type[0] * sizeof(uint2));
-        ctx->march_queue[1].ensure(ray_cap * per_type[1] * sizeof(uint2));
-        ctx->march_capacity[0] = (uint32_t)std::min<size_t>(ray_cap * per_type[0], 0xFFFFFFFFull);
-        ctx->march_capacity[1] = (uint32_t)std::min<size_t>(ray_cap * per_type[1], 0xFFFFFFFFull);
-        ctx->march_key.ensure((size_t)pool * sizeof(unsigned long long));
+        ln.march_queue[0].ensure(ray_cap * per_type[0] * sizeof(uint2));
+        ln.march_queue[1].ensure(ray_cap * per_type[1] * sizeof(uint2));
+        ln.march_capacity[0] = (uint32_t)std::min<size_t>(ray_cap * per_type[0], 0xFFFFFFFFull);
+        ln.march_capacity[1] = (uint32_t)std::min<size_t>(ray_cap * per_type[1], 0xFFFFFFFFull);
+        ln.march_key.ensure((size_t)pool * sizeof(unsigned long long));
     }
     if (bidir) {
-        ctx->light_vertices.ensure((size_t)pool * (R.light_bounces + 1) * light_vertex_bytes());
-        ctx->cam_vertices.ensure((size_t)pool * std::max<uint32_t>(R.bounces, 1) * cam_vertex_bytes());
+        ln.light_vertices.ensure((size_t)pool * (R.light_bounces + 1) * light_vertex_bytes());
+        ln.cam_vertices.ensure((size_t)pool * std::max<uint32_t>(R.bounces, 1) * cam_vertex_bytes());
     }
-    ctx->pool = pool;
+    ln.pool = pool;
 }
 
 // Paths in flight.  Every wavefront iteration pays fixed costs (the tail of the persistent traversal kernel, launch
@@ -283,6 +313,12 @@ pyr_status pyr_init(int32_t device, pyr_ctx** out) {
         CU(cudaEventCreate(&ctx->ev0));
         CU(cudaEventCreate(&ctx->ev1));
         CU(cudaMallocHost((void**)&ctx->pinned, 4 * sizeof(unsigned long long)));
+        CU(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+        for (Lane& ln : ctx->lanes) {
+            CU(cudaStreamCreateWithFlags(&ln.own_stream, cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&ln.batch_done, cudaEventDisableTiming));
+            CU(cudaMallocHost((void**)&ln.pinned, 4 * sizeof(unsigned long long)));
+        }
         ctx->counters.ensure(sizeof(DeviceCounters));
         CU(cudaMemsetAsync(ctx->counters.p, 0, sizeof(DeviceCounters), ctx->stream));
         ctx->scalars.ensure(16 * sizeof(uint32_t));
@@ -303,8 +339,14 @@ void pyr_shutdown(pyr_ctx* ctx) {
     DeviceBuffer* all[] = {&ctx->nodes, &ctx->prims, &ctx->tri_shade, &ctx->tri_frames, &ctx->planes, &ctx->marched, &ctx->materials,
                            &ctx->components, &ctx->programs, &ctx->code, &ctx->spectra, &ctx->spectrum_data, &ctx->textures, &ctx->texels,
                            &ctx->lamps, &ctx->tiles, &ctx->burns, &ctx->xyz, &ctx->d65, &ctx->film, &ctx->develop_params, &ctx->counters,
-                           &ctx->scalars, &ctx->tile_first, &ctx->paths, &ctx->pend, &ctx->bidir, &ctx->bin_count, &ctx->bin_first, &ctx->bin_fill, &ctx->bin_keys, &ctx->bin_list, &ctx->live_list, &ctx->died_list, &ctx->rays[0], &ctx->rays[1], &ctx->hits, &ctx->shadow_kinds, &ctx->march_queue[0], &ctx->march_queue[1], &ctx->march_key, &ctx->light_vertices, &ctx->cam_vertices,
-                           &ctx->scratch_a, &ctx->scratch_b};
+                           &ctx->scalars, &ctx->tile_first, &ctx->scratch_a, &ctx->scratch_b};
+    for (Lane& ln : ctx->lanes) {
+        ln.release();
+        if (ln.pinned) cudaFreeHost(ln.pinned);
+        if (ln.batch_done) cudaEventDestroy(ln.batch_done);
+        if (ln.own_stream) cudaStreamDestroy(ln.own_stream);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     for (DeviceBuffer* b : all) b->release();
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -333,7 +375,7 @@ pyr_status pyr_project_load(pyr_ctx* ctx, const void* ir_blob, size_t bytes) {
         // freed memory.
         CU(cudaStreamSynchronize(s));
         ctx->loaded = false;
-        ctx->pool = 0;
+        for (Lane& ln : ctx->lanes) ln.pool = 0;
         ctx->develop_params_valid = false;
         upload(ctx->nodes, baked.nodes, s);
         upload(ctx->prims, baked.prims, s);
@@ -367,7 +409,7 @@ pyr_status pyr_project_load(pyr_ctx* ctx, const void* ir_blob, size_t bytes) {
         ctx->film.ensure(ctx->film_floats() * sizeof(float));
         CU(cudaMemsetAsync(ctx->film.p, 0, ctx->film_floats() * sizeof(float), s));
         ctx->develop_params_valid = false;
-        ctx->pool = 0;
+        for (Lane& ln : ctx->lanes) ln.pool = 0;
         CU(cudaStreamSynchronize(s));
         ctx->loaded = true;
     });
@@ -465,17 +507,21 @@ pyr_status pyr_render(pyr_ctx* ctx, const pyr_render_params* params, pyr_progres
         const unsigned long long total = first.back();
         upload(ctx->tile_first, first, s);
 
-        uint32_t pool = p.pool_paths ? p.pool_paths : default_pool(ctx);
-        if ((unsigned long long)pool > total) pool = (uint32_t)std::max<unsigned long long>(total, 1);
-        pool = (pool + 127u) & ~127u;
-        ensure_pool(ctx, pool);
-        if (p.reset_film) CU(cudaMemsetAsync(ctx->film.p, 0, ctx->film_floats() * sizeof(float), s));
-        CU(cudaMemsetAsync(ctx->scalars.p, 0, 16 * sizeof(uint32_t), s));
-        launch_pool_reset(ctx->paths.as<PathCore>(), pool, ctx->live_list.as<uint32_t>(), ctx->live_count(0), s);
-
-        const int trace_blocks = ctx->sm_count * trace_blocks_per_sm();
         const int stats = (p.flags & PYR_RENDER_STATS) ? 1 : 0;
         const bool timing = (p.flags & PYR_RENDER_TIMING) != 0;
+        uint32_t pool = p.pool_paths ? p.pool_paths : default_pool(ctx);
+        if ((unsigned long long)pool > total) pool = (uint32_t)std::max<unsigned long long>(total, 1);
+        // Two wavefronts of half the pool on two streams when the job is big enough to fill both (see Lane); the per-kernel
+        // timing and statistics modes run one wavefront so that their numbers are those of a kernel running alone.
+        int n_lanes = (!timing && !stats && pool >= (1u << 20)) ? 2 : 1;
+        if (const char* e = getenv("PYR_LANES")) n_lanes = std::max(1, std::min(MAX_LANES, atoi(e)));
+        if (timing || stats) n_lanes = 1;
+        const uint32_t lane_pool = ((pool + n_lanes - 1) / n_lanes + 127u) & ~127u;
+        for (int l = 0; l < n_lanes; ++l) ensure_pool(ctx, ctx->lanes[l], lane_pool);
+        if (p.reset_film) CU(cudaMemsetAsync(ctx->film.p, 0, ctx->film_floats() * sizeof(float), s));
+        CU(cudaMemsetAsync(ctx->scalars.p, 0, 16 * sizeof(uint32_t), s));
+
+        const int trace_blocks = ctx->sm_count * trace_blocks_per_sm();
         const int BATCH = 4;
         if (timing)
             while (ctx->timing_events.size() < (size_t)BATCH * 3) {
@@ -483,32 +529,43 @@ pyr_status pyr_render(pyr_ctx* ctx, const pyr_render_params* params, pyr_progres
                 CU(cudaEventCreate(&e));
                 ctx->timing_events.push_back(e);
             }
-        const BinBuffers bins{ctx->bin_count.as<uint32_t>(), ctx->bin_first.as<uint32_t>(), ctx->bin_fill.as<uint32_t>(), ctx->bin_keys.as<uint16_t>(),
-                              ctx->bin_list.as<uint32_t>()};
-        CU(cudaMemsetAsync(bins.count, 0, NUM_KEYS * sizeof(uint32_t), s));
         uint32_t cluster_shift = 0;  // the hit primitive's rank >> shift = one of (at most) BIN_CLUSTERS subtrees of the BVH
         while ((ctx->view.n_prims >> cluster_shift) > BIN_CLUSTERS) ++cluster_shift;
         CU(cudaEventRecord(ctx->ev0, s));
-        int cur = 0;
-        uint32_t grid_paths = pool;  // once every sample has been started the live-slot count only falls: the last value read bounds the grids
-        unsigned long long iterations = 0, launches = 1;
-        bool cancelled = false;
-        for (;;) {
+        if (n_lanes > 1) CU(cudaEventRecord(ctx->ev_fork, s));
+        for (int l = 0; l < n_lanes; ++l) {
+            Lane& ln = ctx->lanes[l];
+            ln.stream = n_lanes > 1 ? ln.own_stream : s;
+            if (n_lanes > 1) CU(cudaStreamWaitEvent(ln.stream, ctx->ev_fork, 0));
+            ln.cur = 0;
+            ln.grid_paths = lane_pool;  // once every sample has been started the live-slot count only falls: the last value read bounds the grids
+            ln.finished = false;
+            CU(cudaMemsetAsync(ln.scalars.p, 0, 16 * sizeof(uint32_t), ln.stream));
+            CU(cudaMemsetAsync(ln.bin_count.p, 0, NUM_KEYS * sizeof(uint32_t), ln.stream));
+            launch_pool_reset(ln.paths.as<PathCore>(), lane_pool, ln.live_list.as<uint32_t>(), ln.live_count(0), ln.stream);
+        }
+        unsigned long long iterations = 0, launches = (unsigned long long)n_lanes;
+
+        // one wavefront iteration of a lane: sort the live slots, shade / regenerate, trace (and sphere-trace) what they asked for
+        auto enqueue_batch = [&](Lane& ln) {
+            cudaStream_t ls = ln.stream;
+            const BinBuffers bins{ln.bin_count.as<uint32_t>(), ln.bin_first.as<uint32_t>(), ln.bin_fill.as<uint32_t>(), ln.bin_keys.as<uint16_t>(),
+                                  ln.bin_list.as<uint32_t>()};
             for (int b = 0; b < BATCH; ++b) {
-                const int nxt = cur ^ 1;
+                const int cur = ln.cur, nxt = cur ^ 1;
                 WaveArgs a{};
-                a.paths = ctx->paths.as<PathCore>();
-                a.pend = ctx->pend.as<PendingLight>();
-                a.bidir = ctx->bidir.as<BidirState>();
-                a.pool = pool;
-                a.grid_paths = std::max<uint32_t>(grid_paths, 1);
-                a.rays_in = ctx->rays[cur].as<Ray>();
-                a.hits_in = ctx->hits.as<Hit>();
-                a.shadow_kinds_in = ctx->shadow_kinds.as<uint32_t>();
-                a.rays_out = ctx->rays[nxt].as<Ray>();
-                a.count_out = ctx->count(nxt);
-                a.shadow_offset = pool;
-                a.trace_cursor = ctx->cursor();
+                a.paths = ln.paths.as<PathCore>();
+                a.pend = ln.pend.as<PendingLight>();
+                a.bidir = ln.bidir.as<BidirState>();
+                a.pool = lane_pool;
+                a.grid_paths = std::max<uint32_t>(ln.grid_paths, 1);
+                a.rays_in = ln.rays[cur].as<Ray>();
+                a.hits_in = ln.hits.as<Hit>();
+                a.shadow_kinds_in = ln.shadow_kinds.as<uint32_t>();
+                a.rays_out = ln.rays[nxt].as<Ray>();
+                a.count_out = ln.count(nxt);
+                a.shadow_offset = lane_pool;
+                a.trace_cursor = ln.cursor();
                 a.next_sample = ctx->next_sample();
                 a.total_samples = total;
                 a.tile_first = ctx->tile_first.as<unsigned long long>();
@@ -517,68 +574,85 @@ pyr_status pyr_render(pyr_ctx* ctx, const pyr_render_params* params, pyr_progres
                 a.sample_stride = stride;
                 a.film = ctx->film.as<float>();
                 a.counters = ctx->counters.as<DeviceCounters>();
-                a.light_vertices = ctx->light_vertices.as<LightVertex>();
-                a.cam_vertices = ctx->cam_vertices.as<CamVertex>();
+                a.light_vertices = ln.light_vertices.as<LightVertex>();
+                a.cam_vertices = ln.cam_vertices.as<CamVertex>();
                 a.light_stride = R.light_bounces + 1;
                 a.cam_stride = std::max<uint32_t>(R.bounces, 1);
-                a.ray_capacity = (uint32_t)(ctx->rays[0].bytes / sizeof(Ray));
-                if (timing) CU(cudaEventRecord(ctx->timing_events[3 * b], s));
-                a.live_list = ctx->live_list.as<uint32_t>();
-                a.live_count_in = ctx->live_count(cur);
-                a.live_count_out = ctx->live_count(nxt);
-                a.died_list = ctx->died_list.as<uint32_t>();
-                a.died_count = ctx->died_count();
-                a.bin_first = ctx->bin_first.as<uint32_t>();
-                a.bin_list = ctx->bin_list.as<uint32_t>();
-                launch_bin(a, bins, cluster_shift, R.algorithm == 1, s);
-                if (R.algorithm == 0) launch_wave_simple(ctx->view, a, s); else launch_wave_bidirectional(ctx->view, a, ctx->sm_count, s);
-                if (timing) CU(cudaEventRecord(ctx->timing_events[3 * b + 1], s));
+                a.ray_capacity = (uint32_t)(ln.rays[0].bytes / sizeof(Ray));
+                if (timing) CU(cudaEventRecord(ctx->timing_events[3 * b], ls));
+                a.live_list = ln.live_list.as<uint32_t>();
+                a.live_count_in = ln.live_count(cur);
+                a.live_count_out = ln.live_count(nxt);
+                a.died_list = ln.died_list.as<uint32_t>();
+                a.died_count = ln.died_count();
+                a.bin_first = ln.bin_first.as<uint32_t>();
+                a.bin_list = ln.bin_list.as<uint32_t>();
+                launch_bin(a, bins, cluster_shift, R.algorithm == 1, ls);
+                if (R.algorithm == 0) launch_wave_simple(ctx->view, a, ls); else launch_wave_bidirectional(ctx->view, a, ctx->sm_count, ls);
+                if (timing) CU(cudaEventRecord(ctx->timing_events[3 * b + 1], ls));
                 TraceArgs t{};
-                t.rays = ctx->rays[nxt].as<Ray>();
-                t.hits = ctx->hits.as<Hit>();
-                t.shadow_kinds = ctx->shadow_kinds.as<uint32_t>();
-                t.count = ctx->count(nxt);
-                t.shadow_offset = pool;
-                t.cursor = ctx->cursor();
+                t.rays = ln.rays[nxt].as<Ray>();
+                t.hits = ln.hits.as<Hit>();
+                t.shadow_kinds = ln.shadow_kinds.as<uint32_t>();
+                t.count = ln.count(nxt);
+                t.shadow_offset = lane_pool;
+                t.cursor = ln.cursor();
                 t.counters = ctx->counters.as<DeviceCounters>();
                 t.stats = stats;
-                t.march_queue[0] = ctx->march_queue[0].as<uint2>();
-                t.march_queue[1] = ctx->march_queue[1].as<uint2>();
-                t.march_count = ctx->march_count();
-                t.march_capacity[0] = ctx->march_capacity[0];
-                t.march_capacity[1] = ctx->march_capacity[1];
-                t.march_key = ctx->march_key.as<unsigned long long>();
-                if (ctx->view.n_marched) CU(cudaMemsetAsync(ctx->march_count(), 0, 4 * sizeof(uint32_t), s));
-                launch_trace(ctx->view, t, trace_blocks, s);
-                if (ctx->view.n_marched) { launch_march(ctx->view, t, trace_blocks, s); launches += 2; }
-                if (timing) CU(cudaEventRecord(ctx->timing_events[3 * b + 2], s));
-                cur = nxt;
+                t.march_queue[0] = ln.march_queue[0].as<uint2>();
+                t.march_queue[1] = ln.march_queue[1].as<uint2>();
+                t.march_count = ln.march_count();
+                t.march_capacity[0] = ln.march_capacity[0];
+                t.march_capacity[1] = ln.march_capacity[1];
+                t.march_key = ln.march_key.as<unsigned long long>();
+                if (ctx->view.n_marched) CU(cudaMemsetAsync(ln.march_count(), 0, 4 * sizeof(uint32_t), ls));
+                launch_trace(ctx->view, t, trace_blocks, ls);
+                if (ctx->view.n_marched) { launch_march(ctx->view, t, trace_blocks, ls); launches += 2; }
+                if (timing) CU(cudaEventRecord(ctx->timing_events[3 * b + 2], ls));
+                ln.cur = nxt;
                 ++iterations;
                 launches += R.algorithm == 0 ? 5 : 4 + wave_bidirectional_launches();
             }
             CU(cudaGetLastError());
-            CU(cudaMemcpyAsync(&ctx->pinned[0], ctx->count(cur), 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-            CU(cudaMemcpyAsync(&ctx->pinned[1], ctx->next_sample(), sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-            CU(cudaMemcpyAsync(&ctx->pinned[2], ctx->live_count(cur), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-            CU(cudaStreamSynchronize(s));
-            if (timing)
-                for (int b = 0; b < BATCH; ++b) {
-                    float shade_ms = 0, trace_ms = 0;
-                    CU(cudaEventElapsedTime(&shade_ms, ctx->timing_events[3 * b], ctx->timing_events[3 * b + 1]));
-                    CU(cudaEventElapsedTime(&trace_ms, ctx->timing_events[3 * b + 1], ctx->timing_events[3 * b + 2]));
-                    ctx->host_counters.shade_seconds += shade_ms * 1e-3;
-                    ctx->host_counters.trace_seconds += trace_ms * 1e-3;
-                    ctx->host_counters.shade_launches += 1;
-                    ctx->host_counters.trace_launches += 1;
+            CU(cudaMemcpyAsync(&ln.pinned[0], ln.count(ln.cur), 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ls));
+            CU(cudaMemcpyAsync(&ln.pinned[1], ctx->next_sample(), sizeof(unsigned long long), cudaMemcpyDeviceToHost, ls));
+            CU(cudaMemcpyAsync(&ln.pinned[2], ln.live_count(ln.cur), sizeof(uint32_t), cudaMemcpyDeviceToHost, ls));
+            CU(cudaEventRecord(ln.batch_done, ls));
+        };
+
+        for (int l = 0; l < n_lanes; ++l) enqueue_batch(ctx->lanes[l]);
+        bool cancelled = false;
+        unsigned long long started = 0;
+        int active = n_lanes;
+        while (active > 0 && !cancelled) {
+            for (int l = 0; l < n_lanes && !cancelled; ++l) {
+                Lane& ln = ctx->lanes[l];
+                if (ln.finished) continue;
+                CU(cudaEventSynchronize(ln.batch_done));   // the other lane's batch keeps the GPU busy meanwhile
+                if (timing)
+                    for (int b = 0; b < BATCH; ++b) {
+                        float shade_ms = 0, trace_ms = 0;
+                        CU(cudaEventElapsedTime(&shade_ms, ctx->timing_events[3 * b], ctx->timing_events[3 * b + 1]));
+                        CU(cudaEventElapsedTime(&trace_ms, ctx->timing_events[3 * b + 1], ctx->timing_events[3 * b + 2]));
+                        ctx->host_counters.shade_seconds += shade_ms * 1e-3;
+                        ctx->host_counters.trace_seconds += trace_ms * 1e-3;
+                        ctx->host_counters.shade_launches += 1;
+                        ctx->host_counters.trace_launches += 1;
+                    }
+                const uint32_t pending = (uint32_t)(ln.pinned[0] & 0xffffffffull) + (uint32_t)(ln.pinned[0] >> 32);
+                started = std::max(started, std::min<unsigned long long>(ln.pinned[1], total));
+                if (pending == 0 && started >= total) { ln.finished = true; --active; continue; }
+                if (started >= total) ln.grid_paths = (uint32_t)(ln.pinned[2] & 0xffffffffull);
+                if (cb) {
+                    uint8_t progress = total ? (uint8_t)((started * 100ull) / total) : 100;
+                    if (cb(progress, "rendering", user)) { cancelled = true; break; }
                 }
-            const uint32_t pending = (uint32_t)(ctx->pinned[0] & 0xffffffffull) + (uint32_t)(ctx->pinned[0] >> 32);
-            const unsigned long long started = std::min<unsigned long long>(ctx->pinned[1], total);
-            if (pending == 0 && started >= total) break;
-            if (started >= total) grid_paths = (uint32_t)(ctx->pinned[2] & 0xffffffffull);
-            if (cb) {
-                uint8_t progress = total ? (uint8_t)((started * 100ull) / total) : 100;
-                if (cb(progress, "rendering", user)) { cancelled = true; break; }
+                enqueue_batch(ln);
             }
+        }
+        for (int l = 0; l < n_lanes; ++l) {   // join the lanes' streams into the context's stream
+            Lane& ln = ctx->lanes[l];
+            if (n_lanes > 1) { CU(cudaEventRecord(ln.batch_done, ln.stream)); CU(cudaStreamWaitEvent(s, ln.batch_done, 0)); }
         }
         CU(cudaEventRecord(ctx->ev1, s));
         if (ctx->view.n_marched)
@@ -593,7 +667,7 @@ pyr_status pyr_render(pyr_ctx* ctx, const pyr_render_params* params, pyr_progres
         }
         ctx->host_counters.wavefront_iterations += iterations;
         ctx->host_counters.kernel_launches += launches;
-        ctx->host_counters.path_samples += cancelled ? std::min<unsigned long long>(ctx->pinned[1], total) : total;
+        ctx->host_counters.path_samples += cancelled ? started : total;
         if (cb && !cancelled) cb(100, "done", user);
         if (cancelled) throw StateError("render cancelled by the progress callback");
     });
@@ -676,6 +750,11 @@ pyr_status pyr_comm_init(pyr_ctx* ctx, int32_t n_ranks, int32_t rank, const uint
         NC(nccl().CommInitRank(&ctx->comm, n_ranks, uid, rank));
         ctx->comm_ranks = n_ranks;
         ctx->comm_rank = rank;
+        // NCCL connects the ranks at the first collective: do that here, on a few bytes, so that pyr_film_reduce costs what
+        // moving the film costs
+        ctx->scratch_a.ensure(1024);
+        NC(nccl().AllReduce(ctx->scratch_a.p, ctx->scratch_a.p, 256, ncclFloat32, ncclSum, ctx->comm, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
     });
 }
 

@@ -25,7 +25,8 @@ with api.Renderer(0) as r:
         r.render(seed=0, spp=1, pool_paths=int(os.environ.get('PYR_POOL', '0')))
         r.counters(reset=True)
     pool = int(os.environ.get('PYR_POOL', '0'))
-    secs = r.render(seed=1, spp=spp, timing=True, pool_paths=pool)
+    timing = os.environ.get('PYR_TIMING', '1') != '0'   # per-kernel timing runs ONE wavefront; PYR_TIMING=0 measures the production path
+    secs = r.render(seed=1, spp=spp, timing=timing, pool_paths=pool)
     c = r.counters()
     print(f"{scene}: {spp} spp in {secs * 1e3:.1f} ms, {c['rays'] / secs / 1e6:.0f} Mrays/s, trace {c['trace_seconds'] * 1e3:.1f} ms shade {c['shade_seconds'] * 1e3:.1f} ms, "
           f"{c['wavefront_iterations']} iterations")
