@@ -393,7 +393,10 @@ __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS) k_wave_simple(c
 // ------------------------------------------------------------------------------------------
 // Traversal stack: the first SHARED_STACK entries live in shared memory ([entry][thread], no bank
 // conflicts), deeper entries (rare) in local memory.
-constexpr int SHARED_STACK = 20;
+#ifndef PYR_SHARED_STACK
+#define PYR_SHARED_STACK 20
+#endif
+constexpr int SHARED_STACK = PYR_SHARED_STACK;
 struct SharedStack {
     int2* entries;  // &smem[threadIdx.x]: (child code, entry distance bits), one 8-byte access per push / pop
     int2 deep[BVH_STACK - SHARED_STACK];
