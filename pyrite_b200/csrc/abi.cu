@@ -143,8 +143,6 @@ struct pyr_ctx {
     DeviceBuffer film, develop_params, counters, scalars, tile_first;
     Lane lanes[MAX_LANES];
     cudaEvent_t ev_fork = nullptr;
-    size_t bvh_bytes = 0, prims_offset = 0;   // nodes | prims in ctx->nodes
-    size_t l2_persist_max = 0, l2_window_max = 0;
     uint32_t shadow_per_path = 1;
     DeviceBuffer scratch_a, scratch_b;
     bool develop_params_valid = false;
@@ -209,29 +207,6 @@ void ensure_develop_params(pyr_ctx* ctx) {
     launch_white_scan(ctx->view, ctx->develop_params.as<float>(), ctx->stream);
     CU(cudaGetLastError());
     ctx->develop_params_valid = true;
-}
-
-// The BVH (4-wide nodes + leaf primitives, ~90 MB for the 871k-triangle mesh) is what the traversal kernel gathers from at
-// random; between two traversal launches the shade kernels stream gigabytes of path state through the 126 MB L2 and evict it.
-// An access-policy window marks the BVH as persisting in L2 (and everything else on the stream as streaming), so that a
-// traversal launch finds its nodes in L2 instead of HBM.  PYR_L2_PERSIST=0 switches it off (A/B).
-void apply_l2_window(pyr_ctx* ctx, cudaStream_t stream, bool on) {
-    static const bool enabled = [] { const char* e = getenv("PYR_L2_PERSIST"); return !(e && e[0] == '0'); }();
-    if (!enabled || !ctx->l2_persist_max || !ctx->l2_window_max || !ctx->bvh_bytes) return;
-    cudaStreamAttrValue attr;
-    memset(&attr, 0, sizeof(attr));
-    if (on) {
-        const size_t window = std::min(ctx->bvh_bytes, ctx->l2_window_max);
-        attr.accessPolicyWindow.base_ptr = ctx->nodes.p;
-        attr.accessPolicyWindow.num_bytes = window;
-        attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)ctx->l2_persist_max / (double)window);
-        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-    } else {
-        attr.accessPolicyWindow.num_bytes = 0;
-    }
-    cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr);   // best effort: a refusal only loses the optimisation
-    cudaGetLastError();
 }
 
 // ray-marched shapes per distance-estimator type: each (ray, shape) pair queues at most once, so rays x shapes-of-a-type
@@ -333,8 +308,6 @@ pyr_status pyr_init(int32_t device, pyr_ctx** out) {
         CU(cudaGetDeviceProperties(&prop, device));
         ctx->sm_count = prop.multiProcessorCount;
         ctx->device_memory = prop.totalGlobalMem;
-        ctx->l2_persist_max = (size_t)std::max(prop.persistingL2CacheMaxSize, 0);
-        ctx->l2_window_max = (size_t)std::max(prop.accessPolicyMaxWindowSize, 0);
         CU(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
         ctx->stream = ctx->own_stream;
         CU(cudaEventCreate(&ctx->ev0));
@@ -404,14 +377,8 @@ pyr_status pyr_project_load(pyr_ctx* ctx, const void* ir_blob, size_t bytes) {
         ctx->loaded = false;
         for (Lane& ln : ctx->lanes) ln.pool = 0;
         ctx->develop_params_valid = false;
-        {   // the 4-wide nodes and the leaf primitives share ONE allocation: a single L2 access-policy window covers the whole BVH
-            const size_t node_bytes = (baked.nodes.size() * sizeof(Node4) + 255) & ~(size_t)255, prim_bytes = baked.prims.size() * sizeof(Prim);
-            ctx->nodes.ensure(node_bytes + prim_bytes + 256);
-            ctx->bvh_bytes = node_bytes + prim_bytes;
-            ctx->prims_offset = node_bytes;
-            if (!baked.nodes.empty()) CU(cudaMemcpyAsync(ctx->nodes.p, baked.nodes.data(), baked.nodes.size() * sizeof(Node4), cudaMemcpyHostToDevice, s));
-            if (!baked.prims.empty()) CU(cudaMemcpyAsync((char*)ctx->nodes.p + node_bytes, baked.prims.data(), prim_bytes, cudaMemcpyHostToDevice, s));
-        }
+        upload(ctx->nodes, baked.nodes, s);
+        upload(ctx->prims, baked.prims, s);
         upload(ctx->tri_shade, baked.tri_shade, s);
         upload(ctx->tri_frames, baked.tri_frames, s);
         upload(ctx->planes, baked.planes, s);
@@ -430,7 +397,7 @@ pyr_status pyr_project_load(pyr_ctx* ctx, const void* ir_blob, size_t bytes) {
         upload(ctx->xyz, baked.xyz, s);
         upload(ctx->d65, baked.d65, s);
         SceneView v = baked.view;
-        v.nodes = ctx->nodes.as<Node4>(); v.prims = reinterpret_cast<const Prim*>((const char*)ctx->nodes.p + ctx->prims_offset); v.tri_shade = ctx->tri_shade.as<TriShade>();
+        v.nodes = ctx->nodes.as<Node4>(); v.prims = ctx->prims.as<Prim>(); v.tri_shade = ctx->tri_shade.as<TriShade>();
         v.tri_frames = ctx->tri_frames.as<TriFrames>(); v.planes = ctx->planes.as<PlaneRec>(); v.marched = ctx->marched.as<MarchedRec>();
         v.materials = ctx->materials.as<MaterialRec>(); v.components = ctx->components.as<ComponentRec>();
         v.programs = ctx->programs.as<ProgramRec>(); v.code = ctx->code.as<Instr>(); v.spectra = ctx->spectra.as<SpectrumRec>();
@@ -443,7 +410,6 @@ pyr_status pyr_project_load(pyr_ctx* ctx, const void* ir_blob, size_t bytes) {
         CU(cudaMemsetAsync(ctx->film.p, 0, ctx->film_floats() * sizeof(float), s));
         ctx->develop_params_valid = false;
         for (Lane& ln : ctx->lanes) ln.pool = 0;
-        if (ctx->l2_persist_max) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min(ctx->l2_persist_max, ctx->bvh_bytes)); cudaGetLastError(); }
         CU(cudaStreamSynchronize(s));
         ctx->loaded = true;
     });
@@ -571,7 +537,6 @@ pyr_status pyr_render(pyr_ctx* ctx, const pyr_render_params* params, pyr_progres
             Lane& ln = ctx->lanes[l];
             ln.stream = n_lanes > 1 ? ln.own_stream : s;
             if (n_lanes > 1) CU(cudaStreamWaitEvent(ln.stream, ctx->ev_fork, 0));
-            apply_l2_window(ctx, ln.stream, true);
             ln.cur = 0;
             ln.grid_paths = lane_pool;  // once every sample has been started the live-slot count only falls: the last value read bounds the grids
             ln.finished = false;
@@ -687,7 +652,6 @@ pyr_status pyr_render(pyr_ctx* ctx, const pyr_render_params* params, pyr_progres
         }
         for (int l = 0; l < n_lanes; ++l) {   // join the lanes' streams into the context's stream
             Lane& ln = ctx->lanes[l];
-            apply_l2_window(ctx, ln.stream, false);
             if (n_lanes > 1) { CU(cudaEventRecord(ln.batch_done, ln.stream)); CU(cudaStreamWaitEvent(s, ln.batch_done, 0)); }
         }
         CU(cudaEventRecord(ctx->ev1, s));
