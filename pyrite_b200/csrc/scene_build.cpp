@@ -963,7 +963,7 @@ BakedScene build_scene(const Document& input) {
                 n[0] = it.c[k].n.x; n[1] = it.c[k].n.y; n[2] = it.c[k].n.z;
                 t[0] = it.c[k].t.x; t[1] = it.c[k].t.y;
             }
-            ts.area = 0.5f * length(cross3(e1, e2));  // Shape::surface_area (shapes/mod.rs:279-283)
+            ts.material = it.material;
             if (any_normal_map) out.tri_frames[rank] = TriFrames{quat4(it.c[0].frame), quat4(it.c[1].frame), quat4(it.c[2].frame)};
         } else if (it.kind == KIND_SPHERE) {
             p.a = pack4(it.centre.x, it.centre.y, it.centre.z, it.radius);

@@ -197,8 +197,10 @@ struct Surface {
     float tex[2];
     uint32_t material;
 };
-PYR_HD void triangle_surface(const SceneView& sc, uint32_t rank, float u, float v, bool want_frame, Surface& s) {
+PYR_HD void triangle_surface(const SceneView& sc, uint32_t rank, float u, float v, Surface& s) {
     const TriShade ts = sc.tri_shade[rank];
+    s.material = ts.material;
+    const bool want_frame = sc.tri_frames != nullptr && sc.materials[ts.material].normal_map_program >= 0;
     float w = 1.0f - (u + v);
     s.normal = normalize((ld3(ts.n1) * w + ld3(ts.n2) * u) + ld3(ts.n3) * v);
     s.tex[0] = (ts.t1[0] * w + ts.t2[0] * u) + ts.t3[0] * v;
@@ -264,13 +266,15 @@ PYR_HD void hit_surface(const SceneView& sc, v3 o, v3 d, const Hit& h, Surface& 
         plane_surface(pl, p, s);
         return;
     }
+    if (h.kind == KIND_TRIANGLE) {   // the triangle's shading record carries its material: no Prim fetch
+        s.position = o + d * h.t;
+        triangle_surface(sc, h.rank, h.u, h.v, s);
+        return;
+    }
     const Prim pr = sc.prims[h.rank];
     s.material = prim_material(pr);
     bool want_frame = sc.materials[s.material].normal_map_program >= 0;
-    if (h.kind == KIND_TRIANGLE) {
-        s.position = o + d * h.t;
-        triangle_surface(sc, h.rank, h.u, h.v, want_frame, s);
-    } else if (h.kind == KIND_SPHERE) {
+    if (h.kind == KIND_SPHERE) {
         float t; v3 p;
         sphere_test(prim_v1(pr), pr.a.w, o, d, t, p);
         s.position = p;
@@ -359,7 +363,8 @@ struct LampSample { v3 direction; bool has_sq; float sq_distance; LampSurface su
 
 PYR_HD float prim_surface_area(const SceneView& sc, const Prim& pr, uint32_t rank) {
     if (prim_kind(pr) == KIND_SPHERE) return pr.a.w * pr.a.w * 4.0f * PYR_PI;
-    return sc.tri_shade[rank].area;  // 0.5 * |cross(v2 - v1, v3 - v1)|, shapes/mod.rs:279-283
+    (void)sc; (void)rank;
+    return 0.5f * length(cross(prim_e1(pr), prim_e2(pr)));  // 0.5 * |cross(v2 - v1, v3 - v1)|, shapes/mod.rs:279-283
 }
 // Shape::sample_point (shapes/mod.rs:166-207): position + what get_surface_data needs
 PYR_HD void prim_sample_point(const Prim& pr, Rng& rng, v3& position, float& u_out, float& v_out) {
@@ -379,7 +384,7 @@ PYR_HD void prim_point_surface(const SceneView& sc, const Prim& pr, uint32_t ran
     s.position = position;
     s.material = prim_material(pr);
     if (prim_kind(pr) == KIND_SPHERE) sphere_surface(pr, position, false, s);
-    else triangle_surface(sc, rank, u, v, false, s);
+    else triangle_surface(sc, rank, u, v, s);
 }
 // Lamp::sample (lamp.rs:23-82)
 PYR_HD LampSample lamp_sample(const SceneView& sc, const LampRec& lamp, Rng& rng, v3 target) {
