@@ -297,7 +297,7 @@ def fixed_job(config: str, total_spp: int, small: bool, world: int, rank: int, l
     offset, stride = shard_for_rank(rank, world)
     r.counters(reset=True)
     t0 = time.time()
-    device_s = r.render(seed=seed, spp=total_spp, sample_offset=offset, sample_stride=stride, pool_paths=pool, timing=True)
+    device_s = r.render(seed=seed, spp=total_spp, sample_offset=offset, sample_stride=stride, pool_paths=pool)   # the production path: two wavefront lanes
     phases["render"] = max_over_ranks(time.time() - t0, world, local)
     render_device = max_over_ranks(device_s, world, local)
     c = r.counters()
@@ -311,17 +311,18 @@ def fixed_job(config: str, total_spp: int, small: bool, world: int, rank: int, l
         xyz, srgb = r.develop()
     phases["develop_download"] = max_over_ranks(time.time() - t0, world, local)
     total_s = max_over_ranks(time.time() - t_job, world, local)
-    rays, samples, trace_s, shade_s = sum_over_ranks([c["rays"], c["path_samples"], c["trace_seconds"], c["shade_seconds"]], world, local)
+    rays, samples = sum_over_ranks([c["rays"], c["path_samples"]], world, local)
     info = r.info
     out = {
         "config": workload_name(config, small), "job_spp": total_spp, "n_gpus": world, "seconds_total": total_s, "seconds": phases,
-        "render_device_seconds": render_device, "rays": rays, "path_samples": samples,
+        "render_device_seconds": render_device, "rays": rays, "path_samples": samples, "kernel_launches": int(c["kernel_launches"]),
         "mrays_per_s_render": rays / render_device / 1e6, "mrays_per_s_job": rays / total_s / 1e6,
         "msamples_per_s_render": samples / render_device / 1e6, "msamples_per_s_job": samples / total_s / 1e6,
         "film_bytes": int(info.width) * int(info.height) * int(info.bins) * 8, "ir_bytes": len(ir), "image_bytes": int(info.width) * int(info.height) * 15,
-        "trace_share_of_render": trace_s / max(trace_s + shade_s, 1e-12),
         "limiter": max(phases, key=phases.get),
     }
+    if config == "C4" and rank == 0:
+        out["sphere_tracing_roofline"] = sphere_tracing_roofline(r, total_spp, pool)
     if check_single and world > 1:
         # the sharded job must be THE single-GPU job: rank 0 renders a small job alone and the ranks render it together
         r.render(seed=seed + 1, spp=2 * world, sample_offset=offset, sample_stride=stride, pool_paths=pool)
@@ -341,6 +342,29 @@ def fixed_job(config: str, total_spp: int, small: bool, world: int, rank: int, l
         out["non_finite_pixels"] = int((~finite).sum())
     r.close()
     return out
+
+
+def sphere_tracing_roofline(r, job_spp: int, pool: int) -> dict:
+    """FP32 roofline of the sphere-tracing stage: distance-estimator iterations counted by the kernel's own
+    statistics variant on one sample pass, times the operation counts of one iteration of `Mandelbulb::get` (30 FP32 + 12
+    SFU-class, distance_estimators.rs:20-36) resp. cubic `QuaternionJulia::get` (128 FP32 + 1 sqrt, :59-65,82,90), over the
+    device time of the traversal + sphere-tracing launches of a one-wavefront timing pass, against the measured FFMA peak."""
+    hbm, hbm_src, ffma, ffma_src = measured_peaks()
+    r.counters(reset=True)
+    r.render(seed=9, spp=1, pool_paths=pool, stats=True)
+    cs = r.counters()
+    r.counters(reset=True)
+    r.render(seed=9, spp=1, pool_paths=pool, timing=True)
+    ct = r.counters()
+    julia, bulb = cs["julia_iterations"], cs["march_iterations"] - cs["julia_iterations"]
+    flops = bulb * (30 + 12) + julia * (128 + 1)
+    secs = ct["trace_seconds"]
+    achieved = flops / max(secs, 1e-12) / 1e12
+    return {"bound": "fp32", "kernel": "k_trace + k_march (+ k_march_apply)", "achieved": achieved, "peak": ffma, "unit": "TFLOP/s", "frac": achieved / ffma,
+            "peak_source": ffma_src, "de_evaluations_per_ray": cs["de_evals"] / max(cs["rays"], 1), "iterations_per_de_evaluation": cs["de_iterations"] / max(cs["de_evals"], 1), "rays_of_the_pass": cs["rays"],
+            "mandelbulb_iterations": bulb, "julia_iterations": julia, "ops_per_iteration": {"mandelbulb": 42, "julia_cubic": 129},
+            "seconds_of_one_pass": secs, "share_of_render": secs / max(ct["trace_seconds"] + ct["shade_seconds"], 1e-12),
+            "note": "the time is that of the whole traversal stage of a one-wavefront pass (BVH walk + sphere tracing); profiles/ has the sphere-tracing kernel's share and its pipe utilisation"}
 
 
 def run_fixed(args):
@@ -365,7 +389,7 @@ def run_fixed(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(args, world), "clocks": clocks,
             "e2e": {"value": job["mrays_per_s_job"], "unit": "Mrays/s", "h2d_bytes_per_step": job["ir_bytes"], "d2h_bytes_per_step": job["image_bytes"],
                     "what": "the whole job through the public API: project IR in host memory -> pyr_project_load -> pyr_render -> pyr_film_reduce -> pyr_film_develop -> images in host memory, wall clock"},
-            "gpu_launches": None, "fixed_job": job,
+            "gpu_launches": job.get("kernel_launches"), "roofline": job.get("sphere_tracing_roofline"), "fixed_job": job,
         }
         print(json.dumps(line), flush=True)
     finish(world)

@@ -97,6 +97,8 @@ typedef struct pyr_counters {
     uint64_t trace_launches, shade_launches;
     uint64_t node_fetches; /* 128-byte BVH nodes fetched (stats mode); nodes_visited counts the boxes tested */
     uint64_t path_rays;    /* the part of `rays` that are path segments (closest-hit); the rest are visibility rays */
+    uint64_t march_iterations, julia_iterations; /* stats mode: estimator iterations run by the sphere-tracing kernel (de_iterations also counts
+                                                   the normal estimation of the shade stage), and the quaternion-Julia part of them */
 } pyr_counters;
 
 /* renderer::Progress{progress: u8, message} (renderer/mod.rs:229-232); invoked on the calling

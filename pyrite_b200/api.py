@@ -61,7 +61,8 @@ class Counters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("rays", "path_samples", "nodes_visited", "leaves_tested", "de_evals", "de_iterations",
                                           "wavefront_iterations", "kernel_launches")] + [
         ("render_seconds", C.c_double), ("trace_seconds", C.c_double), ("shade_seconds", C.c_double),
-        ("trace_launches", C.c_uint64), ("shade_launches", C.c_uint64), ("node_fetches", C.c_uint64), ("path_rays", C.c_uint64)]
+        ("trace_launches", C.c_uint64), ("shade_launches", C.c_uint64), ("node_fetches", C.c_uint64), ("path_rays", C.c_uint64),
+        ("march_iterations", C.c_uint64), ("julia_iterations", C.c_uint64)]
 
     def as_dict(self):
         return {n: (float if n.endswith("_seconds") else int)(getattr(self, n)) for n, _ in self._fields_}

@@ -859,6 +859,8 @@ pyr_status pyr_counters_get(pyr_ctx* ctx, pyr_counters* out, int32_t reset) {
             out->leaves_tested = dc.leaves_tested;
             out->de_evals = dc.de_evals;
             out->de_iterations = dc.de_iterations;
+            out->march_iterations = dc.march_iterations;
+            out->julia_iterations = dc.julia_iterations;
             out->node_fetches = dc.node_fetches;
             out->path_rays = dc.path_rays;
         }

@@ -559,7 +559,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_march(const __grid_constant__
     uint32_t n = min(a.march_count[TYPE], a.march_capacity[TYPE]);
     const uint2* queue = a.march_queue[TYPE];
     uint32_t* cursor = cursors + TYPE;
-    unsigned long long evals = 0, iters = 0;
+    unsigned long long evals = 0, iters = 0, julia_iters = 0;
     bool active = false, in_de = false;
     uint32_t at = 0, shape = 0, mode = 0, it = 0;
     float limit = 0.0f, total = 0.0f, hi = 0.0f, r = 0.0f, dr = 1.0f;
@@ -650,7 +650,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_march(const __grid_constant__
                 r = qlength(z);
                 if (r > mr.threshold) de_done = true;
                 else {
-                    if (STATS) ++iters;
+                    if (STATS) { ++iters; ++julia_iters; }
                     if (mr.variant == 0) { dz = scale4(qmul(dz, z), 2.0f); z = qmul(z, z); }
                     else if (mr.variant == 1) { dz = scale4(qmul(qmul(dz, z), z), 3.0f); z = qmul(qmul(z, z), z); }
                     else { dz = scale4(bicomplex_mul(bicomplex_mul(dz, z), z), 2.0f); z = bicomplex_mul(z, z); }
@@ -673,8 +673,11 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_march(const __grid_constant__
         }
     }
     if (STATS) {
-        for (int d = 16; d; d >>= 1) { evals += __shfl_down_sync(FULL, evals, d); iters += __shfl_down_sync(FULL, iters, d); }
-        if (lane_id() == 0) { atomicAdd(&a.counters->de_evals, evals); atomicAdd(&a.counters->de_iterations, iters); }
+        for (int d = 16; d; d >>= 1) {
+            evals += __shfl_down_sync(FULL, evals, d); iters += __shfl_down_sync(FULL, iters, d); julia_iters += __shfl_down_sync(FULL, julia_iters, d);
+        }
+        if (lane_id() == 0) { atomicAdd(&a.counters->de_evals, evals); atomicAdd(&a.counters->de_iterations, iters); atomicAdd(&a.counters->march_iterations, iters);
+                              atomicAdd(&a.counters->julia_iterations, julia_iters); }
     }
 }
 

@@ -16,7 +16,8 @@ struct CamVertex;
 // Device-side work counters (one instance per context).
 struct DeviceCounters {
     unsigned long long rays, path_samples, nodes_visited, leaves_tested, de_evals, de_iterations, node_fetches, path_rays;
-    unsigned long long march_overflow;  // sphere-tracing candidates that did not fit their queue (must stay 0: pyr_render fails otherwise)
+    unsigned long long march_overflow;
+    unsigned long long march_iterations, julia_iterations;  // stats mode: estimator iterations run by k_march, and the quaternion-Julia part of them  // sphere-tracing candidates that did not fit their queue (must stay 0: pyr_render fails otherwise)
 };
 
 // Everything one wavefront iteration needs besides the scene.

@@ -31,7 +31,7 @@ def test_struct_layouts_match_the_header():
     assert api.RAY_DTYPE.itemsize == 32 and api.HIT_DTYPE.itemsize == 20
     assert ctypes.sizeof(api.ProjectInfo) == 16 * 4
     assert ctypes.sizeof(api.RenderParams) == 40
-    assert ctypes.sizeof(api.Counters) == 8 * 8 + 3 * 8 + 4 * 8
+    assert ctypes.sizeof(api.Counters) == 8 * 8 + 3 * 8 + 6 * 8
 
 
 def test_version_string_names_the_target():
