@@ -282,6 +282,12 @@ def fixed_job(config: str, total_spp: int, small: bool, world: int, rank: int, l
 
     ir = build_project(config, small)   # building the stand-in mesh is test-data generation, not part of the job
     phases = {}
+    verbose = os.environ.get("PYR_BENCH_VERBOSE") and rank == 0
+
+    def note(what):
+        if verbose:
+            print(f"[fixed_job {config} {total_spp} spp] {what} at {time.time() - t_job:.2f} s", file=sys.stderr, flush=True)
+
     barrier(world)
     t_job = time.time()
     t0 = time.time()
@@ -289,6 +295,7 @@ def fixed_job(config: str, total_spp: int, small: bool, world: int, rank: int, l
     r.load(ir)                          # IR decode + scene build (host BVH build, replicated on every rank) + upload
     torch.cuda.synchronize()
     phases["load_build_upload"] = max_over_ranks(time.time() - t0, world, local)
+    note("loaded")
     t0 = time.time()
     if world > 1:
         init_film_comm(r)
@@ -300,6 +307,7 @@ def fixed_job(config: str, total_spp: int, small: bool, world: int, rank: int, l
     device_s = r.render(seed=seed, spp=total_spp, sample_offset=offset, sample_stride=stride, pool_paths=pool)   # the production path: two wavefront lanes
     phases["render"] = max_over_ranks(time.time() - t0, world, local)
     render_device = max_over_ranks(device_s, world, local)
+    note("rendered")
     c = r.counters()
     t0 = time.time()
     if world > 1:
@@ -310,6 +318,7 @@ def fixed_job(config: str, total_spp: int, small: bool, world: int, rank: int, l
     if rank == 0:
         xyz, srgb = r.develop()
     phases["develop_download"] = max_over_ranks(time.time() - t0, world, local)
+    note("developed")
     total_s = max_over_ranks(time.time() - t_job, world, local)
     rays, samples = sum_over_ranks([c["rays"], c["path_samples"]], world, local)
     info = r.info
@@ -323,6 +332,7 @@ def fixed_job(config: str, total_spp: int, small: bool, world: int, rank: int, l
     }
     if config == "C4" and rank == 0:
         out["sphere_tracing_roofline"] = sphere_tracing_roofline(r, total_spp, pool)
+        note("sphere-tracing roofline passes done")
     if check_single and world > 1:
         # the sharded job must be THE single-GPU job: rank 0 renders a small job alone and the ranks render it together
         r.render(seed=seed + 1, spp=2 * world, sample_offset=offset, sample_stride=stride, pool_paths=pool)
@@ -437,7 +447,7 @@ def run_product(args):
     t0 = time.time()
     ev0.record(stream)
     for k in range(args.steps):
-        step(k, timing=True)
+        step(k)           # the production path: two wavefront lanes, no per-kernel events
     if world > 1:
         r.film_reduce(0)  # the one NCCL film reduction of the job (pyr_film_reduce, on the same stream)
     ev1.record(stream)
@@ -447,6 +457,13 @@ def run_product(args):
     c = r.counters()
     clocks = sampler.stop(t0, t1) if rank == 0 else None
     total_rays, total_samples, launches = sum_over_ranks([c["rays"], c["path_samples"], c["kernel_launches"]], world, local)
+    # the same steps once more in the one-lane timing mode: CUDA events around every trace / shade launch, for the rooflines
+    if rank == 0:
+        step(0, timing=True)   # untimed: the one-lane pool is allocated here
+        r.counters(reset=True)
+        for k in range(args.steps):
+            step(k, timing=True)
+        c = r.counters()
 
     # ---- end-to-end through the public API with host buffers: render step + develop + image download
     e2e_steps = max(1, min(args.steps, 4))

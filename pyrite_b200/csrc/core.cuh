@@ -706,8 +706,11 @@ PYR_HD bool march_test(const MarchedRec& m, v3 o, v3 d, float& dist, uint32_t& e
         v3 p = origin + d * total;
         ++evals;
         float distance = estimate_distance(m, p, iters);
+        // a step of >= EPSILON that is below half an ulp of `total` would leave it unchanged for ever (the reference's loop,
+        // shapes/mod.rs:127-135, never returns on such a ray): it ends the march like a step below EPSILON
+        const bool stuck = total + distance == total;
         total += distance;
-        if (distance < DIST_EPSILON || total > hi) break;
+        if (distance < DIST_EPSILON || total > hi || stuck) break;
     }
     if (total <= hi) { dist = total; return true; }
     return false;

@@ -662,8 +662,9 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_march(const __grid_constant__
             // the estimate is complete: one step of the march loop (shapes/mod.rs:127-135)
             const float distance = TYPE == 0 ? 0.5f * logf(r) * r / dr : 0.5f * logf(r) * r / qlength(dz);
             in_de = false;
+            const bool stuck = total + distance == total;   // see march_test (core.cuh): the reference would spin for ever here
             total += distance;
-            if (distance < DIST_EPSILON || total > hi || !(total < hi)) {
+            if (distance < DIST_EPSILON || total > hi || !(total < hi) || stuck) {
                 active = false;
                 if (total <= hi && total > DIST_EPSILON) {
                     if (mode == 0) atomicMin(a.march_key + at, pack_hit(total, KIND_RAY_MARCHED, mr.rank));

@@ -609,3 +609,19 @@ def test_first_divergence_on_the_gpu(name):
     assert rep_d["diverged_fraction"] <= 0.02, rep_d
     first_is_id = sum(v for k, v in rep_g["first_differing_field"].items() if k.split("@")[0] in ("kind", "prim_id"))
     assert first_is_id <= 0.002 * n, rep_g
+
+
+def test_a_march_that_cannot_advance_still_ends(gpu_renderer_factory, oracle_factory):
+    """The reference's sphere-tracing loop never returns when a step of >= EPSILON is absorbed by the rounding of `total`
+    (tests/test_host_logic.py has the story); the kernels end the march there and agree with the oracle."""
+    r, o = gpu_renderer_factory("fractals"), oracle_factory("fractals")
+    from pyrite_b200 import api
+
+    rays = np.zeros(64, api.RAY_DTYPE)
+    rays["o"] = (2050.99292, -470.784729, 0.0)
+    rays["d"] = (-0.974572718, 0.224070147, 0.000765009667)
+    rays["d"][1::2] = (-0.974572718, 0.224070147, 0.0008)
+    want, _ = o.trace(rays, threads=1)
+    got = r.trace(rays)
+    assert np.array_equal(want["kind"], got["kind"]) and np.array_equal(want["prim_id"], got["prim_id"])
+    assert np.allclose(want["t"], got["t"], rtol=1e-5)

@@ -242,3 +242,19 @@ def test_parallel_scene_build_equals_the_sequential_one(monkeypatch):
     w, _ = o.trace(rays)
     for f in ("prim_id", "kind", "t", "u", "v"):
         assert np.array_equal(a[f], b[f]) and np.array_equal(a[f], w[f])
+
+
+def test_a_march_that_cannot_advance_still_ends(emu_factory):
+    """shapes/mod.rs:127-135 loops `while total < max { total += DE(p); if DE < EPSILON || total > max { break } }`.  Far from the
+    origin a step of >= EPSILON can be smaller than half an ulp of `total`: the sum does not change and the reference spins for
+    ever (pyrite itself never returns on such a ray).  Found by a 4K render of config C4: a bounce ray leaving the floor plane
+    2100 units out.  Product and oracle end the march there (the only deliberate deviation in the ray queries) and must agree."""
+    emu, oracle = emu_factory("fractals")
+    rays = np.zeros(2, dtype=[("o", np.float32, 3), ("pad0", np.float32), ("d", np.float32, 3), ("pad1", np.float32)])
+    rays["o"] = [[2050.99292, -470.784729, 0.0], [2050.99292, -470.784729, 0.0]]
+    rays["d"] = [[-0.974572718, 0.224070147, 0.000765009667], [-0.974572718, 0.224070147, 0.0008]]
+    want, _ = oracle.trace(rays, threads=1)
+    got, _ = emu.trace(rays)
+    for f in ("prim_id", "kind", "t"):
+        assert np.array_equal(want[f], got[f]), f
+    assert want["kind"][0] == 4 and 2100.0 < want["t"][0] < 2105.0
