@@ -5,6 +5,9 @@
 //   PH_LAMP     the lamp subpath: Lamp::sample_ray (lamp.rs:84-113), the emission vertex
 //               (bidirectional.rs:128-174) and `trace(.., light_bounces, light_samples = 0)`, one path ray
 //               per iteration; vertices are stored in HBM (LightVertex, light_bounces + 1 per path)
+//   PH_FINISH   the end of the lamp subpath (fix-up, reversal, colour programs at the path's wavelengths, tail folds): a step of
+//               its own, without rays - lamp paths end after different numbers of bounces, and inside the lamp kernel the few
+//               finishing lanes of a warp held the others up (4.7 of 32 lanes active in the steady state)
 //   PH_CAMERA   the camera subpath: the same `trace` as the camera-to-light integrator (camera_step),
 //               folding `contribute` as it goes and storing the state at every diffuse vertex (CamVertex)
 //   PH_CONNECT  connect_paths (bidirectional.rs:310-398): for each stored camera vertex, visibility rays to
@@ -23,7 +26,7 @@ namespace pyr {
 
 constexpr int BDPT_STAGE = 16;  // visibility rays staged per path per iteration
 
-enum : uint32_t { PH_LAMP = 0, PH_CAMERA = 1, PH_CONNECT = 2, PH_SPLAT = 3 };
+enum : uint32_t { PH_LAMP = 0, PH_CAMERA = 1, PH_CONNECT = 2, PH_SPLAT = 3, PH_FINISH = 4 };
 enum : uint32_t { VT_DIFFUSE = 0, VT_SPECULAR = 1, VT_EMISSION = 2 };
 
 // One stored vertex of the lamp subpath (tracer.rs:157-167 `Bounce`; lamp paths carry no direct light), plus
@@ -489,10 +492,16 @@ PYR_HD bool lamp_step(const SceneView& sc, PathState& ps, const BidirCtx& cx, co
 
 // ---- one wavefront step per phase.  The kernels run one specialised kernel per phase over the slots sorted by phase (each with
 // the registers ITS phase needs); shade_bidirectional below dispatches for the CPU emulation.
-// PH_LAMP: one iteration of the lamp subpath; when it ends: fix-up, colours, and the camera subpath starts.
+// PH_LAMP: one iteration of the lamp subpath; when it ends the sample goes through PH_FINISH (no ray this iteration).
 PYR_HD void shade_bd_lamp(const SceneView& sc, PathState& ps, const BidirCtx& cx, const Ray* main_ray, const Hit* main_hit, BidirOut& out, PathCounters& pc) {
     out.alive = 0; out.has_main = 0; out.n_shadow = 0; out.shadow_kind = SH_NONE;
     if (lamp_step(sc, ps, cx, load_record_stream(main_ray), load_record(main_hit), out, pc)) return;
+    ps.bd->phase = PH_FINISH;
+    out.alive = 1;
+}
+// PH_FINISH: fix-up, reversal, colours and tail folds of the finished lamp subpath; then the camera subpath starts.
+PYR_HD void shade_bd_finish(const SceneView& sc, PathState& ps, const BidirCtx& cx, BidirOut& out) {
+    out.alive = 0; out.has_main = 0; out.n_shadow = 0; out.shadow_kind = SH_NONE;
     finish_lamp_path(sc, ps, cx);
     ps.light_events = 0;
     begin_camera(ps, out);
@@ -616,6 +625,7 @@ inline void shade_bidirectional(const SceneView& sc, PathState& ps, const BidirC
             return;
         }
         case PH_CONNECT: shade_bd_connect(sc, ps, cx, shadow_kinds, out, add); return;
+        case PH_FINISH: shade_bd_finish(sc, ps, cx, out); return;
         default: shade_bd_splat(sc, ps, cx, shadow_kinds, out, add); return;
     }
 }

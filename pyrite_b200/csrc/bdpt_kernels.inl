@@ -3,7 +3,7 @@
 // One specialised kernel per phase of a path sample (bdpt.cuh) instead of one kernel holding the union of all phases'
 // registers: the slots are already sorted by phase (k_bin_*), so every kernel walks ONE contiguous run of the sorted list
 // with a grid-stride loop (grids are sized by the SM count, not by the pool), each compiled with the registers its phase
-// needs.  Launch order per wavefront iteration:  LAMP, CAMERA, CONNECT, SPLAT (slots that end a sample are appended to the
+// needs.  Launch order per wavefront iteration:  LAMP, FINISH, CAMERA, CONNECT, SPLAT (slots that end a sample are appended to the
 // `died` list), then GEN, which starts new samples in the dead slots of the sorted list and in the slots that just died -
 // so a slot is never idle for an iteration.  All of them append to the same ray queue / live list.
 namespace {
@@ -11,7 +11,7 @@ namespace {
 #ifndef BD_CONNECT_BLOCKS
 #define BD_CONNECT_BLOCKS 4
 #endif
-enum : int { BD_GEN = 0, BD_LAMP = 1, BD_CAMERA = 2, BD_CONNECT = 3, BD_SPLAT = 4 };
+enum : int { BD_GEN = 0, BD_LAMP = 1, BD_CAMERA = 2, BD_CONNECT = 3, BD_SPLAT = 4, BD_FINISH = 5 };
 
 // Queue space for one block: path rays, visibility rays, the live list and the list of slots whose sample just ended.
 struct ReservationBd { uint32_t main_at, shadow_at, live_at, died_at; };
@@ -68,8 +68,8 @@ __device__ __forceinline__ void store_bidir(BidirState* dst_, const BidirState& 
 
 // first / one-past-last position of a phase's run in the sorted list (keys are state * BIN_CLUSTERS + cluster, see bin_key)
 template <int PHASE> __device__ __forceinline__ void phase_run(const WaveArgs& a, uint32_t& lo, uint32_t& hi) {
-    constexpr uint32_t S0 = PHASE == BD_GEN ? 0u : PHASE == BD_CAMERA ? 1u : PHASE == BD_LAMP ? 26u : PHASE == BD_CONNECT ? 32u : 40u;
-    constexpr uint32_t S1 = PHASE == BD_GEN ? 1u : PHASE == BD_CAMERA ? 26u : PHASE == BD_LAMP ? 32u : PHASE == BD_CONNECT ? 40u : BIN_STATES;
+    constexpr uint32_t S0 = PHASE == BD_GEN ? 0u : PHASE == BD_CAMERA ? 1u : PHASE == BD_LAMP ? 26u : PHASE == BD_FINISH ? 31u : PHASE == BD_CONNECT ? 32u : 40u;
+    constexpr uint32_t S1 = PHASE == BD_GEN ? 1u : PHASE == BD_CAMERA ? 26u : PHASE == BD_LAMP ? 31u : PHASE == BD_FINISH ? 32u : PHASE == BD_CONNECT ? 40u : BIN_STATES;
     lo = __ldg(a.bin_first + S0 * BIN_CLUSTERS);
     hi = __ldg(a.bin_first + S1 * BIN_CLUSTERS);
 }
@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, PHASE == BD_CAMERA ? 3 : (PHASE 
             const Hit* main_hit = a.hits_in + ps.ray_base;
             const uint32_t* kinds = a.shadow_kinds_in + ps.shadow_base;
             if (PHASE == BD_LAMP) shade_bd_lamp(sc, ps, cx, main_ray, main_hit, out, pc);
+            else if (PHASE == BD_FINISH) shade_bd_finish(sc, ps, cx, out);
             else if (PHASE == BD_CAMERA) shade_bd_camera(sc, ps, cx, main_ray, main_hit, a.rays_in + a.shadow_offset + ps.shadow_base, kinds, so, out, add, pc);
             else if (PHASE == BD_CONNECT) shade_bd_connect(sc, ps, cx, kinds, out, add);
             else shade_bd_splat(sc, ps, cx, kinds, out, add);
@@ -172,11 +173,12 @@ inline size_t bidir_lean_smem(const SceneView& sc) { return (size_t)5 * sc.rende
 void launch_wave_bidirectional(const SceneView& sc, const WaveArgs& a, int sm_count, cudaStream_t s) {
     const size_t smem = bidir_smem(sc), lean = bidir_lean_smem(sc);
     launch_bd_phase<BD_LAMP>(sc, a, smem, sm_count, s);
+    launch_bd_phase<BD_FINISH>(sc, a, smem, sm_count, s);
     launch_bd_phase<BD_CAMERA>(sc, a, smem, sm_count, s);
     launch_bd_phase<BD_CONNECT>(sc, a, lean, sm_count, s);
     launch_bd_phase<BD_SPLAT>(sc, a, lean, sm_count, s);
     launch_bd_phase<BD_GEN>(sc, a, smem, sm_count, s);
 }
-int wave_bidirectional_launches() { return 5; }
+int wave_bidirectional_launches() { return 6; }
 size_t cam_vertex_bytes() { return sizeof(CamVertex); }
 int bdpt_stage_rays() { return BDPT_STAGE; }

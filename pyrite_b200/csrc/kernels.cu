@@ -185,6 +185,9 @@ __device__ __forceinline__ uint32_t bin_key(const PathCore* paths, const BidirSt
         } else {
             state = 26u + hc;             // 27 .. 30
         }
+    } else if (phase == PH_FINISH) {
+        state = 31u;                                       // a finished lamp subpath waiting for its fix-up / colours / folds
+        cluster = min(n_light, BIN_CLUSTERS - 1u);         // equal path lengths together: the loops run over the lamp vertices
     } else {
         const uint32_t lit = min(unblocked_count(shadow_kinds, shadow_base, n_pending), 14u) >> 1;
         state = (phase == PH_CONNECT ? 32u : 40u) + lit;  // 32 .. 47
@@ -595,7 +598,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_march(const __grid_constant__
                             origin = o + (-bounds_center(mr));
                             total = lo;
                             if (total < hi) { active = true; in_de = false; }
-                            else if (total <= hi && total > DIST_EPSILON) {  // the loop body never runs
+                            else if (total <= hi && total > DIST_EPSILON && total < PYR_INF) {  // the loop body never runs
                                 if (mode == 0) atomicMin(a.march_key + at, pack_hit(total, KIND_RAY_MARCHED, mr.rank));
                                 else if (occludes(mode, total, limit)) a.shadow_kinds[at - a.shadow_offset] = KIND_RAY_MARCHED;
                             }
@@ -666,7 +669,9 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_march(const __grid_constant__
             total += distance;
             if (distance < DIST_EPSILON || total > hi || !(total < hi) || stuck) {
                 active = false;
-                if (total <= hi && total > DIST_EPSILON) {
+                // World::intersect only takes a hit with `distance < closest`, and closest starts at +inf (world.rs:273-299): a march that
+                // runs off to infinity inside an unbounded exit distance (a direction component of exactly 0) "hits" at +inf and is dropped
+                if (total <= hi && total > DIST_EPSILON && total < PYR_INF) {
                     if (mode == 0) atomicMin(a.march_key + at, pack_hit(total, KIND_RAY_MARCHED, mr.rank));
                     else if (occludes(mode, total, limit)) a.shadow_kinds[at - a.shadow_offset] = KIND_RAY_MARCHED;
                 }

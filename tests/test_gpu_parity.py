@@ -625,3 +625,23 @@ def test_a_march_that_cannot_advance_still_ends(gpu_renderer_factory, oracle_fac
     got = r.trace(rays)
     assert np.array_equal(want["kind"], got["kind"]) and np.array_equal(want["prim_id"], got["prim_id"])
     assert np.allclose(want["t"], got["t"], rtol=1e-5)
+
+
+def test_a_march_to_infinity_is_a_miss(gpu_renderer_factory, oracle_factory):
+    """A direction component of exactly 0 makes the box exit distance +inf (BoundingVolume::intersect, shapes/mod.rs:591-658); a
+    ray that misses the fractal then marches off to total = +inf, `total <= max` holds and Shape::ray_intersect returns a hit at
+    +inf, which World::intersect drops (`distance < closest`, closest starts at +inf).  The wavefront (k_march merges by atomicMin)
+    must drop it too - found as NaN pixels in the 512-spp C4 render by tools/find_nonfinite.py + tools/replay_sample.py."""
+    from pyrite_b200 import api
+
+    r, o = gpu_renderer_factory("fractals"), oracle_factory("fractals")
+    rays = np.zeros(32, api.RAY_DTYPE)
+    rays["o"] = (-2.3175702, -2.6104007, 0.0)
+    rays["d"] = (0.0, 0.5699651, 0.8216689)
+    want, _ = o.trace(rays, threads=1)
+    got = r.trace(rays)
+    assert np.array_equal(want["kind"], got["kind"]) and want["kind"][0] == 0
+    # and through the wavefront: a render leaves no more non-finite bins behind than the oracle's does
+    r.render(seed=4242, spp=8)
+    o.render(seed=4242, spp=8)
+    assert (~np.isfinite(r.film())).sum() <= (~np.isfinite(o.film())).sum()
