@@ -278,6 +278,7 @@ PYR_HD bool advance_connect(PathState& ps, const BidirCtx& cx, BidirOut& out) {
     const uint32_t n = stage_connections(ps, cx, cam, light, PYR_STAGE_RAYS(out));
     if (!n) return false;
     ps.bd->conn_next_cam = cam; ps.bd->conn_next = light;
+    ps.n_pending = n;
     out.n_shadow = n; out.shadow_kind = SH_CONNECT; out.alive = 1;
     return true;
 }
@@ -319,7 +320,7 @@ PYR_HD bool advance_splat(const SceneView& sc, PathState& ps, const BidirCtx& cx
         ps.bd->rng_saved = ps.rng;
         uint32_t next;
         uint32_t n = stage_visibility(sc, ps, cx, ps.rng, ps.bd->conn_light, PYR_STAGE_RAYS(out), next);
-        if (n) { ps.bd->conn_next = next; out.n_shadow = n; out.shadow_kind = SH_SPLAT; out.alive = 1; return true; }
+        if (n) { ps.bd->conn_next = next; ps.n_pending = n; out.n_shadow = n; out.shadow_kind = SH_SPLAT; out.alive = 1; return true; }
         ps.bd->conn_light = next;
     }
     return false;
@@ -333,17 +334,19 @@ PYR_HD void write_staged(const SceneView& sc, const PathState& ps, const BidirCt
     else if (shadow_kind == SH_SPLAT) { Rng replay = ps.bd->rng_saved; stage_visibility(sc, ps, cx, replay, ps.bd->conn_light, dst, next); }
 }
 
-// After the camera path has ended: expose it, then start connecting (or splatting, or finish).
+// After the camera path has ended: expose it; the connect phase starts with the NEXT iteration (no ray now).  The first batch
+// of connections is staged by the connect kernel, where every lane walks lamp vertices, not here, where only the few lanes whose
+// camera path just ended would (35 % of the camera kernel's stall samples sat in that walk in the steady state).
 template <class Add>
 PYR_HD void end_camera_path(const SceneView& sc, PathState& ps, const BidirCtx& cx, BidirOut& out, Add& add) {
+    (void)cx;
     expose_path(sc, ps, add);  // bidirectional.rs:245-251
-    ps.bd->conn_cam = 0; ps.bd->conn_light = 0;
+    ps.bd->conn_cam = 0; ps.bd->conn_light = 0; ps.bd->conn_next_cam = 0; ps.bd->conn_next = 0;
+    ps.n_pending = 0;
     if (ps.bd->n_light > 0) {
         ps.bd->phase = PH_CONNECT;
-        if (advance_connect(ps, cx, out)) return;
-        ps.bd->phase = PH_SPLAT;
-        ps.bd->conn_light = 0;
-        if (advance_splat(sc, ps, cx, out)) return;
+        out.alive = 1;   // n_shadow = 0: the connect step finds nothing to evaluate and stages the first batch
+        return;
     }
     out.alive = 0;
 }
@@ -536,6 +539,7 @@ PYR_HD void shade_bd_connect(const SceneView& sc, PathState& ps, const BidirCtx&
     float brdf = 1.0f;
     bool cam_additional = false;
     uint32_t cam = ps.bd->conn_cam, light = ps.bd->conn_light;
+    if (ps.n_pending)   // (a sample that has just entered the phase has nothing staged yet)
     for_each_connection(ps, cx, cam, light,
         [&](uint32_t, const CamVertex& stored, const Vec8& head) {
             // the sample state right after this camera vertex' `contribute`: fetched once per vertex, not once per connection
