@@ -927,7 +927,8 @@ struct Traversal {
             m &= m - 1u;
             const MarchedRec& mr = sc.marched[i];
             float ht = 0.0f;
-            if (march_test(mr, o, d, ht, de_evals, de_iters) && ht > DIST_EPSILON) {
+            // (a march that runs off to +inf "hits" there: World::intersect's `distance < closest` drops it, closest starting at +inf)
+            if (march_test(mr, o, d, ht, de_evals, de_iters) && ht > DIST_EPSILON && ht < PYR_INF) {
                 if (mode != 0) {
                     if (occludes(mode, ht, limit)) { t = ht; u = 0; v = 0; rank = mr.rank; kind = KIND_RAY_MARCHED; return; }
                 } else if (ht < closest || (ht == closest && kind != KIND_PLANE && mr.rank < rank)) {
