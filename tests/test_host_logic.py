@@ -258,3 +258,17 @@ def test_a_march_that_cannot_advance_still_ends(emu_factory):
     for f in ("prim_id", "kind", "t"):
         assert np.array_equal(want[f], got[f]), f
     assert want["kind"][0] == 4 and 2100.0 < want["t"][0] < 2105.0
+
+
+def test_a_march_to_infinity_is_a_miss(emu_factory):
+    """An exactly-zero direction component makes the bounding box' exit distance +inf; a ray that then misses the fractal marches
+    off to total = +inf, where Shape::ray_intersect reports a hit (`total <= max`) that World::intersect drops (`distance <
+    closest` with closest = +inf, world.rs:273-299).  The product's tie rule must not take inf == inf for a tie."""
+    emu, oracle = emu_factory("fractals")
+    rays = np.zeros(1, dtype=[("o", np.float32, 3), ("pad0", np.float32), ("d", np.float32, 3), ("pad1", np.float32)])
+    rays["o"] = [[-2.3175702, -2.6104007, 0.0]]
+    rays["d"] = [[0.0, 0.5699651, 0.8216689]]
+    want, _ = oracle.trace(rays, threads=1)
+    got, _ = emu.trace(rays)
+    assert want["kind"][0] == got["kind"][0] and np.array_equal(want["prim_id"], got["prim_id"])
+    assert want["kind"][0] == 0 or np.isfinite(want["t"][0])
