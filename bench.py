@@ -298,8 +298,7 @@ def fixed_job(config: str, total_spp: int, small: bool, world: int, rank: int, l
     note("loaded")
     t0 = time.time()
     if world > 1:
-        init_film_comm(r)
-        torch.cuda.synchronize()
+        init_film_comm(r, wait=False)   # pyr_comm_init_async: NCCL's set-up runs under the render, pyr_film_reduce waits for it
     phases["comm_init"] = max_over_ranks(time.time() - t0, world, local)
     offset, stride = shard_for_rank(rank, world)
     r.counters(reset=True)

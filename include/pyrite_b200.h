@@ -158,11 +158,15 @@ pyr_status pyr_film_device_ptr(pyr_ctx* ctx, void** d_ptr, size_t* bytes);
  * 128-byte id from rank 0 to the other ranks (a file, a socket, MPI, torch.distributed ...).
  *   pyr_comm_unique_id  rank 0: a fresh id (ncclGetUniqueId)
  *   pyr_comm_init       every rank, collectively (ncclCommInitRank on the context's device)
+ *   pyr_comm_init_async the same, but returns at once: the communicator is set up on a thread and a stream of the library's
+ *                       own while the host goes on to pyr_render (on an 8-GPU box the set-up takes ~3 s, a sixth of the
+ *                       1024-spp target job); pyr_film_reduce / pyr_comm_destroy wait for it and report its failure
  *   pyr_film_reduce     every rank, collectively: film := sum over ranks, on `root` (root < 0: on every rank)
  * NCCL (libnccl.so.2) is bound when the first of these is called; without it they fail with PYR_ERR_STATE. */
 #define PYR_COMM_ID_BYTES 128
 pyr_status pyr_comm_unique_id(uint8_t* id_out /* PYR_COMM_ID_BYTES */);
 pyr_status pyr_comm_init(pyr_ctx* ctx, int32_t n_ranks, int32_t rank, const uint8_t* id /* PYR_COMM_ID_BYTES */);
+pyr_status pyr_comm_init_async(pyr_ctx* ctx, int32_t n_ranks, int32_t rank, const uint8_t* id /* PYR_COMM_ID_BYTES */);
 pyr_status pyr_film_reduce(pyr_ctx* ctx, int32_t root);
 pyr_status pyr_comm_destroy(pyr_ctx* ctx);
 

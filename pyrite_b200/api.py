@@ -33,7 +33,7 @@ RENDER_TIMING = 2
 EXPORTS = [
     "pyr_init", "pyr_shutdown", "pyr_stream_set", "pyr_last_error", "pyr_project_load", "pyr_project_info_get", "pyr_trace", "pyr_trace_device",
     "pyr_trace_stats", "pyr_bvh_leaf_order", "pyr_render", "pyr_film_expose", "pyr_film_clear", "pyr_film_download", "pyr_film_upload",
-    "pyr_film_device_ptr", "pyr_comm_unique_id", "pyr_comm_init", "pyr_film_reduce", "pyr_comm_destroy", "pyr_film_develop", "pyr_camera_sample", "pyr_debug_path", "pyr_counters_get", "pyr_version",
+    "pyr_film_device_ptr", "pyr_comm_unique_id", "pyr_comm_init", "pyr_comm_init_async", "pyr_film_reduce", "pyr_comm_destroy", "pyr_film_develop", "pyr_camera_sample", "pyr_debug_path", "pyr_counters_get", "pyr_version",
 ]
 
 
@@ -106,6 +106,7 @@ def load_library(path: Optional[Path] = None):
     L.pyr_film_develop.argtypes = [vp, C.c_float, vp, vp]
     L.pyr_comm_unique_id.argtypes = [vp]
     L.pyr_comm_init.argtypes = [vp, C.c_int32, C.c_int32, vp]
+    L.pyr_comm_init_async.argtypes = [vp, C.c_int32, C.c_int32, vp]
     L.pyr_film_reduce.argtypes = [vp, C.c_int32]
     L.pyr_comm_destroy.argtypes = [vp]
     L.pyr_camera_sample.argtypes = [vp, C.c_uint64, C.c_uint32, C.c_uint64, vp, vp, vp, vp]
@@ -250,10 +251,12 @@ class Renderer:
             raise PyriteError(status, L.pyr_last_error(None).decode())
         return bytes(buf)
 
-    def comm_init(self, n_ranks: int, rank: int, comm_id: bytes):
+    def comm_init(self, n_ranks: int, rank: int, comm_id: bytes, wait: bool = True):
+        """Every rank, collectively.  `wait=False` (`pyr_comm_init_async`) returns at once and lets the library set the
+        communicator up while this rank renders; `film_reduce` waits for it."""
         assert len(comm_id) == 128
         buf = (C.c_uint8 * 128).from_buffer_copy(comm_id)
-        self._check(self.L.pyr_comm_init(self.h, n_ranks, rank, buf))
+        self._check((self.L.pyr_comm_init if wait else self.L.pyr_comm_init_async)(self.h, n_ranks, rank, buf))
 
     def film_reduce(self, root: int = 0):
         """Collective: film := sum of the ranks' films on `root` (root < 0: everywhere)."""

@@ -10,6 +10,7 @@
 #include <exception>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/pyrite_b200.h"
@@ -148,8 +149,15 @@ struct pyr_ctx {
     bool develop_params_valid = false;
     pyr_counters host_counters{};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    ncclComm_t comm = nullptr;   // pyr_comm_init
+    ncclComm_t comm = nullptr;   // pyr_comm_init / pyr_comm_init_async
     int comm_ranks = 0, comm_rank = 0;
+    // The communicator is set up on a thread of its own, on a stream of its own, so that a render can run meanwhile
+    // (ncclCommInitRank + NCCL's connection set-up at the first collective take seconds on an 8-GPU box).  Everything that
+    // uses `comm` joins the thread first (comm_wait).
+    std::thread comm_thread;
+    std::string comm_error;       // written by the thread, read after the join
+    cudaStream_t comm_stream = nullptr;
+    DeviceBuffer comm_scratch;
     unsigned long long* pinned = nullptr;  // [3] sphere-tracing overflow counter
 
     size_t film_floats() const { return (size_t)view.film.width * view.film.height * view.film.bins * 2; }
@@ -335,7 +343,10 @@ void pyr_shutdown(pyr_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm_thread.joinable()) ctx->comm_thread.join();
     if (ctx->comm) { try { nccl().CommDestroy(ctx->comm); } catch (...) {} ctx->comm = nullptr; }
+    if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
+    ctx->comm_scratch.release();
     DeviceBuffer* all[] = {&ctx->nodes, &ctx->prims, &ctx->tri_shade, &ctx->tri_frames, &ctx->planes, &ctx->marched, &ctx->materials,
                            &ctx->components, &ctx->programs, &ctx->code, &ctx->spectra, &ctx->spectrum_data, &ctx->textures, &ctx->texels,
                            &ctx->lamps, &ctx->tiles, &ctx->burns, &ctx->xyz, &ctx->d65, &ctx->film, &ctx->develop_params, &ctx->counters,
@@ -740,26 +751,60 @@ pyr_status pyr_comm_unique_id(uint8_t* id_out) {
     }
 }
 
-pyr_status pyr_comm_init(pyr_ctx* ctx, int32_t n_ranks, int32_t rank, const uint8_t* id) {
+namespace {
+// Joins the communicator set-up started by pyr_comm_init_async and reports its failure, if any.
+void comm_wait(pyr_ctx* ctx) {
+    if (ctx->comm_thread.joinable()) ctx->comm_thread.join();
+    if (!ctx->comm_error.empty()) {
+        const std::string e = ctx->comm_error;
+        ctx->comm_error.clear();
+        throw CudaError("communicator set-up failed: " + e);
+    }
+}
+}  // namespace
+
+pyr_status pyr_comm_init_async(pyr_ctx* ctx, int32_t n_ranks, int32_t rank, const uint8_t* id) {
     return guarded(ctx, [&] {
         if (!id) throw ir::BuildError("null communicator id");
         if (n_ranks < 1 || rank < 0 || rank >= n_ranks) throw ir::BuildError("bad rank / rank count");
-        if (ctx->comm) { NC(nccl().CommDestroy(ctx->comm)); ctx->comm = nullptr; }
+        comm_wait(ctx);
+        if (ctx->comm) { NC(nccl().CommDestroy(ctx->comm)); ctx->comm = nullptr; ctx->comm_ranks = 0; }
+        nccl();  // bind NCCL here, so that a missing library is reported by this call
         ncclUniqueId uid;
         memcpy(&uid, id, sizeof(uid));
-        NC(nccl().CommInitRank(&ctx->comm, n_ranks, uid, rank));
+        if (!ctx->comm_stream) CU(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+        ctx->comm_scratch.ensure(1024);
+        CU(cudaMemsetAsync(ctx->comm_scratch.p, 0, 1024, ctx->comm_stream));
+        CU(cudaStreamSynchronize(ctx->comm_stream));
         ctx->comm_ranks = n_ranks;
         ctx->comm_rank = rank;
-        // NCCL connects the ranks at the first collective: do that here, on a few bytes, so that pyr_film_reduce costs what
-        // moving the film costs
-        ctx->scratch_a.ensure(1024);
-        NC(nccl().AllReduce(ctx->scratch_a.p, ctx->scratch_a.p, 256, ncclFloat32, ncclSum, ctx->comm, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
+        ctx->comm_thread = std::thread([ctx, uid, n_ranks, rank] {
+            try {
+                CU(cudaSetDevice(ctx->device));
+                NC(nccl().CommInitRank(&ctx->comm, n_ranks, uid, rank));
+                // NCCL connects the ranks at the first collective: do that here, on a few bytes and on a stream that no render
+                // uses, so that pyr_film_reduce costs what moving the film costs
+                NC(nccl().AllReduce(ctx->comm_scratch.p, ctx->comm_scratch.p, 256, ncclFloat32, ncclSum, ctx->comm, ctx->comm_stream));
+                CU(cudaStreamSynchronize(ctx->comm_stream));
+            } catch (const std::exception& e) {
+                ctx->comm_error = e.what();
+                if (ctx->comm_error.empty()) ctx->comm_error = "unknown error";
+            }
+        });
+    });
+}
+
+pyr_status pyr_comm_init(pyr_ctx* ctx, int32_t n_ranks, int32_t rank, const uint8_t* id) {
+    const pyr_status st = pyr_comm_init_async(ctx, n_ranks, rank, id);
+    if (st != PYR_OK) return st;
+    return guarded(ctx, [&] {
+        try { comm_wait(ctx); } catch (...) { ctx->comm = nullptr; ctx->comm_ranks = 0; throw; }
     });
 }
 
 pyr_status pyr_comm_destroy(pyr_ctx* ctx) {
     return guarded(ctx, [&] {
+        try { comm_wait(ctx); } catch (...) { ctx->comm = nullptr; ctx->comm_ranks = 0; throw; }
         if (!ctx->comm) return;
         CU(cudaStreamSynchronize(ctx->stream));
         NC(nccl().CommDestroy(ctx->comm));
@@ -771,6 +816,7 @@ pyr_status pyr_comm_destroy(pyr_ctx* ctx) {
 pyr_status pyr_film_reduce(pyr_ctx* ctx, int32_t root) {
     return guarded(ctx, [&] {
         need_project(ctx);
+        comm_wait(ctx);
         if (!ctx->comm) throw StateError("pyr_comm_init has not been called on this context");
         if (root >= ctx->comm_ranks) throw ir::BuildError("root rank out of range");
         // (accumulator, weight) pairs are summed BEFORE developing: a bin's value is the ratio of the two sums (film.rs:132-143)

@@ -762,6 +762,13 @@ PYR_HD Prim fetch_prim(const Prim* p) {
 // the entry distance of its box, so that a subtree made irrelevant by a closer hit is dropped at pop
 // time without fetching its node.
 struct LocalStack {
+    // Slots below FAST_DEPTH may be written speculatively (Traversal::node_step stores all four children and only moves the
+    // stack pointer past the real ones).  Here every slot is alike; the kernels' SharedStack keeps exactly these in shared
+    // memory, and the host emulation takes the same code path as the device with the same depth.
+    static constexpr int FAST_DEPTH = 20;
+    PYR_HD void put_fast(int i, int code, float dist) { codes[i] = code; dists[i] = dist; }
+    PYR_HD int code_fast(int i) const { return codes[i]; }
+    PYR_HD float dist_fast(int i) const { return dists[i]; }
     int codes[BVH_STACK];
     float dists[BVH_STACK];
     float m;  // max(hit distance, entry distance of its leaf's box) of the current closest hit (Traversal::leaf_step)
@@ -800,6 +807,9 @@ struct Traversal {
         bound = PYR_INF;
         if (mode == 1) bound = limit > 0.0f ? sqrtf(limit) : 0.0f;
         else if (mode == 2) bound = limit;
+        // (a visibility ray never takes a closest hit - it ends at its first occluder - so its `cull` is free to carry `bound`:
+        // one comparison per box serves both kinds of ray)
+        cull = bound;
         t = PYR_INF; u = 0; v = 0; rank = 0xFFFFFFFFu; kind = KIND_MISS;
         vn = 0; vl = 0; vf = 0; de_evals = 0; de_iters = 0; march_mask = 0;
         sp = 0; cur = 0; done = true;
@@ -830,6 +840,13 @@ struct Traversal {
         for (;;) {
             if (sp == 0) { done = true; return; }
             --sp;
+            if (Stack::FAST_DEPTH > 0 && sp < Stack::FAST_DEPTH) {  // the rest of the stack is in the fast region: a loop without the region test
+                for (;;) {
+                    if (!(stack.dist_fast(sp) > cull)) { cur = stack.code_fast(sp); return; }
+                    if (sp == 0) { done = true; return; }
+                    --sp;
+                }
+            }
             const float entry_dist = stack.dist(sp);
             if (!(entry_dist > cull)) { cur = stack.code(sp); return; }
         }
@@ -852,7 +869,7 @@ struct Traversal {
             // A box is skipped only when it starts beyond the closest hit by more than rounding: a leaf that ties with the
             // current hit (a ray through a shared edge) can have a box entry a few ulps beyond its own hit distance, and the
             // reference, walking in pre-order, would have tested it first (World::intersect's tie rule, world.rs:288-296).
-            h = h && code[k] != NODE4_EMPTY && !(dk > cull) && !(mode != 0 && dk > bound);
+            h = h && code[k] != NODE4_EMPTY && !(dk > cull);
             if (STATS) vn += code[k] != NODE4_EMPTY ? 1u : 0u;
             dist[k] = h ? dk : PYR_INF;
             if (!h) code[k] = NODE4_EMPTY;
@@ -863,6 +880,17 @@ struct Traversal {
                           const int ca = sw ? code[b] : code[a], cb = sw ? code[a] : code[b]; dist[a] = da; dist[b] = db; code[a] = ca; code[b] = cb; }
         PYR_CSWAP(0, 1) PYR_CSWAP(2, 3) PYR_CSWAP(0, 2) PYR_CSWAP(1, 3) PYR_CSWAP(1, 2)
 #undef PYR_CSWAP
+        if (Stack::FAST_DEPTH > 0 && sp + 4 <= Stack::FAST_DEPTH) {
+            // branch-free: every entry is stored, the stack pointer only moves past the real ones (misses sorted to the end, so what
+            // a skipped store leaves behind lies above the top); the last store puts the entry distance of `cur`'s box where
+            // leaf_step expects it
+            stack.put_fast(sp, code[3], dist[3]); sp += code[3] != NODE4_EMPTY ? 1 : 0;
+            stack.put_fast(sp, code[2], dist[2]); sp += code[2] != NODE4_EMPTY ? 1 : 0;
+            stack.put_fast(sp, code[1], dist[1]); sp += code[1] != NODE4_EMPTY ? 1 : 0;
+            stack.put_fast(sp, code[0], dist[0]);
+            if (code[0] != NODE4_EMPTY) cur = code[0]; else pop(stack);
+            return;
+        }
         if (code[3] != NODE4_EMPTY) stack.put(sp++, code[3], dist[3]);
         if (code[2] != NODE4_EMPTY) stack.put(sp++, code[2], dist[2]);
         if (code[1] != NODE4_EMPTY) stack.put(sp++, code[1], dist[1]);

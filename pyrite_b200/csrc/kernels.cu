@@ -402,6 +402,10 @@ __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MIN_BLOCKS) k_wave_simple(c
 constexpr int SHARED_STACK = PYR_SHARED_STACK;
 struct SharedStack {
     int2* entries;  // &smem[threadIdx.x]: (child code, entry distance bits), one 8-byte access per push / pop
+    static constexpr int FAST_DEPTH = SHARED_STACK;  // slots below it need no region test (Traversal::node_step / pop)
+    __device__ __forceinline__ void put_fast(int i, int code, float dist) { entries[i * TRACE_THREADS] = make_int2(code, __float_as_int(dist)); }
+    __device__ __forceinline__ int code_fast(int i) const { return entries[i * TRACE_THREADS].x; }
+    __device__ __forceinline__ float dist_fast(int i) const { return __int_as_float(entries[i * TRACE_THREADS].y); }
     int2 deep[BVH_STACK - SHARED_STACK];
     __device__ __forceinline__ void put(int i, int code, float dist) {
         const int2 e = make_int2(code, __float_as_int(dist));

@@ -49,14 +49,16 @@ def all_reduce_film(film: torch.Tensor, group=None) -> torch.Tensor:
     return film
 
 
-def init_film_comm(renderer, group=None) -> None:
+def init_film_comm(renderer, group=None, wait: bool = True) -> None:
     """Create the renderer's own NCCL communicator over the ranks of the (already initialised) torch.distributed group:
-    rank 0 draws the id (`pyr_comm_unique_id`), the object broadcast carries it, every rank calls `pyr_comm_init`."""
+    rank 0 draws the id (`pyr_comm_unique_id`), the object broadcast carries it, every rank calls `pyr_comm_init`.
+    `wait=False`: `pyr_comm_init_async` - the library sets the communicator up on its own thread and stream while the
+    caller renders (seconds on an 8-GPU box), and `film_reduce` waits for it."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     box = [type(renderer).comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(box, src=0, group=group)
-    renderer.comm_init(world, rank, box[0])
+    renderer.comm_init(world, rank, box[0], wait=wait)
     renderer._film_comm = True
 
 
@@ -69,7 +71,7 @@ def render_sharded(renderer, seed: int = 0, spp: int = 0, develop: bool = True, 
     rank = dist.get_rank() if dist.is_initialized() else 0
     offset, stride = shard_for_rank(rank, world)
     if world > 1 and not getattr(renderer, "_film_comm", False):
-        init_film_comm(renderer)
+        init_film_comm(renderer, wait=False)   # set up under the render
     renderer.render(seed=seed, spp=spp, sample_offset=offset, sample_stride=stride, **kw)
     if world > 1:
         renderer.film_reduce(0)
