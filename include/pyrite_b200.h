@@ -136,6 +136,10 @@ pyr_status pyr_trace_stats(pyr_ctx* ctx, const pyr_ray* rays, size_t n, pyr_hit*
 /* The flattened BVH's leaf pre-order (spatial/bvh.rs:250-275): object id of every leaf rank,
  * n_objects entries.  World::intersect's tie rule (earlier leaf wins, world.rs:288-296) is defined on it. */
 pyr_status pyr_bvh_leaf_order(pyr_ctx* ctx, uint32_t* object_ids_out);
+/* Test hook: out4[0] = 1 when the BVH of the loaded project was built on the GPU (bvh_build.cu; meshes of 16384 triangles or more,
+ * PYR_BVH_BUILD=host|gpu overrides), [1] a digest of the 4-wide nodes, [2] a digest of the leaf pre-order, [3] microseconds the
+ * last pyr_project_load took.  The GPU build and the host build of Bvh::new (spatial/bvh.rs:13-155) give the same digests. */
+pyr_status pyr_bvh_digest(pyr_ctx* ctx, uint64_t* out4);
 
 /* Renderer::render (renderer/mod.rs:77-111 -> simple.rs:17-141 / bidirectional.rs:31-308):
  * runs the wavefront pipeline into the context's film. */

@@ -32,7 +32,7 @@ RENDER_TIMING = 2
 
 EXPORTS = [
     "pyr_init", "pyr_shutdown", "pyr_stream_set", "pyr_last_error", "pyr_project_load", "pyr_project_info_get", "pyr_trace", "pyr_trace_device",
-    "pyr_trace_stats", "pyr_bvh_leaf_order", "pyr_render", "pyr_film_expose", "pyr_film_clear", "pyr_film_download", "pyr_film_upload",
+    "pyr_trace_stats", "pyr_bvh_leaf_order", "pyr_bvh_digest", "pyr_render", "pyr_film_expose", "pyr_film_clear", "pyr_film_download", "pyr_film_upload",
     "pyr_film_device_ptr", "pyr_comm_unique_id", "pyr_comm_init", "pyr_comm_init_async", "pyr_film_reduce", "pyr_comm_destroy", "pyr_film_develop", "pyr_camera_sample", "pyr_debug_path", "pyr_counters_get", "pyr_version",
 ]
 
@@ -97,6 +97,7 @@ def load_library(path: Optional[Path] = None):
     L.pyr_trace_stats.argtypes = [vp, vp, sz, vp]
     L.pyr_trace_device.argtypes = [vp, vp, sz, vp, C.c_uint32]
     L.pyr_bvh_leaf_order.argtypes = [vp, vp]
+    L.pyr_bvh_digest.argtypes = [vp, vp]
     L.pyr_render.argtypes = [vp, C.POINTER(RenderParams), PROGRESS_CB, vp]
     L.pyr_film_expose.argtypes = [vp, vp, vp, sz]
     L.pyr_film_clear.argtypes = [vp]
@@ -196,6 +197,13 @@ class Renderer:
         """Trace `n` rays resident at device address `d_rays`; returns the device seconds of all repeats."""
         self._check(self.L.pyr_trace_device(self.h, C.c_void_p(d_rays), n, C.c_void_p(d_hits), repeat))
         return self.counters()["render_seconds"]
+
+    def bvh_digest(self) -> dict:
+        """Test hook: whether the BVH was built on the GPU, digests of the 4-wide nodes and of the leaf pre-order, and the
+        seconds the last `load` took inside the library."""
+        out = (C.c_uint64 * 4)()
+        self._check(self.L.pyr_bvh_digest(self.h, out))
+        return {"built_on_gpu": bool(out[0]), "nodes": int(out[1]), "leaf_order": int(out[2]), "load_seconds": out[3] * 1e-6}
 
     def bvh_leaf_order(self) -> np.ndarray:
         out = np.empty(self.info.n_objects, dtype=np.uint32)

@@ -5,6 +5,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <exception>
@@ -137,6 +138,8 @@ struct pyr_ctx {
     std::vector<cudaEvent_t> timing_events;
     std::string error;
     bool loaded = false;
+    bool bvh_built_on_gpu = false;
+    double load_seconds = 0.0;  // IR decode + scene build + upload of the last pyr_project_load
     BakedScene scene;
     SceneView view{};
     DeviceBuffer nodes, prims, tri_shade, tri_frames, planes, marched, materials, components, programs, code, spectra, spectrum_data,
@@ -377,9 +380,20 @@ pyr_status pyr_stream_set(pyr_ctx* ctx, void* cuda_stream) {
 pyr_status pyr_project_load(pyr_ctx* ctx, const void* ir_blob, size_t bytes) {
     return guarded(ctx, [&] {
         if (!ir_blob) throw ir::BuildError("null project IR");
+        const auto t_load = std::chrono::steady_clock::now();
         ir::Document doc = ir::decode(ir_blob, bytes);
-        BakedScene baked = build_scene(doc);
         cudaStream_t s = ctx->stream;
+        // The BVH of a big scene is built on the GPU (bvh_build.cu: the reference's tree, level by level); small ones, where the
+        // launches would cost more than the work, on the host.  PYR_BVH_BUILD=host / gpu forces one of them.
+        const BvhBuildFn gpu_builder = [s](const float* boxes6, size_t n, const float* hull12, BvhTree& tree) { gpu_bvh_build(boxes6, n, hull12, tree, s); };
+        size_t n_bvh_items = 0;
+        for (const auto& o : doc.objects)
+            if (o.kind == ir::OBJ_MESH && o.mesh < doc.meshes.size())
+                for (const auto& part : doc.meshes[o.mesh].objects) n_bvh_items += part.corners.size() / 9;
+        bool on_gpu = n_bvh_items >= 16384;
+        if (const char* e = getenv("PYR_BVH_BUILD")) on_gpu = std::string(e) == "gpu";
+        BakedScene baked = build_scene(doc, on_gpu ? &gpu_builder : nullptr);
+        ctx->bvh_built_on_gpu = on_gpu && baked.n_objects >= 2;
         // From here on the old project's buffers are freed / overwritten in place: the context holds NO project until the
         // last upload has completed, so a failure half-way (out of device memory on a bigger scene) leaves it in the
         // "nothing loaded" state - the next pyr_render / pyr_trace / pyr_film_* returns PYR_ERR_STATE instead of touching
@@ -423,6 +437,7 @@ pyr_status pyr_project_load(pyr_ctx* ctx, const void* ir_blob, size_t bytes) {
         for (Lane& ln : ctx->lanes) ln.pool = 0;
         CU(cudaStreamSynchronize(s));
         ctx->loaded = true;
+        ctx->load_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_load).count();
     });
 }
 
@@ -926,6 +941,29 @@ pyr_status pyr_bvh_leaf_order(pyr_ctx* ctx, uint32_t* object_ids_out) {
         need_project(ctx);
         if (!object_ids_out && ctx->scene.n_objects) throw ir::BuildError("null output buffer");
         for (uint32_t obj = 0; obj < ctx->scene.n_objects; ++obj) object_ids_out[ctx->scene.rank_of_object[obj]] = obj;
+    });
+}
+
+// How the BVH of the loaded project was built, and a digest of it (test hook: the GPU build and the host build must agree)
+pyr_status pyr_bvh_digest(pyr_ctx* ctx, uint64_t* out4) {
+    return guarded(ctx, [&] {
+        need_project(ctx);
+        if (!out4) throw ir::BuildError("null output buffer");
+        auto fnv = [](uint64_t h, uint32_t w) { for (int i = 0; i < 4; ++i) { h ^= (w >> (8 * i)) & 0xffu; h *= 1099511628211ull; } return h; };
+        uint64_t h_nodes = 14695981039346656037ull, h_order = 14695981039346656037ull;
+        for (const Node4& nd : ctx->scene.nodes) {
+            uint32_t w[32];
+            memcpy(w, &nd, sizeof(w));
+            for (int i = 0; i < 24; ++i) if (w[i] == 0x80000000u) w[i] = 0;  // a box coordinate of -0 and one of +0 are the same box
+            for (int i = 0; i < 28; ++i) h_nodes = fnv(h_nodes, w[i]);
+        }
+        std::vector<uint32_t> order(ctx->scene.n_objects);
+        for (uint32_t obj = 0; obj < ctx->scene.n_objects; ++obj) order[ctx->scene.rank_of_object[obj]] = obj;
+        for (uint32_t o : order) h_order = fnv(h_order, o);
+        out4[0] = ctx->bvh_built_on_gpu ? 1 : 0;
+        out4[1] = h_nodes;
+        out4[2] = h_order;
+        out4[3] = (uint64_t)(ctx->load_seconds * 1e6);
     });
 }
 

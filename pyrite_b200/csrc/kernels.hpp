@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "bvh_build.hpp"
 #include "device_types.h"
 
 namespace pyr {
@@ -122,5 +123,8 @@ size_t light_vertex_bytes();
 size_t cam_vertex_bytes();
 int bdpt_stage_rays();
 int trace_blocks_per_sm();
+
+// bvh_build.cu: Bvh::new (spatial/bvh.rs:13-155) level by level on the GPU; the tree of the depth-first host builder.
+void gpu_bvh_build(const float* boxes6, size_t n, const float* root_hull12, BvhTree& out, cudaStream_t stream);
 
 }  // namespace pyr

@@ -478,7 +478,8 @@ struct TreeBuilder {
     const std::vector<Item>& items;
     BakedScene& out;
     std::vector<uint32_t> order;  // item index per rank
-    struct Interior { Box box[2]; int32_t child[2]; };
+    struct Interior { Box box[2]; int32_t child[2]; };  // same layout as BvhInterior (bvh_build.hpp): the GPU builder's records are taken as they are
+    static_assert(sizeof(Box) == 24, "Box is six floats");
     std::vector<Interior> interiors;
     int max_depth = 0;
 
@@ -706,7 +707,7 @@ struct BuildTimer {  // PYR_BUILD_TIMING=1: phase times of the scene build on st
 };
 }  // namespace
 
-BakedScene build_scene(const Document& input) {
+BakedScene build_scene(const Document& input, const BvhBuildFn* bvh_builder) {
     BuildTimer timer;
     Document doc = input;  // material flattening appends expression nodes
     timer.lap("copy of the document");
@@ -924,25 +925,56 @@ BakedScene build_scene(const Document& input) {
 
     timer.lap("materials, items, boxes");
     // ---- BVH + rank order
+    // the per-rank output arrays (100+ MB of fresh pages for a big mesh) are sized on a thread of their own while the tree is built
+    bool any_normal_map = false;
+    for (const auto& m : out.materials) any_normal_map = any_normal_map || m.normal_map_program >= 0;
+    struct Joiner { std::thread t; void join() { if (t.joinable()) t.join(); } ~Joiner() { join(); } };
+    bool sizing_failed = false;
+    Joiner sized{std::thread([&out, &sizing_failed, any_normal_map, n = items.size()] {
+        try {
+            out.rank_of_object.assign(n, 0);
+            out.prims.resize(n);
+            out.tri_shade.resize(n);
+            if (any_normal_map) out.tri_frames.resize(n);
+        } catch (...) { sizing_failed = true; }
+    })};
     TreeBuilder tb{items, out, {}, {}};
+    BvhTree gpu_tree;  // holds the interior records when `bvh_builder` made the tree (they are read where they are)
     if (!items.empty()) {
-        std::vector<uint32_t> all(items.size());
-        for (uint32_t i = 0; i < all.size(); ++i) all[i] = i;
         Hull2 hull = Hull2::around(items[0].box);
         for (const auto& it : items) hull = hull.plus(it.box);
-        sv.root = tb.run(std::move(all), hull);
+        if (bvh_builder && *bvh_builder && items.size() >= 2) {
+            // the level-synchronous build (bvh_build_core.hpp; on the GPU: bvh_build.cu) - the same tree as TreeBuilder's
+            std::vector<float> boxes(items.size() * 6);
+            parallel_ranges(items.size(), [&](size_t from, size_t to) {
+                for (size_t i = from; i < to; ++i) {
+                    const Box& b = items[i].box;
+                    float* v = &boxes[6 * i];
+                    v[0] = b.lo.x; v[1] = b.lo.y; v[2] = b.lo.z; v[3] = b.hi.x; v[4] = b.hi.y; v[5] = b.hi.z;
+                }
+            });
+            const float hull12[12] = {hull.all.lo.x, hull.all.lo.y, hull.all.lo.z, hull.all.hi.x, hull.all.hi.y, hull.all.hi.z,
+                                      hull.centres.lo.x, hull.centres.lo.y, hull.centres.lo.z, hull.centres.hi.x, hull.centres.hi.y, hull.centres.hi.z};
+            BvhTree tree;
+            (*bvh_builder)(boxes.data(), items.size(), hull12, tree);
+            if (tree.order.size() != items.size() || tree.n_interiors + 1 != items.size() || !tree.interiors) throw BuildError("the BVH builder returned a tree of the wrong size");
+            tb.order = std::move(tree.order);
+            gpu_tree = std::move(tree);
+            tb.max_depth = tree.max_depth;
+            sv.root = tree.root;
+        } else {
+            std::vector<uint32_t> all(items.size());
+            for (uint32_t i = 0; i < all.size(); ++i) all[i] = i;
+            sv.root = tb.run(std::move(all), hull);
+        }
         // the traversal defers at most one child per level
         if (tb.max_depth >= BVH_STACK) throw BuildError("the BVH is deeper than the traversal stack (" + std::to_string(tb.max_depth) + " levels)");
         out.bvh_depth = (uint32_t)tb.max_depth;
         sv.root_lo[0] = hull.all.lo.x; sv.root_lo[1] = hull.all.lo.y; sv.root_lo[2] = hull.all.lo.z;
         sv.root_hi[0] = hull.all.hi.x; sv.root_hi[1] = hull.all.hi.y; sv.root_hi[2] = hull.all.hi.z;
     }
-    out.rank_of_object.assign(items.size(), 0);
-    bool any_normal_map = false;
-    for (const auto& m : out.materials) any_normal_map = any_normal_map || m.normal_map_program >= 0;
-    out.prims.resize(items.size());
-    out.tri_shade.resize(items.size());
-    if (any_normal_map) out.tri_frames.resize(items.size());
+    sized.join();
+    if (sizing_failed) throw std::bad_alloc();
     timer.lap("BVH build");
     parallel_ranges(tb.order.size(), [&](size_t rank_from, size_t rank_to) {
     for (uint32_t rank = (uint32_t)rank_from; rank < (uint32_t)rank_to; ++rank) {
@@ -980,8 +1012,11 @@ BakedScene build_scene(const Document& input) {
     }
     });
     // fold the binary tree into 4-wide nodes: a Node4 per binary node that is the root or a grandchild-level entry
-    if (!tb.interiors.empty()) {
-        std::vector<int32_t> node4_of(tb.interiors.size(), -1);
+    static_assert(sizeof(TreeBuilder::Interior) == sizeof(BvhInterior) && sizeof(Box) == 24, "interior records of the two builders have one layout");
+    const size_t n_interiors = gpu_tree.interiors ? gpu_tree.n_interiors : tb.interiors.size();
+    const TreeBuilder::Interior* interiors = gpu_tree.interiors ? reinterpret_cast<const TreeBuilder::Interior*>(gpu_tree.interiors.get()) : tb.interiors.data();
+    if (n_interiors) {
+        std::vector<int32_t> node4_of(n_interiors, -1);
         std::vector<uint32_t> todo;  // binary interior indices that need a Node4
         auto node4_for = [&](uint32_t binary) {
             if (node4_of[binary] < 0) {
@@ -999,11 +1034,11 @@ BakedScene build_scene(const Document& input) {
             Entry entries[4];
             int n = 0;
             for (int side = 0; side < 2; ++side) {
-                const int32_t c = tb.interiors[b].child[side];
-                if (c < 0) { entries[n++] = Entry{c, tb.interiors[b].box[side]}; continue; }
+                const int32_t c = interiors[b].child[side];
+                if (c < 0) { entries[n++] = Entry{c, interiors[b].box[side]}; continue; }
                 for (int g = 0; g < 2; ++g) {
-                    const int32_t gc = tb.interiors[c].child[g];
-                    entries[n++] = Entry{gc < 0 ? gc : node4_for((uint32_t)gc), tb.interiors[c].box[g]};
+                    const int32_t gc = interiors[c].child[g];
+                    entries[n++] = Entry{gc < 0 ? gc : node4_for((uint32_t)gc), interiors[c].box[g]};
                 }
             }
             Node4 nd;

@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 
+#include "bvh_build.hpp"
 #include "device_types.h"
 #include "project_ir.hpp"
 
@@ -39,7 +40,9 @@ struct BakedScene {
 };
 
 // Throws ir::BuildError on a malformed project (missing mesh material, vector used as number...).
-BakedScene build_scene(const ir::Document& doc);
+// `bvh_builder`: who builds the BVH of two items or more (nullptr: the depth-first host builder in scene_build.cpp; the C ABI
+// passes the GPU build of bvh_build.cu - both make the same tree, tests/test_host_logic.py and tests/test_gpu_parity.py).
+BakedScene build_scene(const ir::Document& doc, const BvhBuildFn* bvh_builder = nullptr);
 
 // renderer/algorithm.rs:152-188 `make_tiles` + cameras.rs:57-68 `to_view_area` (row-major order;
 // the reference's centre-out sort only changes scheduling order).

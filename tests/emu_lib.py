@@ -36,6 +36,8 @@ def lib():
         L = C.CDLL(str(LIB))
         L.emu_last_error.restype = C.c_char_p
         L.emu_load.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+        L.emu_load_with.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]
+        L.emu_bvh_digest.argtypes = [C.c_void_p, C.c_void_p]
         L.emu_free.argtypes = [C.c_void_p]
         L.emu_info.argtypes = [C.c_void_p, C.c_void_p]
         L.emu_leaf_order.argtypes = [C.c_void_p, C.c_void_p]
@@ -63,17 +65,23 @@ class EmuError(RuntimeError):
 
 
 class Emu:
-    def __init__(self, ir: bytes, shape):
-        """shape = (height, width, bins) of the film (from the oracle's / product's project info)."""
+    def __init__(self, ir: bytes, shape, level_sync_bvh: bool = False):
+        """shape = (height, width, bins) of the film (from the oracle's / product's project info).  `level_sync_bvh`: build the BVH
+        with the level-synchronous algorithm of the GPU builder (bvh_build_core.hpp) instead of the depth-first host builder."""
         self.L = lib()
         self.h = C.c_void_p()
         buf = (C.c_char * len(ir)).from_buffer_copy(ir)
-        if self.L.emu_load(buf, len(ir), C.byref(self.h)) != 0:
+        if self.L.emu_load_with(buf, len(ir), 1 if level_sync_bvh else 0, C.byref(self.h)) != 0:
             raise EmuError(self.L.emu_last_error().decode())
         self.shape = tuple(shape)
         info = np.zeros(9, np.uint32)
         self.L.emu_info(self.h, _ptr(info))
         self.info = dict(zip(("n_objects", "n_planes", "n_lamps", "n_nodes", "n_materials", "n_programs", "n_instr", "n_tiles", "bvh_depth"), map(int, info)))
+
+    def bvh_digest(self):
+        out = np.zeros(2, np.uint64)
+        self.L.emu_bvh_digest(self.h, _ptr(out))
+        return int(out[0]), int(out[1])
 
     def __del__(self):
         try:

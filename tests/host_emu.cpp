@@ -3,11 +3,13 @@
 // that the host logic (IR decode, material flattening, bytecode compiler, BVH build, wavefront
 // state machine) can be checked against the oracle in the GPU-less container.  Not shipped and not
 // loaded by the product; built by tests/conftest.py into tests/_build/libhostemu.so.
+#include <algorithm>
 #include <cstring>
 #include <memory>
 #include <string>
 #include <vector>
 
+#include "../pyrite_b200/csrc/bvh_build_core.hpp"
 #include "../pyrite_b200/csrc/scene_build.hpp"
 #include "../pyrite_b200/csrc/bdpt.cuh"
 
@@ -22,6 +24,86 @@ struct Emu {
 };
 thread_local std::string g_error;
 
+// The level-synchronous BVH build of bvh_build_core.hpp, phase by phase like the kernels of bvh_build.cu (assign, split, rank,
+// scatter) but with plain loops: the same per-item / per-node functions the GPU runs, checked here against the depth-first builder.
+void level_sync_build(const float* boxes6, size_t n_items, const float* hull12, BvhTree& out) {
+    using namespace bvhb;
+    const uint32_t n = (uint32_t)n_items;
+    std::vector<uint32_t> ids(n), ids_next(n), node_of(n, 0u), node_next(n), rank_at(n, 0u), pre(n);
+    std::vector<uint8_t> bucket(n);
+    for (uint32_t i = 0; i < n; ++i) ids[i] = i;
+    std::vector<LevelNode> nodes(1), next;
+    nodes[0].start = 0; nodes[0].count = n; nodes[0].rank_base = 0; nodes[0].interior = 0;
+    for (int k = 0; k < 3; ++k) {
+        nodes[0].hull.lo[k] = hull12[k]; nodes[0].hull.hi[k] = hull12[3 + k];
+        nodes[0].hull.c_lo[k] = hull12[6 + k]; nodes[0].hull.c_hi[k] = hull12[9 + k];
+    }
+    out.allocate_interiors(n - 1);
+    int level = 0;
+    while (!nodes.empty()) {
+        std::vector<BucketStats> stats(nodes.size());
+        memset(stats.data(), 0, stats.size() * sizeof(BucketStats));
+        for (uint32_t p = 0; p < n; ++p) {  // k_bvh_assign
+            const uint32_t j = node_of[p];
+            if (j == NO_NODE) { bucket[p] = (uint8_t)BUCKET_NONE; continue; }
+            const float* box = boxes6 + 6 * (size_t)ids[p];
+            const uint32_t b = item_bucket(nodes[j], p, box);
+            uint32_t key[12];
+            item_keys(box, key);
+            bucket[p] = (uint8_t)b;
+            stats[j].count[b] += 1;
+            for (int k = 0; k < 12; ++k) stats[j].key[b][k] = std::max(stats[j].key[b][k], key[k]);
+        }
+        std::vector<Split> splits(nodes.size());
+        next.clear();
+        for (size_t j = 0; j < nodes.size(); ++j) {  // k_bvh_split
+            const LevelNode& nd = nodes[j];
+            const SplitChoice c = choose_split(nd, stats[j]);
+            Split& sp = splits[j];
+            for (int s = 0; s < BUCKETS; ++s) sp.offset[s] = c.offset[s];
+            sp.cut = c.cut;
+            if (c.n_a == 0 || c.n_b == 0) throw ir::BuildError("BVH split produced an empty side");
+            LevelNode a, b;
+            a.start = nd.start; a.count = c.n_a; a.rank_base = nd.rank_base + c.n_b; a.interior = nd.interior + c.n_b; a.hull = c.hull_a;
+            b.start = nd.start + c.n_a; b.count = c.n_b; b.rank_base = nd.rank_base; b.interior = nd.interior + 1; b.hull = c.hull_b;
+            BvhInterior in;
+            for (int k = 0; k < 3; ++k) {
+                in.box[0][k] = b.hull.lo[k]; in.box[0][3 + k] = b.hull.hi[k];
+                in.box[1][k] = a.hull.lo[k]; in.box[1][3 + k] = a.hull.hi[k];
+            }
+            in.child[0] = b.count == 1 ? ~(int32_t)b.rank_base : (int32_t)b.interior;
+            in.child[1] = a.count == 1 ? ~(int32_t)a.rank_base : (int32_t)a.interior;
+            out.interiors[nd.interior] = in;
+            sp.child[0] = sp.child[1] = NO_NODE;
+            if (a.count == 1) rank_at[a.start] = a.rank_base; else { sp.child[0] = (uint32_t)next.size(); next.push_back(a); }
+            if (b.count == 1) rank_at[b.start] = b.rank_base; else { sp.child[1] = (uint32_t)next.size(); next.push_back(b); }
+        }
+        uint32_t seen[BUCKETS] = {0, 0, 0, 0, 0, 0};  // k_bvh_tile_scan + k_bvh_rank: items of the same bucket at earlier positions
+        std::vector<uint32_t> node_prefix(nodes.size() * 8, 0u);
+        for (uint32_t p = 0; p < n; ++p) {
+            const uint32_t b = bucket[p];
+            if (b == BUCKET_NONE) continue;
+            const uint32_t j = node_of[p];
+            if (nodes[j].start == p) for (int k = 0; k < BUCKETS; ++k) node_prefix[j * 8 + k] = seen[k];
+            pre[p] = seen[b]++;
+        }
+        for (uint32_t p = 0; p < n; ++p) {  // k_bvh_scatter
+            const uint32_t b = bucket[p];
+            if (b == BUCKET_NONE) { ids_next[p] = ids[p]; node_next[p] = NO_NODE; continue; }
+            const uint32_t j = node_of[p];
+            const uint32_t to = nodes[j].start + splits[j].offset[b] + (pre[p] - node_prefix[j * 8 + b]);
+            ids_next[to] = ids[p];
+            node_next[to] = splits[j].child[b < splits[j].cut ? 0 : 1];
+        }
+        ids.swap(ids_next); node_of.swap(node_next); nodes.swap(next);
+        ++level;
+    }
+    out.order.resize(n);
+    for (uint32_t p = 0; p < n; ++p) out.order[rank_at[p]] = ids[p];
+    out.root = 0;
+    out.max_depth = level;
+}
+
 struct HostAdd {
     float* film;
     void operator()(uint64_t index, float increment, float weight) const { film[2 * index] += increment; film[2 * index + 1] += weight; }
@@ -32,10 +114,31 @@ extern "C" {
 
 const char* emu_last_error() { return g_error.c_str(); }
 
-int emu_load(const void* ir_blob, size_t bytes, void** out) {
+// A digest of the built BVH (4-wide nodes with -0 box coordinates read as +0, leaf order), as pyr_bvh_digest computes it
+void emu_bvh_digest(void* h, uint64_t* out2) {
+    Emu* e = (Emu*)h;
+    auto fnv = [](uint64_t x, uint32_t w) { for (int i = 0; i < 4; ++i) { x ^= (w >> (8 * i)) & 0xffu; x *= 1099511628211ull; } return x; };
+    uint64_t h_nodes = 14695981039346656037ull, h_order = 14695981039346656037ull;
+    for (const Node4& nd : e->scene.nodes) {
+        uint32_t w[32];
+        memcpy(w, &nd, sizeof(w));
+        for (int i = 0; i < 24; ++i) if (w[i] == 0x80000000u) w[i] = 0;
+        for (int i = 0; i < 28; ++i) h_nodes = fnv(h_nodes, w[i]);
+    }
+    std::vector<uint32_t> order(e->scene.n_objects);
+    for (uint32_t obj = 0; obj < e->scene.n_objects; ++obj) order[e->scene.rank_of_object[obj]] = obj;
+    for (uint32_t o : order) h_order = fnv(h_order, o);
+    out2[0] = h_nodes; out2[1] = h_order;
+}
+
+int emu_load_with(const void* ir_blob, size_t bytes, int level_sync_bvh, void** out);
+int emu_load(const void* ir_blob, size_t bytes, void** out) { return emu_load_with(ir_blob, bytes, 0, out); }
+// level_sync_bvh != 0: the BVH comes from the level-synchronous build (the algorithm of the GPU builder) instead of the depth-first one
+int emu_load_with(const void* ir_blob, size_t bytes, int level_sync_bvh, void** out) {
     try {
         auto e = std::make_unique<Emu>();
-        e->scene = build_scene(ir::decode(ir_blob, bytes));
+        const BvhBuildFn level_sync = level_sync_build;
+        e->scene = build_scene(ir::decode(ir_blob, bytes), level_sync_bvh ? &level_sync : nullptr);
         BakedScene& b = e->scene;
         SceneView v = b.view;
         v.nodes = b.nodes.data(); v.prims = b.prims.data(); v.tri_shade = b.tri_shade.data(); v.tri_frames = b.tri_frames.data();

@@ -19,6 +19,7 @@ Bars (BASELINE.json north_star / SURVEY.md §8d):
 Every observed number is also written to gpurun_out/parity_gpu.json (copied to profiles/parity_r2.json).
 """
 import json
+import os
 from pathlib import Path
 
 import numpy as np
@@ -647,3 +648,58 @@ def test_a_march_to_infinity_is_a_miss(gpu_renderer_factory, oracle_factory):
     r.render(seed=4242, spp=8)
     o.render(seed=4242, spp=8)
     assert (~np.isfinite(r.film())).sum() <= (~np.isfinite(o.film())).sum()
+
+
+def _load_both_ways(ir):
+    """The same project loaded with the host BVH builder and with the GPU one: (digest, leaf order) of each."""
+    from pyrite_b200 import api
+
+    got = {}
+    old = os.environ.get("PYR_BVH_BUILD")
+    try:
+        for how in ("host", "gpu"):
+            os.environ["PYR_BVH_BUILD"] = how
+            with api.Renderer(0) as r:
+                r.load(ir)
+                r.load(ir)   # the second load is the one timed: the first pays for the library's lazily loaded kernels
+                got[how] = (r.bvh_digest(), r.bvh_leaf_order())
+    finally:
+        if old is None:
+            os.environ.pop("PYR_BVH_BUILD", None)
+        else:
+            os.environ["PYR_BVH_BUILD"] = old
+    return got
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["spheres", "cornell", "diamonds", "snowflake", "dragon", "coinciding"])
+def test_gpu_bvh_build_is_the_host_tree(name):
+    """bvh_build.cu builds Bvh::new's tree (spatial/bvh.rs:13-155) level by level on the GPU: identical 4-wide nodes and leaf
+    pre-order to the depth-first host builder (which tests/test_host_logic.py holds against the oracle's)."""
+    from test_host_logic import _coinciding_centres_scene
+
+    from pyrite_b200 import project as P
+
+    ir = P.serialize_project(_coinciding_centres_scene()) if name == "coinciding" else scene_ir(name)
+    got = _load_both_ways(ir)
+    (dh, oh), (dg, og) = got["host"], got["gpu"]
+    assert not dh["built_on_gpu"] and dg["built_on_gpu"]
+    assert np.array_equal(oh, og)
+    assert dh["nodes"] == dg["nodes"] and dh["leaf_order"] == dg["leaf_order"]
+
+
+@pytest.mark.gpu
+def test_gpu_bvh_build_at_full_size():
+    """Config C5's scene (871,236 items, depth 28): same tree from both builders, and the default load builds it on the GPU."""
+    from pyrite_b200 import api, project, scenes
+
+    ir = project.serialize_project(scenes.bdpt_cornell_dragon())
+    got = _load_both_ways(ir)
+    (dh, oh), (dg, og) = got["host"], got["gpu"]
+    print(f"C5 scene load: host BVH build {dh['load_seconds']:.3f} s, GPU BVH build {dg['load_seconds']:.3f} s")
+    RECORD["bvh_build"] = ({"items": int(len(oh)), "load_seconds_host_bvh": dh["load_seconds"], "load_seconds_gpu_bvh": dg["load_seconds"]})
+    assert np.array_equal(oh, og)
+    assert dh["nodes"] == dg["nodes"] and dh["leaf_order"] == dg["leaf_order"]
+    with api.Renderer(0) as r:
+        r.load(ir)
+        assert r.bvh_digest()["built_on_gpu"]

@@ -272,3 +272,44 @@ def test_a_march_to_infinity_is_a_miss(emu_factory):
     got, _ = emu.trace(rays)
     assert want["kind"][0] == got["kind"][0] and np.array_equal(want["prim_id"], got["prim_id"])
     assert want["kind"][0] == 0 or np.isfinite(want["t"][0])
+
+
+def _coinciding_centres_scene():
+    """Spheres that share a centre (their boxes' centres coincide: Bvh::new halves such groups by position, bvh.rs:66-88),
+    some of them several times over, next to ordinary ones."""
+    from pyrite_b200.project import camera, material, renderer, shape, transform, vector
+
+    objs = []
+    for k in range(7):
+        objs.append(shape.sphere(radius=0.5 + 0.1 * k, position=vector(0, 1, 5), material={"surface": material.diffuse(color=0.5)}))
+    for k in range(5):
+        objs.append(shape.sphere(radius=0.3, position=vector(-2 + k, 0.3, 4 + 0.5 * k), material={"surface": material.diffuse(color=0.8)}))
+    objs += [shape.sphere(radius=0.2, position=vector(2, 2, 6), material={"surface": material.emissive(color=3)})] * 3
+    return {"image": {"width": 32, "height": 32},
+            "camera": camera.perspective(fov=50, transform=transform.look_at(**{"from": vector(0, 1, 0), "to": vector(0, 1, 1)})),
+            "renderer": renderer.simple(pixel_samples=2, spectrum_samples=4, spectrum_bins=10, tile_size=16, light_samples=1),
+            "world": {"objects": objs}}
+
+
+@pytest.mark.parametrize("name", SCENE_NAMES + ["coinciding"])
+def test_level_synchronous_bvh_build_is_the_depth_first_tree(name):
+    """The GPU builds the BVH level by level (pyrite_b200/csrc/bvh_build_core.hpp, run by the kernels of bvh_build.cu); the same
+    functions, run level by level on the CPU, must give the tree of the depth-first builder that mirrors Bvh::new
+    (spatial/bvh.rs:13-155): identical 4-wide nodes and identical leaf pre-order."""
+    from emu_lib import Emu
+
+    ir = P.serialize_project(_coinciding_centres_scene()) if name == "coinciding" else scene_ir(name)
+    a, b = Emu(ir, (8, 8, 1)), Emu(ir, (8, 8, 1), level_sync_bvh=True)
+    assert a.info == b.info
+    assert np.array_equal(a.leaf_order(), b.leaf_order())
+    assert a.bvh_digest() == b.bvh_digest()
+
+
+def test_level_synchronous_bvh_build_on_a_big_mesh():
+    from emu_lib import Emu
+    from pyrite_b200 import scenes
+
+    ir = P.serialize_project(scenes.dragon(width=64, height=48, spp=1, mesh=scenes.dragon_mesh(1500, 48)))   # 144,000 triangles
+    a, b = Emu(ir, (8, 8, 1)), Emu(ir, (8, 8, 1), level_sync_bvh=True)
+    assert a.info["n_objects"] == 144000 and a.info == b.info
+    assert a.bvh_digest() == b.bvh_digest()
