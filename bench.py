@@ -524,8 +524,9 @@ def run_product(args):
         ref_bytes_per_ray = (REF_RAY_IO + ref_nodes * REF_NODE_BYTES + ref_leaves * REF_TRI_BYTES) if ref_nodes is not None else None
         bytes_per_ray = ref_bytes_per_ray if ref_bytes_per_ray is not None else own_bytes_per_ray
         achieved = rays_per_launch * bytes_per_ray / max(launch_s, 1e-12) / 1e9
-        t_dram = traffic.get("k_trace")
-        t_l2 = traffic.get("k_trace_l2_bytes")
+        # measured DRAM / L2 bytes per ray of a whole profiled render (tools/summarize_ncu.py --traffic), scaled to this run's launches
+        t_dram = traffic["k_trace_dram_bytes_per_ray"] * rays_per_launch if "k_trace_dram_bytes_per_ray" in traffic else traffic.get("k_trace")
+        t_l2 = traffic["k_trace_l2_bytes_per_ray"] * rays_per_launch if "k_trace_l2_bytes_per_ray" in traffic else traffic.get("k_trace_l2_bytes")
         trace = {
             "bound": "hbm", "kernel": "k_trace", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": t_dram,
             "peak_source": hbm_src, "bytes_per_ray": bytes_per_ray,
@@ -551,7 +552,8 @@ def run_product(args):
         shadow = c["rays"] - c["path_rays"]
         shade_bytes = path_iterations * 2 * core_bytes + c["path_rays"] * (32 + 32 + 32) + shadow * (4 + 32 + 64) + c["path_samples"] * S * 8
         shade_achieved = shade_bytes / max(shade_s, 1e-12) / 1e9
-        t_shade = traffic.get("k_wave_simple")
+        t_shade = (traffic["shade_dram_bytes_per_path_iteration"] * path_iterations / shade_n if "shade_dram_bytes_per_path_iteration" in traffic
+                   else traffic.get("k_wave_simple"))
         shade = {"bound": "hbm", "kernel": "k_bin_* + k_wave_simple", "achieved": shade_achieved, "peak": hbm, "unit": "GB/s", "frac": shade_achieved / hbm,
                  "traffic": t_shade, "peak_source": hbm_src, "bytes_per_path_iteration": shade_bytes / max(path_iterations, 1),
                  "dram_frac": (t_shade / max(shade_s / shade_n, 1e-12) / 1e9 / hbm) if t_shade else None,

@@ -28,5 +28,9 @@ with api.Renderer(0) as r:
     timing = os.environ.get('PYR_TIMING', '1') != '0'   # per-kernel timing runs ONE wavefront; PYR_TIMING=0 measures the production path
     secs = r.render(seed=1, spp=spp, timing=timing, pool_paths=pool)
     c = r.counters()
+    if os.environ.get("PYR_COUNTS_JSON"):
+        import json
+        Path(os.environ["PYR_COUNTS_JSON"]).write_text(json.dumps({"scene": scene, "spp": spp, "rays": c["rays"], "path_rays": c["path_rays"], "path_samples": c["path_samples"],
+                                                                   "iterations": c["wavefront_iterations"]}) + "\n")
     print(f"{scene}: {spp} spp in {secs * 1e3:.1f} ms, {c['rays'] / secs / 1e6:.0f} Mrays/s, trace {c['trace_seconds'] * 1e3:.1f} ms shade {c['shade_seconds'] * 1e3:.1f} ms, "
           f"{c['wavefront_iterations']} iterations")
