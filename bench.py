@@ -575,8 +575,9 @@ def run_product(args):
         if rank == 0:
             strong["sharding_check_on_small_C2"] = check.get("sharding_check")
             strong["note"] = ("a FIXED job split over the ranks, timed from the IR in host memory to the developed image on rank 0; the per-rank fixed costs "
-                              "(replicated host BVH build in load_build_upload, communicator set-up) do not shrink with N, so a job this short scales worse "
-                              "than the 1024-spp target (profiles/ holds that run)")
+                              "(scene build and upload in load_build_upload, develop) do not shrink with N, so a job a quarter of the target's length scales a "
+                              "little worse than the 1024-spp target itself (profiles/ holds that run); the communicator is set up under the render "
+                              "(pyr_comm_init_async), film_reduce includes whatever wait for it is left")
 
     if rank == 0:
         line = {
@@ -608,7 +609,7 @@ def main():
     ap.add_argument("--config", default=None, choices=sorted(CONFIGS), help="run ONE fixed job of this BASELINE config (strong scaling) instead of the C2 step benchmark")
     ap.add_argument("--spp", type=int, default=0, help="--config: total sample passes of the fixed job (0 = the config's own: C3 200, C4 512, C5 1024)")
     ap.add_argument("--spp-per-step", type=int, default=32, help="sample passes per GPU per step (8 steps of 32 = the 256-spp C2 job)")
-    ap.add_argument("--strong-spp", type=int, default=32, help="sample passes of the small fixed C5 job reported under strong_scaling (0 = skip)")
+    ap.add_argument("--strong-spp", type=int, default=256, help="sample passes of the fixed C5 job reported under strong_scaling: a quarter of the 1024-spp target (0 = skip)")
     ap.add_argument("--pool", type=int, default=0, help="paths in flight (0 = library default)")
     ap.add_argument("--cpu-fraction", type=int, default=1, help="the CPU legs render every N-th path sample of a pass")
     ap.add_argument("--cpu-spp", type=int, default=4, help="sample passes of the cpu_baseline leg (4 passes = about 15 s on 16 cores)")

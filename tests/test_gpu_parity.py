@@ -672,15 +672,20 @@ def _load_both_ways(ir):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["spheres", "cornell", "diamonds", "snowflake", "dragon", "coinciding"])
+@pytest.mark.parametrize("name", ["spheres", "cornell", "diamonds", "snowflake", "dragon", "coinciding", "random0", "random1", "random2", "random3"])
 def test_gpu_bvh_build_is_the_host_tree(name):
     """bvh_build.cu builds Bvh::new's tree (spatial/bvh.rs:13-155) level by level on the GPU: identical 4-wide nodes and leaf
     pre-order to the depth-first host builder (which tests/test_host_logic.py holds against the oracle's)."""
-    from test_host_logic import _coinciding_centres_scene
+    from test_host_logic import _coinciding_centres_scene, _random_sphere_project
 
     from pyrite_b200 import project as P
 
-    ir = P.serialize_project(_coinciding_centres_scene()) if name == "coinciding" else scene_ir(name)
+    if name == "coinciding":
+        ir = P.serialize_project(_coinciding_centres_scene())
+    elif name.startswith("random"):
+        ir = P.serialize_project(_random_sphere_project(int(name[6:]))[1])
+    else:
+        ir = scene_ir(name)
     got = _load_both_ways(ir)
     (dh, oh), (dg, og) = got["host"], got["gpu"]
     assert not dh["built_on_gpu"] and dg["built_on_gpu"]

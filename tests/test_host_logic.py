@@ -313,3 +313,34 @@ def test_level_synchronous_bvh_build_on_a_big_mesh():
     a, b = Emu(ir, (8, 8, 1)), Emu(ir, (8, 8, 1), level_sync_bvh=True)
     assert a.info["n_objects"] == 144000 and a.info == b.info
     assert a.bvh_digest() == b.bvh_digest()
+
+
+def _random_sphere_project(seed):
+    """Spheres drawn from a coarse grid: many coinciding centres (groups halved by position, bvh.rs:66-88), duplicates, empty buckets,
+    groups of two and three."""
+    from pyrite_b200.project import camera, material, renderer, shape, transform, vector
+
+    rng = np.random.default_rng(100 + seed)
+    n = int(rng.integers(2, 400))
+    grid = int(rng.integers(1, 6))
+    objs = []
+    for _ in range(n):
+        x, y, z = (float(v) for v in rng.integers(0, grid, 3) * 0.5)
+        objs.append(shape.sphere(radius=float(rng.choice([0.1, 0.25, 0.4])), position=vector(x, y, z + 4), material={"surface": material.diffuse(color=0.5)}))
+    return n, {"image": {"width": 16, "height": 16},
+               "camera": camera.perspective(fov=50, transform=transform.look_at(**{"from": vector(0, 1, 0), "to": vector(0, 1, 1)})),
+               "renderer": renderer.simple(pixel_samples=1, spectrum_samples=2, spectrum_bins=4, tile_size=16, light_samples=0),
+               "world": {"objects": objs}}
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_level_synchronous_bvh_build_on_random_item_sets(seed):
+    """On random item sets with many ties the level-synchronous build must still be the depth-first tree."""
+    from emu_lib import Emu
+
+    n, proj = _random_sphere_project(seed)
+    ir = P.serialize_project(proj)
+    a, b = Emu(ir, (8, 8, 1)), Emu(ir, (8, 8, 1), level_sync_bvh=True)
+    assert a.info == b.info and a.info["n_objects"] == n
+    assert np.array_equal(a.leaf_order(), b.leaf_order())
+    assert a.bvh_digest() == b.bvh_digest()

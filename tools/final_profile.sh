@@ -18,6 +18,6 @@ PYR_COUNTS_JSON=$out/${tag}_c2_traffic_counts.json ncu --metrics dram__bytes_rea
 ncu --set full --clock-control none --import-source on -k regex:"k_trace|k_wave_simple|k_bin_keys|k_bin_scatter" -s 12 -c 4 -o $out/${tag}_c2 -f python tools/profile_step.py 8 dragon > $out/${tag}_c2_ncu3.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"k_trace|k_wave_bd" -s 28 -c 7 -o $out/${tag}_c5 -f python tools/profile_step.py 2 bdpt_cornell_dragon > $out/${tag}_c5_ncu3.log 2>&1
 # the GPU BVH build (load of config C5's scene)
-PYR_BVH_BUILD=gpu ncu --set full --clock-control none --import-source on -k regex:"k_bvh" -s 10 -c 5 -o $out/${tag}_bvh -f python tools/load_timing.py bdpt_cornell_dragon gpu > $out/${tag}_bvh_ncu.log 2>&1
+PYR_BVH_BUILD=gpu ncu --set full --clock-control none --import-source on -k regex:"k_bvh" -s 61 -c 5 -o $out/${tag}_bvh -f python tools/load_timing.py bdpt_cornell_dragon gpu > $out/${tag}_bvh_ncu.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_bvh" -c 200 --csv --log-file $out/${tag}_bvh_launches.csv python tools/load_timing.py bdpt_cornell_dragon gpu > $out/${tag}_bvh_ncu1.log 2>&1
 ls -la $out/${tag}_*
