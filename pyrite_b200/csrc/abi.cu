@@ -88,7 +88,7 @@ struct DeviceBuffer {
     template <class T> T* as() const { return (T*)p; }
 };
 
-template <class T> void upload(DeviceBuffer& b, const std::vector<T>& v, cudaStream_t s) {
+template <class T, class A> void upload(DeviceBuffer& b, const std::vector<T, A>& v, cudaStream_t s) {
     b.ensure(v.size() * sizeof(T));
     if (!v.empty()) CU(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
 }

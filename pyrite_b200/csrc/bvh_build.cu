@@ -301,6 +301,11 @@ void gpu_bvh_build(const float* boxes6, size_t n_items, const float* root_hull12
     lap("download");
     out.root = 0;
     out.max_depth = level;
+    if (timing) {
+        cudaFree(s.base);
+        s.base = nullptr;
+        lap("release");
+    }
 }
 
 }  // namespace pyr

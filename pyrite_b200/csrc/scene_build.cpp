@@ -475,7 +475,7 @@ struct Hull2 {
 };
 
 struct TreeBuilder {
-    const std::vector<Item>& items;
+    const RawVector<Item>& items;
     BakedScene& out;
     std::vector<uint32_t> order;  // item index per rank
     struct Interior { Box box[2]; int32_t child[2]; };  // same layout as BvhInterior (bvh_build.hpp): the GPU builder's records are taken as they are
@@ -800,7 +800,7 @@ BakedScene build_scene(const Document& input, const BvhBuildFn* bvh_builder) {
     sv.white_program = doc.white.some ? compile_program(doc, out, doc.white.ex, false, ALLOW_SPECTRUM_ONLY) : -1;
 
     // ---- world (world.rs:39-271)
-    std::vector<Item> items;
+    RawVector<Item> items;  // (resize() leaves new entries to the threads that fill them)
     struct LampSeed { bool from_item; uint32_t item; LampRec rec; };
     std::vector<LampSeed> lamp_seeds;
     const std::vector<ir::SceneObject> objects = doc.objects;
@@ -925,24 +925,23 @@ BakedScene build_scene(const Document& input, const BvhBuildFn* bvh_builder) {
 
     timer.lap("materials, items, boxes");
     // ---- BVH + rank order
-    // the per-rank output arrays (100+ MB of fresh pages for a big mesh) are sized on a thread of their own while the tree is built
     bool any_normal_map = false;
     for (const auto& m : out.materials) any_normal_map = any_normal_map || m.normal_map_program >= 0;
-    struct Joiner { std::thread t; void join() { if (t.joinable()) t.join(); } ~Joiner() { join(); } };
-    bool sizing_failed = false;
-    Joiner sized{std::thread([&out, &sizing_failed, any_normal_map, n = items.size()] {
-        try {
-            out.rank_of_object.assign(n, 0);
-            out.prims.resize(n);
-            out.tri_shade.resize(n);
-            if (any_normal_map) out.tri_frames.resize(n);
-        } catch (...) { sizing_failed = true; }
-    })};
     TreeBuilder tb{items, out, {}, {}};
     BvhTree gpu_tree;  // holds the interior records when `bvh_builder` made the tree (they are read where they are)
     if (!items.empty()) {
+        // the hull of all items: minima and maxima, so partial hulls of ranges combine exactly
         Hull2 hull = Hull2::around(items[0].box);
-        for (const auto& it : items) hull = hull.plus(it.box);
+        {
+            std::mutex hull_mutex;
+            parallel_ranges(items.size(), [&](size_t from, size_t to) {
+                if (from >= to) return;
+                Hull2 part = Hull2::around(items[from].box);
+                for (size_t i = from; i < to; ++i) part = part.plus(items[i].box);
+                std::lock_guard<std::mutex> g(hull_mutex);
+                hull = hull.joined(part);
+            });
+        }
         if (bvh_builder && *bvh_builder && items.size() >= 2) {
             // the level-synchronous build (bvh_build_core.hpp; on the GPU: bvh_build.cu) - the same tree as TreeBuilder's
             std::vector<float> boxes(items.size() * 6);
@@ -955,8 +954,10 @@ BakedScene build_scene(const Document& input, const BvhBuildFn* bvh_builder) {
             });
             const float hull12[12] = {hull.all.lo.x, hull.all.lo.y, hull.all.lo.z, hull.all.hi.x, hull.all.hi.y, hull.all.hi.z,
                                       hull.centres.lo.x, hull.centres.lo.y, hull.centres.lo.z, hull.centres.hi.x, hull.centres.hi.y, hull.centres.hi.z};
+            timer.lap("  hull + box array");
             BvhTree tree;
             (*bvh_builder)(boxes.data(), items.size(), hull12, tree);
+            timer.lap("  builder");
             if (tree.order.size() != items.size() || tree.n_interiors + 1 != items.size() || !tree.interiors) throw BuildError("the BVH builder returned a tree of the wrong size");
             tb.order = std::move(tree.order);
             gpu_tree = std::move(tree);
@@ -973,8 +974,11 @@ BakedScene build_scene(const Document& input, const BvhBuildFn* bvh_builder) {
         sv.root_lo[0] = hull.all.lo.x; sv.root_lo[1] = hull.all.lo.y; sv.root_lo[2] = hull.all.lo.z;
         sv.root_hi[0] = hull.all.hi.x; sv.root_hi[1] = hull.all.hi.y; sv.root_hi[2] = hull.all.hi.z;
     }
-    sized.join();
-    if (sizing_failed) throw std::bad_alloc();
+    // per-rank outputs: sized without zero-filling (RawVector), every record is written in full by the parallel loop below
+    out.rank_of_object.assign(items.size(), 0);
+    out.prims.resize(items.size());
+    out.tri_shade.resize(items.size());
+    if (any_normal_map) out.tri_frames.resize(items.size());
     timer.lap("BVH build");
     parallel_ranges(tb.order.size(), [&](size_t rank_from, size_t rank_to) {
     for (uint32_t rank = (uint32_t)rank_from; rank < (uint32_t)rank_to; ++rank) {

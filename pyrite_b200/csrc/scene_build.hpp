@@ -5,7 +5,10 @@
 // ProgramCompiler::compile (program/compiler.rs:48-586) and Bvh::new (spatial/bvh.rs:13-155).
 // It runs once per project on the host; nothing in it is on the per-sample path.
 #pragma once
+#include <memory>
 #include <string>
+#include <type_traits>
+#include <utility>
 #include <vector>
 
 #include "bvh_build.hpp"
@@ -14,11 +17,25 @@
 
 namespace pyr {
 
+// std::vector whose resize() does not zero-fill trivial records: the per-primitive arrays of a big mesh (hundreds of MB) are written
+// in full by several threads right after they are sized, and those threads - not one zero-filling thread - should touch the pages first.
+template <class T> struct DefaultInitAllocator : std::allocator<T> {
+    template <class U> struct rebind { using other = DefaultInitAllocator<U>; };
+    using std::allocator<T>::allocator;
+    // (records of plain floats / integers with default member initialisers are not "trivial" for the language, but nothing reads an
+    // entry before the filling loop has assigned it: such entries are not constructed at all)
+    template <class U> void construct(U* p) noexcept {
+        if constexpr (!(std::is_trivially_copyable<U>::value && std::is_trivially_destructible<U>::value)) ::new (static_cast<void*>(p)) U;
+    }
+    template <class U, class... Args> void construct(U* p, Args&&... args) { ::new (static_cast<void*>(p)) U(std::forward<Args>(args)...); }
+};
+template <class T> using RawVector = std::vector<T, DefaultInitAllocator<T>>;
+
 struct BakedScene {
     std::vector<Node4> nodes;
-    std::vector<Prim> prims;            // leaf pre-order ("rank")
-    std::vector<TriShade> tri_shade;    // by rank
-    std::vector<TriFrames> tri_frames;  // by rank; empty unless some material has a normal map
+    RawVector<Prim> prims;            // leaf pre-order ("rank")
+    RawVector<TriShade> tri_shade;    // by rank
+    RawVector<TriFrames> tri_frames;  // by rank; empty unless some material has a normal map
     std::vector<PlaneRec> planes;
     std::vector<MarchedRec> marched;
     std::vector<MaterialRec> materials;
