@@ -148,7 +148,7 @@ struct pyr_ctx {
     Lane lanes[MAX_LANES];
     cudaEvent_t ev_fork = nullptr;
     uint32_t shadow_per_path = 1;
-    DeviceBuffer scratch_a, scratch_b;
+    DeviceBuffer scratch_a, scratch_b, bvh_scratch;
     bool develop_params_valid = false;
     pyr_counters host_counters{};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -353,7 +353,7 @@ void pyr_shutdown(pyr_ctx* ctx) {
     DeviceBuffer* all[] = {&ctx->nodes, &ctx->prims, &ctx->tri_shade, &ctx->tri_frames, &ctx->planes, &ctx->marched, &ctx->materials,
                            &ctx->components, &ctx->programs, &ctx->code, &ctx->spectra, &ctx->spectrum_data, &ctx->textures, &ctx->texels,
                            &ctx->lamps, &ctx->tiles, &ctx->burns, &ctx->xyz, &ctx->d65, &ctx->film, &ctx->develop_params, &ctx->counters,
-                           &ctx->scalars, &ctx->tile_first, &ctx->scratch_a, &ctx->scratch_b};
+                           &ctx->scalars, &ctx->tile_first, &ctx->scratch_a, &ctx->scratch_b, &ctx->bvh_scratch};
     for (Lane& ln : ctx->lanes) {
         ln.release();
         if (ln.pinned) cudaFreeHost(ln.pinned);
@@ -385,7 +385,10 @@ pyr_status pyr_project_load(pyr_ctx* ctx, const void* ir_blob, size_t bytes) {
         cudaStream_t s = ctx->stream;
         // The BVH of a big scene is built on the GPU (bvh_build.cu: the reference's tree, level by level); small ones, where the
         // launches would cost more than the work, on the host.  PYR_BVH_BUILD=host / gpu forces one of them.
-        const BvhBuildFn gpu_builder = [s](const float* boxes6, size_t n, const float* hull12, BvhTree& tree) { gpu_bvh_build(boxes6, n, hull12, tree, s); };
+        // (its scratch block stays with the context for the next load: releasing it cost 30 - 240 ms of cudaFree)
+        const BvhBuildFn gpu_builder = [s, ctx](const float* boxes6, size_t n, const float* hull12, BvhTree& tree) {
+            gpu_bvh_build(boxes6, n, hull12, tree, s, [ctx](size_t bytes) { ctx->bvh_scratch.ensure(bytes); return ctx->bvh_scratch.p; });
+        };
         size_t n_bvh_items = 0;
         for (const auto& o : doc.objects)
             if (o.kind == ir::OBJ_MESH && o.mesh < doc.meshes.size())

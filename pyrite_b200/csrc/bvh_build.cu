@@ -201,27 +201,20 @@ __global__ void k_bvh_init(uint32_t* ids, uint32_t* node_of_pos, uint32_t n) {
     if (p < n) { ids[p] = p; node_of_pos[p] = 0u; }
 }
 
-struct Scratch {  // one device allocation, carved up; released on every way out
+struct Scratch {  // one device block from the caller (kept by the context: cudaFree of it cost 30 - 240 ms on a B200), carved up
     char* base = nullptr;
-    size_t used = 0, capacity = 0;
+    size_t used = 0;
     template <class T> size_t plan(size_t elements) {  // first pass: sizes -> offsets
         const size_t at = used;
         used += (elements * sizeof(T) + 255) / 256 * 256;
         return at;
     }
-    void allocate() {
-        capacity = used;
-        void* p = nullptr;
-        BV(cudaMalloc(&p, capacity));
-        base = static_cast<char*>(p);
-    }
     template <class T> T* at(size_t offset) const { return reinterpret_cast<T*>(base + offset); }
-    ~Scratch() { if (base) cudaFree(base); }
 };
 
 }  // namespace
 
-void gpu_bvh_build(const float* boxes6, size_t n_items, const float* root_hull12, BvhTree& out, cudaStream_t stream) {
+void gpu_bvh_build(const float* boxes6, size_t n_items, const float* root_hull12, BvhTree& out, cudaStream_t stream, const std::function<void*(size_t)>& device_scratch) {
     if (n_items < 2) throw std::runtime_error("GPU BVH build: needs at least two items");
     if (n_items > 0x7fffffffull) throw ir::BuildError("too many BVH items");
     const bool timing = getenv("PYR_BUILD_TIMING") != nullptr;
@@ -241,7 +234,8 @@ void gpu_bvh_build(const float* boxes6, size_t n_items, const float* root_hull12
     const size_t o_nodes0 = s.plan<LevelNode>(node_cap), o_nodes1 = s.plan<LevelNode>(node_cap), o_stats = s.plan<BucketStats>(node_cap);
     const size_t o_splits = s.plan<Split>(node_cap), o_node_prefix = s.plan<uint32_t>(node_cap * 8), o_tile_hist = s.plan<uint32_t>((size_t)tiles * 8);
     const size_t o_interiors = s.plan<BvhInterior>((size_t)n - 1), o_flags = s.plan<uint32_t>(4);
-    s.allocate();
+    s.base = static_cast<char*>(device_scratch(s.used));
+    if (!s.base) throw std::runtime_error("GPU BVH build: no scratch memory");
     Box6* d_boxes = s.at<Box6>(o_boxes);
     uint32_t* d_ids[2] = {s.at<uint32_t>(o_ids0), s.at<uint32_t>(o_ids1)};
     uint32_t* d_node[2] = {s.at<uint32_t>(o_node0), s.at<uint32_t>(o_node1)};
@@ -301,11 +295,6 @@ void gpu_bvh_build(const float* boxes6, size_t n_items, const float* root_hull12
     lap("download");
     out.root = 0;
     out.max_depth = level;
-    if (timing) {
-        cudaFree(s.base);
-        s.base = nullptr;
-        lap("release");
-    }
 }
 
 }  // namespace pyr

@@ -125,6 +125,7 @@ int bdpt_stage_rays();
 int trace_blocks_per_sm();
 
 // bvh_build.cu: Bvh::new (spatial/bvh.rs:13-155) level by level on the GPU; the tree of the depth-first host builder.
-void gpu_bvh_build(const float* boxes6, size_t n, const float* root_hull12, BvhTree& out, cudaStream_t stream);
+// `device_scratch(bytes)` returns a device block of that size that stays valid for the call (about 350 bytes per item).
+void gpu_bvh_build(const float* boxes6, size_t n, const float* root_hull12, BvhTree& out, cudaStream_t stream, const std::function<void*(size_t)>& device_scratch);
 
 }  // namespace pyr

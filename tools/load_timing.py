@@ -11,6 +11,6 @@ ir = project.serialize_project(scenes.SCENES[sys.argv[1] if len(sys.argv) > 1 el
 for how in (sys.argv[2:] or ["gpu", "host"]):
     os.environ["PYR_BVH_BUILD"] = how
     with api.Renderer(0) as r:
-        for k in range(3):
+        for k in range(int(os.environ.get("PYR_LOADS", "3"))):
             t = time.time(); r.load(ir); dt = time.time() - t
             print(f"{how} BVH build, load {k}: {dt:.3f} s (inside the library {r.bvh_digest()['load_seconds']:.3f} s)", flush=True)
