@@ -36,7 +36,17 @@ def parity_record():
     yield RECORD
     out = ROOT / "gpurun_out"
     out.mkdir(exist_ok=True)
-    (out / "parity_gpu.json").write_text(json.dumps(RECORD, indent=1, sort_keys=True) + "\n")
+    merged = {}
+    try:  # a partial run (-k ...) adds to what a full run recorded instead of replacing it
+        merged = json.loads((out / "parity_gpu.json").read_text())
+    except (OSError, ValueError):
+        pass
+    for key, value in RECORD.items():
+        if isinstance(value, dict) and isinstance(merged.get(key), dict):
+            merged[key].update(value)
+        else:
+            merged[key] = value
+    (out / "parity_gpu.json").write_text(json.dumps(merged, indent=1, sort_keys=True, default=float) + "\n")
 
 
 def film_triplet(name, xg, xo, xd):
