@@ -6,10 +6,12 @@
 #include <nccl.h>
 
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstring>
 #include <exception>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -158,6 +160,13 @@ struct pyr_ctx {
     // (ncclCommInitRank + NCCL's connection set-up at the first collective take seconds on an 8-GPU box).  Everything that
     // uses `comm` joins the thread first (comm_wait).
     std::thread comm_thread;
+    // The thread starts its NCCL calls when the gate opens: pyr_render opens it once its buffers are allocated and its first
+    // wavefront iterations are queued (ncclCommInitRank and a render's start-up allocations block each other in the driver: on an
+    // 8-GPU box the render started 1.7 s late with the set-up running from the beginning), anything that needs the communicator
+    // opens it at once, and it opens by itself after 5 s.
+    std::mutex comm_gate_mutex;
+    std::condition_variable comm_gate_cv;
+    bool comm_gate_open = true;
     std::string comm_error;       // written by the thread, read after the join
     cudaStream_t comm_stream = nullptr;
     DeviceBuffer comm_scratch;
@@ -193,6 +202,11 @@ template <class F> pyr_status guarded(pyr_ctx* ctx, F&& body) {
     } catch (const std::exception& e) {
         return fail(ctx, PYR_ERR_INVALID, e.what());
     }
+}
+
+void open_comm_gate(pyr_ctx* ctx) {
+    { std::lock_guard<std::mutex> g(ctx->comm_gate_mutex); ctx->comm_gate_open = true; }
+    ctx->comm_gate_cv.notify_all();
 }
 
 void need_project(pyr_ctx* ctx) {
@@ -346,6 +360,7 @@ void pyr_shutdown(pyr_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    open_comm_gate(ctx);
     if (ctx->comm_thread.joinable()) ctx->comm_thread.join();
     if (ctx->comm) { try { nccl().CommDestroy(ctx->comm); } catch (...) {} ctx->comm = nullptr; }
     if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
@@ -650,6 +665,7 @@ pyr_status pyr_render(pyr_ctx* ctx, const pyr_render_params* params, pyr_progres
         };
 
         for (int l = 0; l < n_lanes; ++l) enqueue_batch(ctx->lanes[l]);
+        open_comm_gate(ctx);   // a communicator waiting to be set up (pyr_comm_init_async) starts now, under the queued iterations
         bool cancelled = false;
         unsigned long long started = 0;
         int active = n_lanes;
@@ -772,6 +788,7 @@ pyr_status pyr_comm_unique_id(uint8_t* id_out) {
 namespace {
 // Joins the communicator set-up started by pyr_comm_init_async and reports its failure, if any.
 void comm_wait(pyr_ctx* ctx) {
+    open_comm_gate(ctx);
     if (ctx->comm_thread.joinable()) ctx->comm_thread.join();
     if (!ctx->comm_error.empty()) {
         const std::string e = ctx->comm_error;
@@ -796,8 +813,17 @@ pyr_status pyr_comm_init_async(pyr_ctx* ctx, int32_t n_ranks, int32_t rank, cons
         CU(cudaStreamSynchronize(ctx->comm_stream));
         ctx->comm_ranks = n_ranks;
         ctx->comm_rank = rank;
+        {
+            const char* e = getenv("PYR_COMM_GATE");   // PYR_COMM_GATE=0: start the set-up at once (A/B)
+            std::lock_guard<std::mutex> g(ctx->comm_gate_mutex);
+            ctx->comm_gate_open = e && atoi(e) == 0;
+        }
         ctx->comm_thread = std::thread([ctx, uid, n_ranks, rank] {
             try {
+                {
+                    std::unique_lock<std::mutex> lk(ctx->comm_gate_mutex);
+                    ctx->comm_gate_cv.wait_for(lk, std::chrono::seconds(5), [ctx] { return ctx->comm_gate_open; });
+                }
                 CU(cudaSetDevice(ctx->device));
                 NC(nccl().CommInitRank(&ctx->comm, n_ranks, uid, rank));
                 // NCCL connects the ranks at the first collective: do that here, on a few bytes and on a stream that no render
