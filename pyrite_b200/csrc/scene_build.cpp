@@ -1015,17 +1015,22 @@ BakedScene build_scene(const Document& input, const BvhBuildFn* bvh_builder) {
         out.tri_shade[rank] = ts;
     }
     });
+    timer.lap("primitive records");
     // fold the binary tree into 4-wide nodes: a Node4 per binary node that is the root or a grandchild-level entry
     static_assert(sizeof(TreeBuilder::Interior) == sizeof(BvhInterior) && sizeof(Box) == 24, "interior records of the two builders have one layout");
     const size_t n_interiors = gpu_tree.interiors ? gpu_tree.n_interiors : tb.interiors.size();
     const TreeBuilder::Interior* interiors = gpu_tree.interiors ? reinterpret_cast<const TreeBuilder::Interior*>(gpu_tree.interiors.get()) : tb.interiors.data();
     if (n_interiors) {
+        // 1. which binary nodes become Node4s and under which index: a sequential walk (the numbering is the order of discovery, which is
+        //    the nodes' order in memory), touching child codes only
         std::vector<int32_t> node4_of(n_interiors, -1);
-        std::vector<uint32_t> todo;  // binary interior indices that need a Node4
+        std::vector<uint32_t> todo;      // binary interior indices whose Node4 is still to be walked
+        std::vector<uint32_t> binary_of; // Node4 index -> binary interior index
+        binary_of.reserve(n_interiors / 2 + 1);
         auto node4_for = [&](uint32_t binary) {
             if (node4_of[binary] < 0) {
-                node4_of[binary] = (int32_t)out.nodes.size();
-                out.nodes.emplace_back();
+                node4_of[binary] = (int32_t)binary_of.size();
+                binary_of.push_back(binary);
                 todo.push_back(binary);
             }
             return node4_of[binary];
@@ -1034,37 +1039,52 @@ BakedScene build_scene(const Document& input, const BvhBuildFn* bvh_builder) {
         while (!todo.empty()) {
             const uint32_t b = todo.back();
             todo.pop_back();
-            struct Entry { int32_t code; Box box; };
-            Entry entries[4];
-            int n = 0;
             for (int side = 0; side < 2; ++side) {
                 const int32_t c = interiors[b].child[side];
-                if (c < 0) { entries[n++] = Entry{c, interiors[b].box[side]}; continue; }
+                if (c < 0) continue;
                 for (int g = 0; g < 2; ++g) {
                     const int32_t gc = interiors[c].child[g];
-                    entries[n++] = Entry{gc < 0 ? gc : node4_for((uint32_t)gc), interiors[c].box[g]};
+                    if (gc >= 0) node4_for((uint32_t)gc);
                 }
             }
-            Node4 nd;
-            memset(&nd, 0, sizeof(nd));
-            const float inf = std::numeric_limits<float>::infinity();
-            float* comps[6] = {&nd.lo_x.x, &nd.lo_y.x, &nd.lo_z.x, &nd.hi_x.x, &nd.hi_y.x, &nd.hi_z.x};
-            for (int k = 0; k < 4; ++k) {
-                if (k < n) {
-                    const Box& bx = entries[k].box;
-                    const float v[6] = {bx.lo.x, bx.lo.y, bx.lo.z, bx.hi.x, bx.hi.y, bx.hi.z};
-                    for (int c = 0; c < 6; ++c) comps[c][k] = v[c];
-                    nd.child[k] = entries[k].code;
-                } else {
-                    for (int c = 0; c < 6; ++c) comps[c][k] = c < 3 ? inf : -inf;  // an empty slot can never be hit
-                    nd.child[k] = NODE4_EMPTY;
-                }
-            }
-            out.nodes[node4_of[b]] = nd;
         }
+        // 2. the records: every Node4 is a function of its binary node, its children and the numbering - filled by several threads
+        out.nodes.resize(binary_of.size());
+        parallel_ranges(binary_of.size(), [&](size_t from, size_t to) {
+            for (size_t at = from; at < to; ++at) {
+                const uint32_t b = binary_of[at];
+                struct Entry { int32_t code; Box box; };
+                Entry entries[4];
+                int n = 0;
+                for (int side = 0; side < 2; ++side) {
+                    const int32_t c = interiors[b].child[side];
+                    if (c < 0) { entries[n++] = Entry{c, interiors[b].box[side]}; continue; }
+                    for (int g = 0; g < 2; ++g) {
+                        const int32_t gc = interiors[c].child[g];
+                        entries[n++] = Entry{gc < 0 ? gc : node4_of[gc], interiors[c].box[g]};
+                    }
+                }
+                Node4 nd;
+                memset(&nd, 0, sizeof(nd));
+                const float inf = std::numeric_limits<float>::infinity();
+                float* comps[6] = {&nd.lo_x.x, &nd.lo_y.x, &nd.lo_z.x, &nd.hi_x.x, &nd.hi_y.x, &nd.hi_z.x};
+                for (int k = 0; k < 4; ++k) {
+                    if (k < n) {
+                        const Box& bx = entries[k].box;
+                        const float v[6] = {bx.lo.x, bx.lo.y, bx.lo.z, bx.hi.x, bx.hi.y, bx.hi.z};
+                        for (int c = 0; c < 6; ++c) comps[c][k] = v[c];
+                        nd.child[k] = entries[k].code;
+                    } else {
+                        for (int c = 0; c < 6; ++c) comps[c][k] = c < 3 ? inf : -inf;  // (an empty slot is recognised by its child code)
+                        nd.child[k] = NODE4_EMPTY;
+                    }
+                }
+                out.nodes[at] = nd;
+            }
+        });
     }
 
-    timer.lap("primitive records + Node4 fold");
+    timer.lap("Node4 fold");
     // ---- lamps, in the order the reference collects them (world.rs:75-83, 250-262)
     for (const auto& seed : lamp_seeds) {
         LampRec l = seed.rec;

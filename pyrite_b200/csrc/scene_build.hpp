@@ -32,7 +32,7 @@ template <class T> struct DefaultInitAllocator : std::allocator<T> {
 template <class T> using RawVector = std::vector<T, DefaultInitAllocator<T>>;
 
 struct BakedScene {
-    std::vector<Node4> nodes;
+    RawVector<Node4> nodes;
     RawVector<Prim> prims;            // leaf pre-order ("rank")
     RawVector<TriShade> tri_shade;    // by rank
     RawVector<TriFrames> tri_frames;  // by rank; empty unless some material has a normal map
