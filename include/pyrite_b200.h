@@ -164,7 +164,10 @@ pyr_status pyr_film_device_ptr(pyr_ctx* ctx, void** d_ptr, size_t* bytes);
  *   pyr_comm_init       every rank, collectively (ncclCommInitRank on the context's device)
  *   pyr_comm_init_async the same, but returns at once: the communicator is set up on a thread and a stream of the library's
  *                       own while the host goes on to pyr_render (on an 8-GPU box the set-up takes ~3 s, a sixth of the
- *                       1024-spp target job); pyr_film_reduce / pyr_comm_destroy wait for it and report its failure
+ *                       1024-spp target job); pyr_film_reduce / pyr_comm_destroy wait for it and report its failure.  The
+ *                       set-up and a render's start-up allocations block each other in the driver, so the thread begins its
+ *                       NCCL calls when the next pyr_render has allocated its buffers and queued its first iterations (or when
+ *                       something needs the communicator, or after 5 s; PYR_COMM_GATE=0: at once)
  *   pyr_film_reduce     every rank, collectively: film := sum over ranks, on `root` (root < 0: on every rank)
  * NCCL (libnccl.so.2) is bound when the first of these is called; without it they fail with PYR_ERR_STATE. */
 #define PYR_COMM_ID_BYTES 128
