@@ -73,3 +73,69 @@ def test_shard_plan_partitions_every_tile():
             assert sum(samples_of_shard(iterations, *shard_for_rank(r, world)) for r in range(world)) == iterations
     with pytest.raises(ValueError):
         shard_for_rank(2, 2)
+
+
+class _RecordingRenderer:
+    """Stands in for api.Renderer in the host-logic test below: records what the plumbing calls, in order."""
+    ids_drawn = 0
+
+    def __init__(self):
+        self.calls = []
+
+    @staticmethod
+    def comm_unique_id():
+        _RecordingRenderer.ids_drawn += 1
+        return bytes([7] * 64 + [os.getpid() % 251] * 64)
+
+    def comm_init(self, n_ranks, rank, comm_id, wait=True):
+        self.calls.append(("comm_init", n_ranks, rank, bytes(comm_id), wait))
+
+    def render(self, **kw):
+        self.calls.append(("render", kw["sample_offset"], kw["sample_stride"], kw["seed"], kw["spp"]))
+
+    def film_reduce(self, root):
+        self.calls.append(("film_reduce", root))
+
+    def develop(self):
+        self.calls.append(("develop",))
+        return "xyz", "srgb"
+
+
+def _plumbing_worker(rank, world, port, out_dir):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import json
+
+    from pyrite_b200.distributed import render_sharded
+
+    r = _RecordingRenderer()
+    first = render_sharded(r, seed=5, spp=8)
+    second = render_sharded(r, seed=6, spp=8, develop=False)   # the communicator exists now: no second set-up
+    calls = [[c[0]] + [x.hex() if isinstance(x, bytes) else x for x in c[1:]] for c in r.calls]
+    (Path(out_dir) / f"calls{rank}.json").write_text(json.dumps({"calls": calls, "ids_drawn": _RecordingRenderer.ids_drawn,
+                                                                  "first": list(first), "second": list(second)}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_render_sharded_plumbing_on_two_ranks(tmp_path):
+    """`render_sharded` on two gloo ranks with a recording renderer: rank 0 draws ONE communicator id, both ranks hand the same 128 bytes
+    to `comm_init` without waiting for the set-up (`pyr_comm_init_async`: it runs under the render), every rank renders its own sample
+    passes, the reduce comes after the render and only rank 0 develops."""
+    import json
+
+    world = 2
+    mp.spawn(_plumbing_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    got = [json.loads((tmp_path / f"calls{r}.json").read_text()) for r in range(world)]
+    assert got[0]["ids_drawn"] == 1 and got[1]["ids_drawn"] == 0
+    ids = set()
+    for rank, g in enumerate(got):
+        names = [c[0] for c in g["calls"]]
+        assert names == (["comm_init", "render", "film_reduce"] + (["develop"] if rank == 0 else []) + ["render", "film_reduce"]), names
+        init = g["calls"][0]
+        assert init[1] == world and init[2] == rank and init[4] is False and len(bytes.fromhex(init[3])) == 128
+        ids.add(init[3])
+        assert g["calls"][1][1:] == [rank, world, 5, 8]
+        assert g["first"] == (["xyz", "srgb"] if rank == 0 else [None, None]) and g["second"] == [None, None]
+    assert len(ids) == 1
