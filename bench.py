@@ -11,7 +11,8 @@ A ray = one World::intersect call, a path sample = one render_tile iteration.
     python bench.py --impl reference --steps 3 --warmup 1    # CPU arm: the oracle port on the host cores
     python bench.py --config C5 --spp 64                     # a FIXED job (strong scaling): load -> render -> reduce -> develop
 
-Every run also measures a small fixed C5 job (4K bidirectional, `--strong-spp` sample passes split over the ranks) and
+Every run also measures a fixed C5 job (4K bidirectional, `--strong-spp` = 256 sample passes, a quarter of the 1024-spp target, split
+over the ranks) and
 reports it under "strong_scaling", so that the 1/2/4/8-GPU sweep of the default command carries strong-scaling numbers
 next to the weak-scaling headline.  Prints ONE JSON line (rank 0).  DESIGN.md §8 defines every field.
 """
