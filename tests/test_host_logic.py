@@ -344,3 +344,22 @@ def test_level_synchronous_bvh_build_on_random_item_sets(seed):
     assert a.info == b.info and a.info["n_objects"] == n
     assert np.array_equal(a.leaf_order(), b.leaf_order())
     assert a.bvh_digest() == b.bvh_digest()
+
+
+@pytest.mark.parametrize("n,same", [(2, False), (2, True), (3, True), (64, True), (65, True)])
+def test_level_synchronous_bvh_build_on_tiny_and_degenerate_sets(n, same):
+    """Two items (one split), and sets whose centres ALL coincide (every level halves by position, bvh.rs:66-88)."""
+    from emu_lib import Emu
+    from pyrite_b200.project import camera, material, renderer, shape, transform, vector
+
+    objs = [shape.sphere(radius=0.2 + (0.0 if same else 0.1 * k), position=vector(0 if same else k, 1, 5), material={"surface": material.diffuse(color=0.5)})
+            for k in range(n)]
+    proj = {"image": {"width": 16, "height": 16},
+            "camera": camera.perspective(fov=50, transform=transform.look_at(**{"from": vector(0, 1, 0), "to": vector(0, 1, 1)})),
+            "renderer": renderer.simple(pixel_samples=1, spectrum_samples=2, spectrum_bins=4, tile_size=16, light_samples=0),
+            "world": {"objects": objs}}
+    ir = P.serialize_project(proj)
+    a, b = Emu(ir, (8, 8, 1)), Emu(ir, (8, 8, 1), level_sync_bvh=True)
+    assert a.info == b.info and a.info["n_objects"] == n
+    assert np.array_equal(a.leaf_order(), b.leaf_order())
+    assert a.bvh_digest() == b.bvh_digest()
